@@ -1,0 +1,228 @@
+/*
+ * ingvio_b200.h -- C-ABI of the B200-native (sm_100a CUDA) invariant-EKF hot path of InGVIO.
+ *
+ * The reference (ChangwuLiu/InGVIO, /root/reference) has no FFI: its seam is the C++ class API
+ *   State{_cov,_err_variables} (private, friend StateManager)   ingvio_estimator/src/State.h:72-136
+ *   StateManager static methods                                 ingvio_estimator/src/StateManager.h:33-128
+ *   UpdateBase and the *Update classes                          ingvio_estimator/src/Update.h:36-97
+ * This header is what a maintainer binds from inside those method bodies (INTEGRATION.md shows the
+ * stubs). Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - One opaque handle = a BATCH of B independent filters ("sequences") that share one variable
+ *     layout (same variables in the same order) and live on one device. B = 1 is the drop-in case
+ *     for the single-filter reference. Calls on one handle must be serialised by the caller
+ *     (the reference is single-threaded: ingvio_estimator/src/IngvioNode.cpp:36); handles are
+ *     independent.
+ *   - All floating point data is FP64 (the reference computes in double everywhere).
+ *   - Matrices are COLUMN-MAJOR (Eigen default) unless a parameter says otherwise; 3x3 rotations
+ *     in the state mirror are ROW-MAJOR 9-vectors.
+ *   - Bulk array arguments carry a leading batch dimension: element [b][...] at ptr + b*stride,
+ *     with the per-sequence stride equal to the stated per-sequence size. They are HOST pointers in
+ *     IGV_PTR_HOST mode (default; copied H2D on the handle's stream) or DEVICE pointers in
+ *     IGV_PTR_DEVICE mode (consumed in place). Small index/shape arguments are always host values.
+ *   - Every function returns an igv_status; nothing ever calls exit() (the reference's
+ *     std::exit paths, e.g. StateManager.cpp:157-161, become IGV_ERR_STATE).
+ *   - Work is enqueued on the handle's CUDA stream; igv_synchronize() or any *_get call waits.
+ */
+#ifndef INGVIO_B200_H
+#define INGVIO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct igv_batch igv_batch;
+
+typedef enum {
+  IGV_OK = 0,
+  IGV_ERR_INVALID = 1,   /* bad argument / shape                                                */
+  IGV_ERR_CUDA = 2,      /* CUDA runtime error (see igv_last_error)                             */
+  IGV_ERR_STATE = 3,     /* operation not valid for the current variable layout                 */
+  IGV_ERR_CAPACITY = 4   /* would exceed max_dim / max_clones / max_feats / max_sats / max_rows  */
+} igv_status;
+
+enum { IGV_PTR_HOST = 0, IGV_PTR_DEVICE = 1 };
+
+/* State::GNSSType (State.h:75) */
+enum { IGV_GNSS_GPS = 0, IGV_GNSS_GLO = 1, IGV_GNSS_GAL = 2, IGV_GNSS_BDS = 3, IGV_GNSS_FS = 4, IGV_GNSS_YOF = 5 };
+
+/* measurement-noise argument kinds of igv_ekf_update / igv_chi2_whiten */
+enum { IGV_R_ISO = 0,   /* R = sigma^2 I, R points to ONE double per sequence: sigma^2          */
+       IGV_R_DIAG = 1,  /* R = diag(r), R points to `rows` doubles per sequence                 */
+       IGV_R_FULL = 2   /* dense rows x rows, column-major                                      */ };
+
+/* visual-update flavours (which reference updater the call reproduces) */
+enum { IGV_VIS_ALL_OBS = 0,   /* RemoveLostUpdate: every observation inside the window          */
+       IGV_VIS_SELECTED = 1   /* KeyframeUpdate / SwMargUpdate: observations at selected clones  */ };
+
+/* per-sequence status bits (igv_get_flags) */
+enum { IGV_FLAG_NEG_DIAG = 1,      /* negative covariance diagonal after an update (StateManager.cpp:413-421) */
+       IGV_FLAG_CHOL_FAIL = 2,     /* innovation covariance not positive definite; update skipped            */
+       IGV_FLAG_GNSS_REJECTED = 4  /* joint chi^2 "strong reject" fired (GnssUpdate.cpp:286-287)             */ };
+
+typedef struct {
+  int batch;        /* B >= 1                                                                    */
+  int max_dim;      /* largest state dimension N (leading dimension of the covariance)           */
+  int max_clones;   /* sliding-window capacity                                                   */
+  int max_feats;    /* most tracks per visual update                                             */
+  int max_sats;     /* most satellites per GNSS epoch                                            */
+  int stereo;       /* 0: 2 rows per observation, 1: 4 rows (left + right camera)                */
+  int device;       /* CUDA device ordinal                                                       */
+  void* stream;     /* cudaStream_t to enqueue on, or NULL for a stream owned by the handle      */
+} igv_config;
+
+/* StateParams (State.h:36-70) + gravity (ImuPropagator.h) */
+typedef struct {
+  double noise_g, noise_a, noise_bg, noise_ba;   /* State.cpp:39-42                              */
+  double noise_clockbias, noise_cb_rw;           /* as StateParams holds them AFTER State.cpp:51-52 */
+  double gravity[3];                             /* world gravity vector, e.g. {0,0,-9.8}        */
+  double T_cl2cr_R[9];                           /* row-major; left->right camera (State.cpp:33)  */
+  double T_cl2cr_p[3];
+} igv_params;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+igv_status igv_create(const igv_config* cfg, igv_batch** out);
+igv_status igv_destroy(igv_batch* h);
+const char* igv_last_error(const igv_batch* h);
+igv_status igv_set_pointer_mode(igv_batch* h, int mode);
+igv_status igv_synchronize(igv_batch* h);
+long long igv_launch_count(const igv_batch* h);          /* kernels launched so far on this handle */
+igv_status igv_set_params(igv_batch* h, const igv_params* p);
+/* chi^2 quantile table: table[d-1] = quantile(d), d = 1..max_dof.  Replaces
+ * UpdateBase::setChiSquaredTable (Update.cpp:27-34, boost::math::quantile). */
+igv_status igv_set_chi2_table(igv_batch* h, const double* table, int max_dof);
+
+/* ---- state: variables and mean --------------------------------------------------------------
+ * State::State + State::initStateAndCov (State.cpp:60-91,126-167): variables SE23@0, bg@9, ba@12,
+ * cam-IMU extrinsics@15 (N = 21); covariance = diag(cov_diag[21]).
+ * R_* are row-major 3x3; every array is per sequence (B x ...), cov_diag is shared (21). */
+igv_status igv_state_init(igv_batch* h, const double* R_i2w, const double* p, const double* v,
+                          const double* bg, const double* ba, const double* R_ext, const double* p_ext,
+                          const double* cov_diag21);
+int igv_dim(const igv_batch* h);          /* State::curr_cov_size()            State.h:108 */
+int igv_num_variables(const igv_batch* h);/* State::curr_err_variable_size()   State.h:109 */
+int igv_num_clones(const igv_batch* h);
+int igv_clone_idx(const igv_batch* h, int slot);   /* Type::idx() of the slot-th oldest clone, -1 if none */
+int igv_gnss_idx(const igv_batch* h, int gtype);   /* Type::idx() of a GNSS scalar, -1 if absent          */
+/* Packed mean per sequence, doubles:
+ *  [0:9) R_i2w  [9:12) p  [12:15) v  [15:18) bg  [18:21) ba  [21:30) R_ext  [30:33) p_ext
+ *  [33:39) gnss values (GPS,GLO,GAL,BDS,FS,YOF; 0 if absent)
+ *  [39 + 12*s ...) clone s: R_c2w (9), p (3)        -> igv_state_size() doubles in total          */
+int igv_state_size(const igv_batch* h);
+igv_status igv_state_get(igv_batch* h, double* dst);
+igv_status igv_state_set(igv_batch* h, const double* src);
+
+/* ---- covariance lifecycle (StateManager.cpp:121-242) ---------------------------------------- */
+igv_status igv_cov_get(igv_batch* h, double* dst, int ld);         /* getFullCov; B x (ld*N)       */
+igv_status igv_cov_set(igv_batch* h, const double* src, int ld);   /* also checkpoint restore      */
+/* getMarginalCov (StateManager.cpp:128-153): dst is B x (n x n), n = sum(size) */
+igv_status igv_cov_get_blocks(igv_batch* h, int n_blocks, const int* idx, const int* size, double* dst);
+/* addGNSSVariable / margGNSSVariable (StateManager.cpp:216-242). value: B doubles. */
+igv_status igv_add_gnss_variable(igv_batch* h, int gtype, const double* value, double cov);
+igv_status igv_marg_gnss_variable(igv_batch* h, int gtype);
+/* addVariableIndependent (StateManager.cpp:194-214) for an opaque variable (no mean mirror);
+ * cov_block is size x size column-major, shared by all sequences. */
+igv_status igv_add_variable_independent(igv_batch* h, int size, const double* cov_block);
+/* marginalize (StateManager.cpp:155-192) of the variable that starts at `idx`. */
+igv_status igv_marginalize(igv_batch* h, int idx);
+/* margSlidingWindowPose (StateManager.cpp:316-338): slot 0 is the oldest clone. */
+igv_status igv_marginalize_clone(igv_batch* h, int slot);
+
+/* ---- propagation ---------------------------------------------------------------------------- */
+/* StateManager::propagateStateCov (StateManager.cpp:42-119). Phi: B x 225 (15x15 col-major),
+ * G: B x 180 (15x12 col-major), dt: B. Covariance only (the caller owns the mean). */
+igv_status igv_propagate_cov(igv_batch* h, const double* Phi, const double* G, const double* dt);
+/* ImuPropagator::propagateUntil loop body x n_steps (ImuPropagator.cpp:98-162 analytic branch +
+ * :260-271 + StateManager.cpp:42-119), on the device mean mirror: gyro/accel: B x n_steps x 3 (raw,
+ * biases are subtracted on device), dt: B x n_steps (steps with dt < 1e-6 are skipped, :262). */
+igv_status igv_propagate_imu(igv_batch* h, int n_steps, const double* gyro, const double* accel,
+                             const double* dt);
+/* StateManager::augmentSlidingWindowPose (StateManager.cpp:253-296) from the device mean mirror. */
+igv_status igv_augment_clone(igv_batch* h);
+/* Same, covariance only, rotation supplied by the caller (J depends on R_i2w only, :279-282).
+ * R_i2w: B x 9 row-major. The clone mean in the mirror is set from clone_R/clone_p if non-NULL. */
+igv_status igv_augment_clone_cov(igv_batch* h, const double* R_i2w, const double* clone_R,
+                                 const double* clone_p);
+
+/* ---- EKF update (StateManager.cpp:359-426) -------------------------------------------------- */
+/* var_order is given as (idx,size) blocks; H: B x (ldh*n) col-major with n = sum(size);
+ * res: B x rows; R by r_kind. Applies the retraction to the device mean mirror (boxPlus,
+ * StateManager.cpp:244-251) and, if dx_out != NULL, returns dx (B x N) for the caller's Type objects. */
+igv_status igv_ekf_update(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows,
+                          const double* H, int ldh, const double* res, const double* R, int r_kind,
+                          double* dx_out);
+/* UpdateBase::whitenResidual (Update.cpp:36-79): gamma[b] = res^T (H P_s H^T + R)^-1 res. */
+igv_status igv_chi2_whiten(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows,
+                           const double* H, int ldh, const double* res, const double* R, int r_kind,
+                           double* gamma_out);
+/* StateManager::boxPlus (StateManager.cpp:244-251) on the device mean mirror; dx: B x N. */
+igv_status igv_box_plus(igv_batch* h, const double* dx);
+
+/* ---- fused MSCKF visual update --------------------------------------------------------------
+ * RemoveLostUpdate::updateState{Mono,Stereo} (RemoveLostUpdate.cpp:40-167, :276-405),
+ * KeyframeUpdate::updateState* (KeyframeUpdate.cpp:438-735), SwMargUpdate::updateState*
+ * (SwMargUpdate.cpp:42-365) after track selection and triangulation: per-feature residual /
+ * Jacobian over clone poses, left null-space projection, chi^2 gate, stacking, QR compression,
+ * ekfUpdate, boxPlus. Clone poses are read from the device mean mirror. */
+typedef struct {
+  int mode;                  /* IGV_VIS_ALL_OBS | IGV_VIS_SELECTED                                */
+  int n_feats;               /* F <= max_feats                                                    */
+  const double* pf_w;        /* B x F x 3      triangulated landmark, world frame                 */
+  const int* anchor_slot;    /* B x F          clone slot of the landmark's anchor pose           */
+  const double* obs;         /* B x F x SW x rho  normalised image coordinates per clone slot     */
+  const unsigned char* obs_mask; /* B x F x SW  1 if the track has an observation at that slot and
+                                    (SELECTED mode) the slot is one of the selected clones        */
+  const int* chi2_dof;       /* B x F  dof of the gate: #obs-1 (RemoveLostUpdate.cpp:95-96),
+                                #selected-1 (SwMargUpdate.cpp:129-130), 2 (KeyframeUpdate.cpp:525-526) */
+  int obs_slots;             /* SW: slot dimension of obs / obs_mask (>= current clone count)      */
+  double noise;              /* visual_noise (sigma, normalised units)                             */
+  int max_valid;             /* stop after this many accepted tracks (RemoveLostUpdate.h:38); <=0: no cap */
+  double* dx_out;            /* optional B x N                                                    */
+  int* n_accepted_out;       /* optional B                                                        */
+  double* gamma_out;         /* optional B x F chi^2 statistics (NaN for tracks with < 2 usable obs) */
+} igv_msckf_args;
+igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a);
+
+/* ---- fused GNSS update ------------------------------------------------------------------------
+ * GnssUpdate::updateTrackedSys (GnssUpdate.cpp:84-293) from the psr_res / dopp_res output
+ * boundary (gnss_comm/src/gnss_spp.cpp:99-146, :256-282). */
+typedef struct {
+  int n_sats;                /* S <= max_sats                                                     */
+  const double* unit;        /* B x S x 3  receiver->satellite unit vectors (= -J[:,0:3]), ECEF    */
+  const double* res_pos;     /* B x S      psr_res output                                          */
+  const double* res_vel;     /* B x S      dopp_res output                                         */
+  const double* sigma_psr;   /* B x S      psr_noise of GnssUpdate.cpp:187                         */
+  const double* sigma_dopp;  /* B x S      dopp_noise of GnssUpdate.cpp:256                        */
+  const int* sys;            /* B x S      IGV_GNSS_GPS..BDS of each satellite                     */
+  const double* R_enu2ecef;  /* B x 9 row-major (GvioAligner::getRenu2ecef)                        */
+  int is_adjust_yof;         /* GnssUpdate.cpp:164-167,239-242                                     */
+  int chi2_test;             /* per-row gate (gnss_chi2_test, :190,:259)                           */
+  int strong_reject;         /* joint gate if rows <= 14 (:286)                                    */
+  double* dx_out;            /* optional B x N                                                    */
+} igv_gnss_args;
+igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a);
+
+/* ---- delayed initialisation / linear replacement ------------------------------------------------
+ * StateManager::addVariableDelayed (StateManager.cpp:547-630, with :462-541): new 1-dim variable.
+ * H_old: B x (rows x n_old) col-major (ld = rows), H_new: B x rows, res: B x rows.
+ * accepted_out: B ints (0/1); sequences that fail the chi^2 keep a decoupled variable with the
+ * supplied prior_cov_if_rejected so that the batch keeps one layout. gtype >= 0 registers the new
+ * scalar as that GNSS state (value: B doubles), gtype < 0 adds an opaque scalar. */
+igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value, int n_blocks,
+                                    const int* blk_idx, const int* blk_size, int rows, const double* H_old,
+                                    const double* H_new, const double* res, double noise_iso,
+                                    double chi2_mult, int do_chi2, double prior_cov_if_rejected,
+                                    int* accepted_out);
+/* StateManager::replaceVarLinear (StateManager.cpp:632-693). H: size(target) x n, col-major, B x ... */
+igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size, int n_blocks,
+                                  const int* blk_idx, const int* blk_size, const double* H);
+
+/* ---- per-sequence read-outs (SURVEY.md §5 metrics) --------------------------------------------- */
+igv_status igv_get_flags(igv_batch* h, int* flags_out /* B */, int clear);
+igv_status igv_cov_trace(igv_batch* h, double* trace_out /* B */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INGVIO_B200_H */
