@@ -1,0 +1,126 @@
+"""ctypes binding of libingvio_b200.so (the C-ABI declared in include/ingvio_b200.h).
+
+The CUDA library is mandatory: `load()` raises if it has not been built
+(`python -c "import __graft_entry__ as g; g.build()"`); there is no CPU fallback in the product.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libingvio_b200.so")
+
+IGV_OK, IGV_ERR_INVALID, IGV_ERR_CUDA, IGV_ERR_STATE, IGV_ERR_CAPACITY = range(5)
+IGV_PTR_HOST, IGV_PTR_DEVICE = 0, 1
+GPS, GLO, GAL, BDS, FS, YOF = range(6)
+R_ISO, R_DIAG, R_FULL = 0, 1, 2
+VIS_ALL_OBS, VIS_SELECTED = 0, 1
+FLAG_NEG_DIAG, FLAG_CHOL_FAIL, FLAG_GNSS_REJECTED = 1, 2, 4
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_ucp = C.POINTER(C.c_ubyte)
+
+
+class igv_config(C.Structure):
+    _fields_ = [("batch", C.c_int), ("max_dim", C.c_int), ("max_clones", C.c_int), ("max_feats", C.c_int),
+                ("max_sats", C.c_int), ("stereo", C.c_int), ("device", C.c_int), ("stream", C.c_void_p)]
+
+
+class igv_params(C.Structure):
+    _fields_ = [("noise_g", C.c_double), ("noise_a", C.c_double), ("noise_bg", C.c_double),
+                ("noise_ba", C.c_double), ("noise_clockbias", C.c_double), ("noise_cb_rw", C.c_double),
+                ("gravity", C.c_double * 3), ("T_cl2cr_R", C.c_double * 9), ("T_cl2cr_p", C.c_double * 3)]
+
+
+class igv_msckf_args(C.Structure):
+    _fields_ = [("mode", C.c_int), ("n_feats", C.c_int), ("pf_w", C.c_void_p), ("anchor_slot", C.c_void_p),
+                ("obs", C.c_void_p), ("obs_mask", C.c_void_p), ("chi2_dof", C.c_void_p), ("obs_slots", C.c_int),
+                ("noise", C.c_double), ("max_valid", C.c_int), ("dx_out", C.c_void_p),
+                ("n_accepted_out", C.c_void_p), ("gamma_out", C.c_void_p)]
+
+
+class igv_gnss_args(C.Structure):
+    _fields_ = [("n_sats", C.c_int), ("unit", C.c_void_p), ("res_pos", C.c_void_p), ("res_vel", C.c_void_p),
+                ("sigma_psr", C.c_void_p), ("sigma_dopp", C.c_void_p), ("sys", C.c_void_p),
+                ("R_enu2ecef", C.c_void_p), ("is_adjust_yof", C.c_int), ("chi2_test", C.c_int),
+                ("strong_reject", C.c_int), ("dx_out", C.c_void_p)]
+
+
+# every symbol include/ingvio_b200.h declares: (restype, argtypes)
+_H = C.c_void_p
+_VP = C.c_void_p
+SIGNATURES = {
+    "igv_create": (C.c_int, [C.POINTER(igv_config), C.POINTER(_H)]),
+    "igv_destroy": (C.c_int, [_H]),
+    "igv_last_error": (C.c_char_p, [_H]),
+    "igv_set_pointer_mode": (C.c_int, [_H, C.c_int]),
+    "igv_synchronize": (C.c_int, [_H]),
+    "igv_launch_count": (C.c_longlong, [_H]),
+    "igv_set_params": (C.c_int, [_H, C.POINTER(igv_params)]),
+    "igv_set_chi2_table": (C.c_int, [_H, c_dp, C.c_int]),
+    "igv_state_init": (C.c_int, [_H] + [_VP] * 7 + [c_dp]),
+    "igv_dim": (C.c_int, [_H]),
+    "igv_num_variables": (C.c_int, [_H]),
+    "igv_num_clones": (C.c_int, [_H]),
+    "igv_clone_idx": (C.c_int, [_H, C.c_int]),
+    "igv_gnss_idx": (C.c_int, [_H, C.c_int]),
+    "igv_state_size": (C.c_int, [_H]),
+    "igv_state_get": (C.c_int, [_H, _VP]),
+    "igv_state_set": (C.c_int, [_H, _VP]),
+    "igv_cov_get": (C.c_int, [_H, _VP, C.c_int]),
+    "igv_cov_set": (C.c_int, [_H, _VP, C.c_int]),
+    "igv_cov_get_blocks": (C.c_int, [_H, C.c_int, c_ip, c_ip, _VP]),
+    "igv_add_gnss_variable": (C.c_int, [_H, C.c_int, _VP, C.c_double]),
+    "igv_marg_gnss_variable": (C.c_int, [_H, C.c_int]),
+    "igv_add_variable_independent": (C.c_int, [_H, C.c_int, c_dp]),
+    "igv_marginalize": (C.c_int, [_H, C.c_int]),
+    "igv_marginalize_clone": (C.c_int, [_H, C.c_int]),
+    "igv_propagate_cov": (C.c_int, [_H, _VP, _VP, _VP]),
+    "igv_propagate_imu": (C.c_int, [_H, C.c_int, _VP, _VP, _VP]),
+    "igv_augment_clone": (C.c_int, [_H]),
+    "igv_augment_clone_cov": (C.c_int, [_H, _VP, _VP, _VP]),
+    "igv_ekf_update": (C.c_int, [_H, C.c_int, c_ip, c_ip, C.c_int, _VP, C.c_int, _VP, _VP, C.c_int, _VP]),
+    "igv_chi2_whiten": (C.c_int, [_H, C.c_int, c_ip, c_ip, C.c_int, _VP, C.c_int, _VP, _VP, C.c_int, _VP]),
+    "igv_box_plus": (C.c_int, [_H, _VP]),
+    "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
+    "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
+    "igv_add_variable_delayed": (C.c_int, [_H, C.c_int, _VP, C.c_int, c_ip, c_ip, C.c_int, _VP, _VP, _VP,
+                                           C.c_double, C.c_double, C.c_int, C.c_double, _VP]),
+    "igv_replace_var_linear": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_ip, c_ip, _VP]),
+    "igv_get_flags": (C.c_int, [_H, _VP, C.c_int]),
+    "igv_cov_trace": (C.c_int, [_H, _VP]),
+}
+
+_lib = None
+
+
+class IgvError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"igv status {status}: {msg}")
+        self.status = status
+
+
+def load():
+    """Loads the shared library and declares every prototype. Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is mandatory (no CPU fallback). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def header_symbols():
+    """Names declared in include/ingvio_b200.h (parsed), for the export test."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "ingvio_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(igv_[a-z0-9_]+)\s*\(", txt)))

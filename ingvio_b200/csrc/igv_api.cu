@@ -1,0 +1,707 @@
+// C-ABI entry points (include/ingvio_b200.h): handle lifetime, variable layout bookkeeping
+// (the host-side mirror of State::_err_variables, State.h:129-135), staging of host arguments and
+// kernel sequencing.  No torch types, no exit(): every failure is an igv_status + igv_last_error.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "igv_internal.h"
+
+namespace {
+
+#define IGV_CUDA(h, call)                                                            \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess) {                                                         \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+      return IGV_ERR_CUDA;                                                           \
+    }                                                                                \
+  } while (0)
+
+igv_status fail(igv_batch* h, igv_status s, const char* msg) {
+  if (h) h->err = msg;
+  return s;
+}
+
+igv_status check_launch(igv_batch* h) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    h->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+    return IGV_ERR_CUDA;
+  }
+  return IGV_OK;
+}
+
+// Device view of a bulk argument: the pointer itself in DEVICE mode, else a copy in the arena.
+template <class T>
+igv_status stage(igv_batch* h, const T* src, size_t count, const T** out) {
+  if (!src) { *out = nullptr; return IGV_OK; }
+  if (h->ptr_mode == IGV_PTR_DEVICE) { *out = src; return IGV_OK; }
+  const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+  if (h->arena_off + bytes > h->arena_cap) {
+    // grow: previous contents may still be in flight -> synchronise first
+    IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+    const size_t ncap = std::max(h->arena_cap * 2, h->arena_off + bytes + (size_t(1) << 20));
+    char* n = nullptr;
+    IGV_CUDA(h, cudaMalloc(&n, ncap));
+    if (h->arena) {
+      IGV_CUDA(h, cudaMemcpy(n, h->arena, h->arena_off, cudaMemcpyDeviceToDevice));
+      cudaFree(h->arena);
+    }
+    h->arena = n;
+    h->arena_cap = ncap;
+  }
+  T* dst = reinterpret_cast<T*>(h->arena + h->arena_off);
+  h->arena_off += bytes;
+  IGV_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  *out = dst;
+  return IGV_OK;
+}
+
+// Device buffer for an output argument; fetch() copies it back in HOST mode.
+template <class T>
+igv_status out_buf(igv_batch* h, T* user, size_t count, T** dev) {
+  if (!user) { *dev = nullptr; return IGV_OK; }
+  if (h->ptr_mode == IGV_PTR_DEVICE) { *dev = user; return IGV_OK; }
+  const T* tmp = nullptr;
+  // reserve arena space without copying
+  const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+  if (h->arena_off + bytes > h->arena_cap) {
+    IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+    const size_t ncap = std::max(h->arena_cap * 2, h->arena_off + bytes + (size_t(1) << 20));
+    char* n = nullptr;
+    IGV_CUDA(h, cudaMalloc(&n, ncap));
+    if (h->arena) {
+      IGV_CUDA(h, cudaMemcpy(n, h->arena, h->arena_off, cudaMemcpyDeviceToDevice));
+      cudaFree(h->arena);
+    }
+    h->arena = n;
+    h->arena_cap = ncap;
+  }
+  (void)tmp;
+  *dev = reinterpret_cast<T*>(h->arena + h->arena_off);
+  h->arena_off += bytes;
+  return IGV_OK;
+}
+template <class T>
+igv_status fetch(igv_batch* h, T* user, const T* dev, size_t count) {
+  if (!user || h->ptr_mode == IGV_PTR_DEVICE) return IGV_OK;
+  IGV_CUDA(h, cudaMemcpyAsync(user, dev, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
+#define IGV_TRY(expr)                 \
+  do {                                \
+    igv_status s_ = (expr);           \
+    if (s_ != IGV_OK) return s_;      \
+  } while (0)
+
+igv_status make_blocks(igv_batch* h, int n_blocks, const int* idx, const int* size, IgvBlocks* out) {
+  if (n_blocks <= 0 || n_blocks > IGV_MAX_BLOCKS || !idx || !size) return fail(h, IGV_ERR_INVALID, "bad block list");
+  out->n_blocks = n_blocks;
+  out->n = 0;
+  for (int i = 0; i < n_blocks; ++i) {
+    // checkSubOrder (StateManager.cpp:428-445): every block must be a variable of the state
+    bool found = false;
+    for (const auto& v : h->vars) if (v.idx == idx[i] && v.size == size[i]) found = true;
+    if (!found) return fail(h, IGV_ERR_STATE, "var_order block is not a variable of the state");
+    out->idx[i] = idx[i];
+    out->size[i] = size[i];
+    out->n += size[i];
+  }
+  if (out->n > 6 * IGV_MAX_BLOCKS) return fail(h, IGV_ERR_CAPACITY, "too many measured columns");
+  return IGV_OK;
+}
+
+void reindex(igv_batch* h) {
+  int idx = 0;
+  for (auto& v : h->vars) { v.idx = idx; idx += v.size; }
+  h->N = idx;
+}
+
+}  // namespace
+
+IgvLayout igv_batch::layout() const {
+  IgvLayout L;
+  L.N = N; L.ld = ld; L.xsize = xsize; L.n_clones = 0;
+  for (int i = 0; i < 6; ++i) L.idx_gnss[i] = -1;
+  for (int i = 0; i < IGV_MAX_CLONES; ++i) L.idx_clone[i] = -1;
+  for (const auto& v : vars) {
+    if (v.kind == VK_GNSS) L.idx_gnss[v.tag] = v.idx;
+    if (v.kind == VK_CLONE && L.n_clones < IGV_MAX_CLONES) L.idx_clone[L.n_clones++] = v.idx;
+  }
+  return L;
+}
+
+extern "C" {
+
+igv_status igv_create(const igv_config* cfg, igv_batch** out) {
+  if (!cfg || !out) return IGV_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->batch < 1 || cfg->max_dim < 21 || cfg->max_dim > 512 || cfg->max_clones < 0 ||
+      cfg->max_clones > IGV_MAX_CLONES || cfg->max_feats < 0 || cfg->max_sats < 0 || cfg->max_sats > 64)
+    return IGV_ERR_INVALID;
+  igv_batch* h = new igv_batch();
+  h->cfg = *cfg;
+  h->B = cfg->batch;
+  h->ld = (cfg->max_dim + 1) & ~1;
+  h->xsize = IGV_X_CORE + 12 * cfg->max_clones;
+  h->rho = cfg->stereo ? 4 : 2;
+  h->ncols_max = 6 * std::max(1, cfg->max_clones);
+  h->qmax = std::max(1, h->rho * cfg->max_clones - 3);
+  h->max_rows = std::max(std::max(h->ncols_max, 2 * cfg->max_sats), 32);
+  auto bail = [&](const char* what, cudaError_t e) {
+    std::fprintf(stderr, "igv_create: %s: %s\n", what, cudaGetErrorString(e));
+    igv_destroy(h);
+    return IGV_ERR_CUDA;
+  };
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return bail("cudaSetDevice", e);
+  if (cfg->stream) {
+    h->stream = static_cast<cudaStream_t>(cfg->stream);
+  } else {
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail("cudaStreamCreate", e);
+    h->own_stream = true;
+  }
+  const size_t B = h->B;
+#define IGV_ALLOC(ptr, count)                                                              \
+  do {                                                                                     \
+    e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), sizeof(*(ptr)) * (size_t)(count));    \
+    if (e != cudaSuccess) return bail(#ptr, e);                                            \
+    e = cudaMemsetAsync((ptr), 0, sizeof(*(ptr)) * (size_t)(count), h->stream);            \
+    if (e != cudaSuccess) return bail(#ptr, e);                                            \
+  } while (0)
+  IGV_ALLOC(h->P[0], B * h->ld * h->ld);
+  IGV_ALLOC(h->P[1], B * h->ld * h->ld);
+  IGV_ALLOC(h->X[0], B * h->xsize);
+  IGV_ALLOC(h->X[1], B * h->xsize);
+  IGV_ALLOC(h->flags, B);
+  IGV_ALLOC(h->chi2, 1024);
+  const size_t F = std::max(1, cfg->max_feats);
+  IGV_ALLOC(h->Hs, B * F * h->qmax * (h->ncols_max + 1));
+  IGV_ALLOC(h->f_rows, B * F);
+  IGV_ALLOC(h->f_gamma, B * F);
+  IGV_ALLOC(h->n_acc, B);
+  IGV_ALLOC(h->Hc, B * h->ncols_max * (h->ncols_max + 1));
+  h->qr_split_cap = (h->B < 296) ? 16 : 1;
+  if (h->qr_split_cap > 1) IGV_ALLOC(h->Rpart, B * h->qr_split_cap * h->ncols_max * (h->ncols_max + 1));
+  IGV_ALLOC(h->Zws, B * h->max_rows * (h->ld + 1));
+  IGV_ALLOC(h->Sws, B * h->max_rows * h->max_rows);
+  IGV_ALLOC(h->dxws, B * h->ld);
+  const size_t S2 = std::max(2, 2 * cfg->max_sats);
+  IGV_ALLOC(h->Hg, B * S2 * 16);
+  IGV_ALLOC(h->rg, B * S2);
+  IGV_ALLOC(h->Rg, B * S2);
+  IGV_ALLOC(h->cnt_g, B);
+  IGV_ALLOC(h->gam_ws, B);
+  IGV_ALLOC(h->Dws, B * (128 * 18 + 2));
+#undef IGV_ALLOC
+  // defaults of StateParams (State.h:48-53)
+  h->params.noise_g = 0.005; h->params.noise_a = 0.05; h->params.noise_bg = 0.001; h->params.noise_ba = 0.01;
+  h->params.noise_cb = 2.0; h->params.noise_cb_rw = 0.2;
+  h->params.g[0] = 0; h->params.g[1] = 0; h->params.g[2] = -9.8;
+  for (int i = 0; i < 9; ++i) h->params.Rc[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int i = 0; i < 3; ++i) h->params.pc[i] = 0.0;
+  *out = h;
+  return IGV_OK;
+}
+
+igv_status igv_destroy(igv_batch* h) {
+  if (!h) return IGV_OK;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
+                  h->Hc, h->Rpart, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->arena};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return IGV_OK;
+}
+
+const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "null handle"; }
+
+igv_status igv_set_pointer_mode(igv_batch* h, int mode) {
+  if (!h || (mode != IGV_PTR_HOST && mode != IGV_PTR_DEVICE)) return IGV_ERR_INVALID;
+  h->ptr_mode = mode;
+  return IGV_OK;
+}
+
+igv_status igv_synchronize(igv_batch* h) {
+  if (!h) return IGV_ERR_INVALID;
+  IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
+long long igv_launch_count(const igv_batch* h) { return h ? h->launches : 0; }
+
+igv_status igv_set_params(igv_batch* h, const igv_params* p) {
+  if (!h || !p) return IGV_ERR_INVALID;
+  h->params.noise_g = p->noise_g; h->params.noise_a = p->noise_a;
+  h->params.noise_bg = p->noise_bg; h->params.noise_ba = p->noise_ba;
+  h->params.noise_cb = p->noise_clockbias; h->params.noise_cb_rw = p->noise_cb_rw;
+  for (int i = 0; i < 3; ++i) { h->params.g[i] = p->gravity[i]; h->params.pc[i] = p->T_cl2cr_p[i]; }
+  for (int i = 0; i < 9; ++i) h->params.Rc[i] = p->T_cl2cr_R[i];
+  return IGV_OK;
+}
+
+igv_status igv_set_chi2_table(igv_batch* h, const double* table, int max_dof) {
+  if (!h || !table || max_dof < 1 || max_dof > 1024) return IGV_ERR_INVALID;
+  IGV_CUDA(h, cudaMemcpyAsync(h->chi2, table, sizeof(double) * max_dof, cudaMemcpyHostToDevice, h->stream));
+  IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->chi2_n = max_dof;
+  h->chi2_host.assign(table, table + max_dof);
+  return IGV_OK;
+}
+
+// ---- state ----------------------------------------------------------------------------------------
+igv_status igv_state_init(igv_batch* h, const double* R_i2w, const double* p, const double* v, const double* bg,
+                          const double* ba, const double* R_ext, const double* p_ext, const double* cov_diag21) {
+  if (!h || !R_i2w || !p || !v || !bg || !ba || !R_ext || !p_ext || !cov_diag21) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  const size_t B = h->B;
+  const double *dR, *dp, *dv, *dbg, *dba, *dRe, *dpe, *dd;
+  IGV_TRY(stage(h, R_i2w, B * 9, &dR)); IGV_TRY(stage(h, p, B * 3, &dp)); IGV_TRY(stage(h, v, B * 3, &dv));
+  IGV_TRY(stage(h, bg, B * 3, &dbg)); IGV_TRY(stage(h, ba, B * 3, &dba));
+  IGV_TRY(stage(h, R_ext, B * 9, &dRe)); IGV_TRY(stage(h, p_ext, B * 3, &dpe));
+  // cov_diag is shared and tiny: always a host array
+  double* ddiag = nullptr;
+  {
+    const int pm = h->ptr_mode;
+    h->ptr_mode = IGV_PTR_HOST;
+    igv_status s = stage(h, cov_diag21, 21, &dd);
+    h->ptr_mode = pm;
+    if (s != IGV_OK) return s;
+    (void)ddiag;
+  }
+  h->vars.clear();
+  h->vars.push_back({VK_SE23, 0, 9, 0});
+  h->vars.push_back({VK_BG, 9, 3, 0});
+  h->vars.push_back({VK_BA, 12, 3, 0});
+  h->vars.push_back({VK_EXT, 15, 6, 0});
+  reindex(h);
+  IGV_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * B, h->stream));
+  igv_launch_state_init(h, dR, dp, dv, dbg, dba, dRe, dpe, dd);
+  return check_launch(h);
+}
+
+int igv_dim(const igv_batch* h) { return h ? h->N : -1; }
+int igv_num_variables(const igv_batch* h) { return h ? (int)h->vars.size() : -1; }
+int igv_num_clones(const igv_batch* h) { return h ? h->layout().n_clones : -1; }
+int igv_clone_idx(const igv_batch* h, int slot) {
+  if (!h) return -1;
+  IgvLayout L = h->layout();
+  return (slot >= 0 && slot < L.n_clones) ? L.idx_clone[slot] : -1;
+}
+int igv_gnss_idx(const igv_batch* h, int gtype) {
+  if (!h || gtype < 0 || gtype > 5) return -1;
+  return h->layout().idx_gnss[gtype];
+}
+int igv_state_size(const igv_batch* h) { return h ? h->xsize : -1; }
+
+igv_status igv_state_get(igv_batch* h, double* dst) {
+  if (!h || !dst) return IGV_ERR_INVALID;
+  const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  IGV_CUDA(h, cudaMemcpyAsync(dst, h->Xc(), sizeof(double) * h->B * h->xsize, k, h->stream));
+  IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+igv_status igv_state_set(igv_batch* h, const double* src) {
+  if (!h || !src) return IGV_ERR_INVALID;
+  const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  IGV_CUDA(h, cudaMemcpyAsync(h->Xc(), src, sizeof(double) * h->B * h->xsize, k, h->stream));
+  return IGV_OK;
+}
+
+// ---- covariance -------------------------------------------------------------------------------------
+igv_status igv_cov_get(igv_batch* h, double* dst, int ld) {
+  if (!h || !dst || ld < h->N) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  double* dev;
+  IGV_TRY(out_buf(h, dst, (size_t)h->B * ld * h->N, &dev));
+  igv_launch_cov_copy(h, dev, ld, true);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, dst, dev, (size_t)h->B * ld * h->N));
+  if (h->ptr_mode == IGV_PTR_DEVICE) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+igv_status igv_cov_set(igv_batch* h, const double* src, int ld) {
+  if (!h || !src || ld < h->N) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  const double* dev;
+  IGV_TRY(stage(h, src, (size_t)h->B * ld * h->N, &dev));
+  igv_launch_cov_copy(h, const_cast<double*>(dev), ld, false);
+  return check_launch(h);
+}
+igv_status igv_cov_get_blocks(igv_batch* h, int n_blocks, const int* idx, const int* size, double* dst) {
+  if (!h || !dst) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  IgvBlocks blk;
+  IGV_TRY(make_blocks(h, n_blocks, idx, size, &blk));
+  double* dev;
+  const size_t cnt = (size_t)h->B * blk.n * blk.n;
+  IGV_TRY(out_buf(h, dst, cnt, &dev));
+  igv_launch_cov_blocks(h, blk, dev);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, dst, dev, cnt));
+  if (h->ptr_mode == IGV_PTR_DEVICE) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
+static igv_status add_variable(igv_batch* h, IgvVarKind kind, int tag, int size, const double* cov_block_host) {
+  if (h->N + size > h->cfg.max_dim) return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds max_dim");
+  const double* dev;
+  const int pm = h->ptr_mode;
+  h->ptr_mode = IGV_PTR_HOST;
+  igv_status s = stage(h, cov_block_host, (size_t)size * size, &dev);
+  h->ptr_mode = pm;
+  if (s != IGV_OK) return s;
+  igv_launch_add_variable(h, size, dev);
+  h->vars.push_back({kind, h->N, size, tag});
+  reindex(h);
+  return check_launch(h);
+}
+
+igv_status igv_add_gnss_variable(igv_batch* h, int gtype, const double* value, double cov) {
+  if (!h || gtype < 0 || gtype > 5) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  if (h->layout().idx_gnss[gtype] >= 0) return fail(h, IGV_ERR_STATE, "GNSS variable already in the state");
+  const double* dv;
+  IGV_TRY(stage(h, value, (size_t)h->B, &dv));
+  IGV_TRY(add_variable(h, VK_GNSS, gtype, 1, &cov));
+  igv_launch_set_gnss_value(h, gtype, dv);
+  return check_launch(h);
+}
+
+static igv_status marginalize_var(igv_batch* h, size_t vi) {
+  const IgvVar v = h->vars[vi];
+  if (v.kind == VK_SE23 || v.kind == VK_BG || v.kind == VK_BA || v.kind == VK_EXT)
+    return fail(h, IGV_ERR_STATE, "core variables cannot be marginalised");
+  int clone_slot = -1;
+  if (v.kind == VK_CLONE) {
+    clone_slot = 0;
+    for (size_t k = 0; k < vi; ++k) if (h->vars[k].kind == VK_CLONE) ++clone_slot;
+  }
+  igv_launch_marginalize(h, v.idx, v.size, clone_slot);
+  h->vars.erase(h->vars.begin() + vi);
+  reindex(h);
+  return check_launch(h);
+}
+
+igv_status igv_marg_gnss_variable(igv_batch* h, int gtype) {
+  if (!h || gtype < 0 || gtype > 5) return IGV_ERR_INVALID;
+  for (size_t i = 0; i < h->vars.size(); ++i)
+    if (h->vars[i].kind == VK_GNSS && h->vars[i].tag == gtype) return marginalize_var(h, i);
+  return fail(h, IGV_ERR_STATE, "GNSS variable not in the state");
+}
+
+igv_status igv_add_variable_independent(igv_batch* h, int size, const double* cov_block) {
+  if (!h || size < 1 || size > 6 || !cov_block) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  return add_variable(h, VK_OPAQUE, 0, size, cov_block);
+}
+
+igv_status igv_marginalize(igv_batch* h, int idx) {
+  if (!h) return IGV_ERR_INVALID;
+  for (size_t i = 0; i < h->vars.size(); ++i)
+    if (h->vars[i].idx == idx) return marginalize_var(h, i);
+  return fail(h, IGV_ERR_STATE, "Marg is not in the current state");  // StateManager.cpp:157-161
+}
+
+igv_status igv_marginalize_clone(igv_batch* h, int slot) {
+  if (!h) return IGV_ERR_INVALID;
+  int s = 0;
+  for (size_t i = 0; i < h->vars.size(); ++i)
+    if (h->vars[i].kind == VK_CLONE) {
+      if (s == slot) return marginalize_var(h, i);
+      ++s;
+    }
+  return fail(h, IGV_ERR_STATE, "clone slot not in the sliding window");
+}
+
+// ---- propagation ------------------------------------------------------------------------------------
+igv_status igv_propagate_cov(igv_batch* h, const double* Phi, const double* G, const double* dt) {
+  if (!h || !Phi || !G || !dt) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  const double *dP, *dG, *ddt;
+  IGV_TRY(stage(h, Phi, (size_t)h->B * 225, &dP));
+  IGV_TRY(stage(h, G, (size_t)h->B * 180, &dG));
+  IGV_TRY(stage(h, dt, (size_t)h->B, &ddt));
+  igv_launch_propagate(h, 1, nullptr, nullptr, ddt, dP, dG);
+  return check_launch(h);
+}
+
+igv_status igv_propagate_imu(igv_batch* h, int n_steps, const double* gyro, const double* accel, const double* dt) {
+  if (!h || n_steps < 0 || !gyro || !accel || !dt) return IGV_ERR_INVALID;
+  if (n_steps == 0) return IGV_OK;
+  h->arena_off = 0;
+  const double *dg, *da, *ddt;
+  IGV_TRY(stage(h, gyro, (size_t)h->B * n_steps * 3, &dg));
+  IGV_TRY(stage(h, accel, (size_t)h->B * n_steps * 3, &da));
+  IGV_TRY(stage(h, dt, (size_t)h->B * n_steps, &ddt));
+  igv_launch_propagate(h, n_steps, dg, da, ddt, nullptr, nullptr);
+  return check_launch(h);
+}
+
+static igv_status augment(igv_batch* h, const double* R, const double* cR, const double* cp) {
+  IgvLayout L = h->layout();
+  if (L.n_clones >= h->cfg.max_clones) return fail(h, IGV_ERR_CAPACITY, "sliding window is full");
+  if (h->N + 6 > h->cfg.max_dim) return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds max_dim");
+  igv_launch_augment(h, R, cR, cp);
+  h->vars.push_back({VK_CLONE, h->N, 6, 0});
+  reindex(h);
+  return check_launch(h);
+}
+igv_status igv_augment_clone(igv_batch* h) {
+  if (!h) return IGV_ERR_INVALID;
+  return augment(h, nullptr, nullptr, nullptr);
+}
+igv_status igv_augment_clone_cov(igv_batch* h, const double* R_i2w, const double* clone_R, const double* clone_p) {
+  if (!h || !R_i2w || ((clone_R == nullptr) != (clone_p == nullptr))) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  const double *dR, *dcR, *dcp;
+  IGV_TRY(stage(h, R_i2w, (size_t)h->B * 9, &dR));
+  IGV_TRY(stage(h, clone_R, (size_t)h->B * 9, &dcR));
+  IGV_TRY(stage(h, clone_p, (size_t)h->B * 3, &dcp));
+  return augment(h, dR, dcR, dcp);
+}
+
+// ---- EKF update -------------------------------------------------------------------------------------
+static igv_status ekf_common(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows,
+                             const double* H, int ldh, const double* res, const double* R, int r_kind, double* dx_out,
+                             double* gamma_out, bool gamma_only) {
+  if (!h || !H || !res || rows < 1 || ldh < rows) return IGV_ERR_INVALID;
+  if (r_kind != IGV_R_ISO && r_kind != IGV_R_DIAG && r_kind != IGV_R_FULL) return IGV_ERR_INVALID;
+  if (!R) return IGV_ERR_INVALID;
+  if (rows > h->max_rows) return fail(h, IGV_ERR_CAPACITY, "rows exceed the EKF workspace (max_rows)");
+  h->arena_off = 0;
+  IgvEkfLaunch e{};
+  IGV_TRY(make_blocks(h, n_blocks, blk_idx, blk_size, &e.blk));
+  const size_t B = h->B;
+  IGV_TRY(stage(h, H, B * ldh * e.blk.n, &e.H));
+  IGV_TRY(stage(h, res, B * rows, &e.res));
+  const size_t rcount = (r_kind == IGV_R_ISO) ? 1 : (r_kind == IGV_R_DIAG ? rows : (size_t)rows * rows);
+  IGV_TRY(stage(h, R, B * rcount, &e.R));
+  e.rows = rows; e.strideH = (long)ldh * e.blk.n; e.h_ld = ldh; e.h_rowmajor = 0;
+  e.strideRes = rows; e.res_inc = 1; e.strideR = (long)rcount; e.r_kind = r_kind;
+  double *ddx = nullptr, *dgam = nullptr;
+  IGV_TRY(out_buf(h, dx_out, B * h->N, &ddx));
+  IGV_TRY(out_buf(h, gamma_out, B, &dgam));
+  e.dx_out = ddx; e.gamma_only = gamma_only ? 1 : 0; e.gamma_out = dgam; e.gate_rows = nullptr;
+  e.apply_boxplus = gamma_only ? 0 : 1;
+  igv_launch_ekf(h, e);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, dx_out, ddx, B * h->N));
+  IGV_TRY(fetch(h, gamma_out, dgam, B));
+  return IGV_OK;
+}
+
+igv_status igv_ekf_update(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows, const double* H,
+                          int ldh, const double* res, const double* R, int r_kind, double* dx_out) {
+  return ekf_common(h, n_blocks, blk_idx, blk_size, rows, H, ldh, res, R, r_kind, dx_out, nullptr, false);
+}
+igv_status igv_chi2_whiten(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows, const double* H,
+                           int ldh, const double* res, const double* R, int r_kind, double* gamma_out) {
+  if (!gamma_out) return IGV_ERR_INVALID;
+  return ekf_common(h, n_blocks, blk_idx, blk_size, rows, H, ldh, res, R, r_kind, nullptr, gamma_out, true);
+}
+
+igv_status igv_box_plus(igv_batch* h, const double* dx) {
+  if (!h || !dx) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  const double* d;
+  IGV_TRY(stage(h, dx, (size_t)h->B * h->N, &d));
+  igv_launch_boxplus(h, d);
+  return check_launch(h);
+}
+
+// ---- fused visual update ------------------------------------------------------------------------------
+igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a) {
+  if (!h || !a) return IGV_ERR_INVALID;
+  if (a->n_feats < 0 || a->n_feats > h->cfg.max_feats) return fail(h, IGV_ERR_CAPACITY, "n_feats exceeds max_feats");
+  IgvLayout L = h->layout();
+  if (a->obs_slots < L.n_clones) return fail(h, IGV_ERR_INVALID, "obs_slots smaller than the clone count");
+  if (a->mode != IGV_VIS_ALL_OBS && a->mode != IGV_VIS_SELECTED) return IGV_ERR_INVALID;
+  if (a->n_feats == 0 || L.n_clones == 0) return IGV_OK;   // `if (update_ids.size() == 0) return;`
+  if (!a->pf_w || !a->anchor_slot || !a->obs || !a->obs_mask || !a->chi2_dof) return IGV_ERR_INVALID;
+  if (h->chi2_n < 1) return fail(h, IGV_ERR_STATE, "chi^2 table not set (igv_set_chi2_table)");
+  h->arena_off = 0;
+  const size_t B = h->B, F = a->n_feats, SW = a->obs_slots;
+  IgvMsckfLaunch m{};
+  m.mode = a->mode; m.F = a->n_feats; m.obs_slots = a->obs_slots; m.max_valid = a->max_valid; m.noise = a->noise;
+  IGV_TRY(stage(h, a->pf_w, B * F * 3, &m.pf));
+  IGV_TRY(stage(h, a->anchor_slot, B * F, &m.anchor));
+  IGV_TRY(stage(h, a->obs, B * F * SW * h->rho, &m.obs));
+  IGV_TRY(stage(h, a->obs_mask, B * F * SW, &m.mask));
+  IGV_TRY(stage(h, a->chi2_dof, B * F, &m.dof));
+  igv_launch_msckf_features(h, m);
+  IGV_TRY(check_launch(h));
+  igv_launch_qr_compress(h, a->n_feats, a->max_valid);
+  IGV_TRY(check_launch(h));
+  const int n = 6 * L.n_clones;
+  IgvEkfLaunch e{};
+  e.blk.n_blocks = L.n_clones; e.blk.n = n;
+  for (int s = 0; s < L.n_clones; ++s) { e.blk.idx[s] = L.idx_clone[s]; e.blk.size[s] = 6; }
+  e.rows = n;
+  e.H = h->Hc; e.strideH = (long)h->ncols_max * (h->ncols_max + 1); e.h_ld = n + 1; e.h_rowmajor = 1;
+  e.res = h->Hc + n; e.strideRes = e.strideH; e.res_inc = n + 1;
+  e.R = nullptr; e.strideR = 0; e.r_kind = IGV_R_ISO; e.r_iso_value = a->noise * a->noise;
+  double* ddx = nullptr;
+  IGV_TRY(out_buf(h, a->dx_out, B * h->N, &ddx));
+  e.dx_out = ddx; e.gamma_only = 0; e.gamma_out = nullptr; e.gate_rows = nullptr; e.only_if = h->n_acc;
+  e.apply_boxplus = 1;
+  igv_launch_ekf(h, e);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, a->dx_out, ddx, B * h->N));
+  if (a->n_accepted_out) {
+    if (h->ptr_mode == IGV_PTR_DEVICE)
+      IGV_CUDA(h, cudaMemcpyAsync(a->n_accepted_out, h->n_acc, sizeof(int) * B, cudaMemcpyDeviceToDevice, h->stream));
+    else IGV_TRY(fetch(h, a->n_accepted_out, h->n_acc, B));
+  }
+  if (a->gamma_out) {
+    const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    IGV_CUDA(h, cudaMemcpy2DAsync(a->gamma_out, sizeof(double) * F, h->f_gamma, sizeof(double) * h->cfg.max_feats,
+                                  sizeof(double) * F, B, k, h->stream));
+    if (h->ptr_mode == IGV_PTR_HOST) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return IGV_OK;
+}
+
+// ---- fused GNSS update --------------------------------------------------------------------------------
+igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
+  if (!h || !a) return IGV_ERR_INVALID;
+  if (a->n_sats < 0 || a->n_sats > h->cfg.max_sats) return fail(h, IGV_ERR_CAPACITY, "n_sats exceeds max_sats");
+  if (a->n_sats == 0) return IGV_OK;                       // GnssUpdate.cpp:92-93
+  IgvLayout L = h->layout();
+  // GnssManager::checkGnssStates (GnssManager.cpp:86-98)
+  if (L.idx_gnss[IGV_GNSS_YOF] < 0 || L.idx_gnss[IGV_GNSS_FS] < 0) return IGV_OK;
+  bool any = false;
+  for (int i = 0; i < 4; ++i) any = any || L.idx_gnss[i] >= 0;
+  if (!any) return IGV_OK;
+  if (!a->unit || !a->res_pos || !a->res_vel || !a->sigma_psr || !a->sigma_dopp || !a->sys || !a->R_enu2ecef)
+    return IGV_ERR_INVALID;
+  if ((a->chi2_test || a->strong_reject) && h->chi2_n < 14)
+    return fail(h, IGV_ERR_STATE, "chi^2 table not set (igv_set_chi2_table)");
+  h->arena_off = 0;
+  const size_t B = h->B, S = a->n_sats;
+  IgvGnssLaunch g{};
+  g.S = a->n_sats; g.adjust_yof = a->is_adjust_yof; g.chi2_test = a->chi2_test;
+  IGV_TRY(stage(h, a->unit, B * S * 3, &g.unit));
+  IGV_TRY(stage(h, a->res_pos, B * S, &g.res_pos));
+  IGV_TRY(stage(h, a->res_vel, B * S, &g.res_vel));
+  IGV_TRY(stage(h, a->sigma_psr, B * S, &g.sig_psr));
+  IGV_TRY(stage(h, a->sigma_dopp, B * S, &g.sig_dopp));
+  IGV_TRY(stage(h, a->sys, B * S, &g.sys));
+  IGV_TRY(stage(h, a->R_enu2ecef, B * 9, &g.R_enu2ecef));
+  // var_order: SE23, YOF, clock biases present, FS
+  IgvBlocks& blk = g.blk;
+  blk.n_blocks = 0; blk.n = 0;
+  auto push = [&](int idx, int size) { blk.idx[blk.n_blocks] = idx; blk.size[blk.n_blocks] = size; blk.n_blocks++; blk.n += size; };
+  for (int i = 0; i < 6; ++i) g.col_of_gnss[i] = -1;
+  push(0, 9);
+  g.col_of_gnss[IGV_GNSS_YOF] = blk.n; push(L.idx_gnss[IGV_GNSS_YOF], 1);
+  for (int i = 0; i < 4; ++i) if (L.idx_gnss[i] >= 0) { g.col_of_gnss[i] = blk.n; push(L.idx_gnss[i], 1); }
+  g.col_of_gnss[IGV_GNSS_FS] = blk.n; push(L.idx_gnss[IGV_GNSS_FS], 1);
+  igv_launch_gnss_rows(h, g);
+  IGV_TRY(check_launch(h));
+  IgvEkfLaunch e{};
+  e.blk = blk; e.rows = 2 * a->n_sats;
+  const int ldh = 2 * h->cfg.max_sats;
+  e.H = h->Hg; e.strideH = (long)ldh * 16; e.h_ld = ldh; e.h_rowmajor = 0;
+  e.res = h->rg; e.strideRes = ldh; e.res_inc = 1;
+  e.R = h->Rg; e.strideR = ldh; e.r_kind = IGV_R_DIAG;
+  double* ddx = nullptr;
+  IGV_TRY(out_buf(h, a->dx_out, B * h->N, &ddx));
+  e.dx_out = ddx; e.gamma_only = 0; e.gamma_out = nullptr;
+  e.gate_rows = a->strong_reject ? h->cnt_g : nullptr;
+  e.only_if = h->cnt_g;   // `if rows == 0` nothing to do
+  e.apply_boxplus = 1;
+  igv_launch_ekf(h, e);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, a->dx_out, ddx, B * h->N));
+  return IGV_OK;
+}
+
+// ---- delayed init / linear replace ------------------------------------------------------------------------
+igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value, int n_blocks, const int* blk_idx,
+                                    const int* blk_size, int rows, const double* H_old, const double* H_new,
+                                    const double* res, double noise_iso, double chi2_mult, int do_chi2,
+                                    double prior_cov_if_rejected, int* accepted_out) {
+  if (!h || !H_old || !H_new || !res || rows < 1 || rows > 128 || gtype > 5) return IGV_ERR_INVALID;
+  if (rows <= 1) return fail(h, IGV_ERR_INVALID, "H_new rows should be larger than H_new cols");  // StateManager.cpp:574-578
+  if (gtype >= 0 && h->layout().idx_gnss[gtype] >= 0) return fail(h, IGV_ERR_STATE, "New var already in state");
+  if (h->N + 1 > h->cfg.max_dim) return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds max_dim");
+  if (rows - 1 > h->max_rows) return fail(h, IGV_ERR_CAPACITY, "rows exceed the EKF workspace");
+  if (do_chi2 && h->chi2_n < rows) return fail(h, IGV_ERR_STATE, "chi^2 table too short");
+  h->arena_off = 0;
+  IgvBlocks blk;
+  IGV_TRY(make_blocks(h, n_blocks, blk_idx, blk_size, &blk));
+  const size_t B = h->B;
+  const double *dHo, *dHn, *dr, *dval = nullptr;
+  IGV_TRY(stage(h, H_old, B * rows * blk.n, &dHo));
+  IGV_TRY(stage(h, H_new, B * rows, &dHn));
+  IGV_TRY(stage(h, res, B * rows, &dr));
+  if (gtype >= 0) IGV_TRY(stage(h, value, B, &dval));
+  if (blk.n > 16) return fail(h, IGV_ERR_CAPACITY, "delayed init supports at most 16 measured columns");
+  int* dacc = h->n_acc;
+  igv_launch_delayed_init(h, blk, rows, dHo, dHn, dr, noise_iso, chi2_mult, do_chi2, prior_cov_if_rejected, dacc);
+  IGV_TRY(check_launch(h));
+  h->vars.push_back({gtype >= 0 ? VK_GNSS : VK_OPAQUE, h->N, 1, gtype >= 0 ? gtype : 0});
+  reindex(h);
+  if (gtype >= 0) { igv_launch_set_gnss_value(h, gtype, dval); IGV_TRY(check_launch(h)); }
+  // EKF on the remaining rows (StateManager.cpp:626-627), only where the variable was accepted
+  IgvEkfLaunch e{};
+  e.blk = blk; e.rows = rows - 1;
+  e.H = h->Dws + 1; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
+  e.res = h->Dws + B * rows * blk.n + 1; e.strideRes = rows; e.res_inc = 1;
+  e.R = nullptr; e.strideR = 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
+  e.only_if = dacc; e.apply_boxplus = 1;
+  igv_launch_ekf(h, e);
+  IGV_TRY(check_launch(h));
+  if (accepted_out) {
+    if (h->ptr_mode == IGV_PTR_DEVICE)
+      IGV_CUDA(h, cudaMemcpyAsync(accepted_out, dacc, sizeof(int) * B, cudaMemcpyDeviceToDevice, h->stream));
+    else IGV_TRY(fetch(h, accepted_out, dacc, B));
+  }
+  return IGV_OK;
+}
+
+igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size, int n_blocks, const int* blk_idx,
+                                  const int* blk_size, const double* H) {
+  if (!h || !H || target_size < 1 || target_size > 6) return IGV_ERR_INVALID;
+  bool found = false;
+  for (const auto& v : h->vars) if (v.idx == target_idx && v.size == target_size) found = true;
+  if (!found) return fail(h, IGV_ERR_STATE, "Target var not in state, cannot linearly replace");
+  h->arena_off = 0;
+  IgvBlocks blk;
+  IGV_TRY(make_blocks(h, n_blocks, blk_idx, blk_size, &blk));
+  const double* dH;
+  IGV_TRY(stage(h, H, (size_t)h->B * target_size * blk.n, &dH));
+  igv_launch_replace_var_linear(h, target_idx, target_size, blk, dH);
+  return check_launch(h);
+}
+
+// ---- read-outs --------------------------------------------------------------------------------------------
+igv_status igv_get_flags(igv_batch* h, int* flags_out, int clear) {
+  if (!h || !flags_out) return IGV_ERR_INVALID;
+  const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  IGV_CUDA(h, cudaMemcpyAsync(flags_out, h->flags, sizeof(int) * h->B, k, h->stream));
+  if (clear) IGV_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * h->B, h->stream));
+  IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
+igv_status igv_cov_trace(igv_batch* h, double* trace_out) {
+  if (!h || !trace_out) return IGV_ERR_INVALID;
+  h->arena_off = 0;
+  double* dev;
+  IGV_TRY(out_buf(h, trace_out, (size_t)h->B, &dev));
+  igv_launch_trace(h, dev);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, trace_out, dev, (size_t)h->B));
+  if (h->ptr_mode == IGV_PTR_DEVICE) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
+}  // extern "C"

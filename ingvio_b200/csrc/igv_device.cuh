@@ -1,0 +1,244 @@
+// Device-side helpers: 3x3 / so(3) math, CTA-cooperative FP64 GEMM / Cholesky / TRSM, box-plus.
+// sm_100a only. FP64 has no tcgen05 kind, so dense contractions here run on the DFMA pipe
+// (B200: 64 DFMA/clk/SM); see DESIGN.md "why not tcgen05".
+#pragma once
+#include <math.h>
+
+#include "igv_internal.h"
+
+namespace igv {
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 row-major helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ void mat3_vec(const double* A, const double* x, double* y) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
+}
+__device__ __forceinline__ void mat3T_vec(const double* A, const double* x, double* y) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] = A[i] * x[0] + A[3 + i] * x[1] + A[6 + i] * x[2];
+}
+__device__ __forceinline__ void skew3(const double* v, double* S) {
+  S[0] = 0.0; S[1] = -v[2]; S[2] = v[1];
+  S[3] = v[2]; S[4] = 0.0; S[5] = -v[0];
+  S[6] = -v[1]; S[7] = v[0]; S[8] = 0.0;
+}
+
+// Gamma_m(phi), m = 0..3.  Reference: AuxGammaFunc.cpp:46-113 (small-angle cut-off 1e-6).
+__device__ inline void gamma_func(const double* vec, int m, double* out) {
+  const double theta = sqrt(vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2]);
+  if (fabs(theta) < 1e-6) {
+    const double f = (m == 3) ? (1.0 / 6.0) : ((m == 2) ? 0.5 : 1.0);
+    for (int i = 0; i < 9; ++i) out[i] = 0.0;
+    out[0] = out[4] = out[8] = f;
+    return;
+  }
+  const double n[3] = {vec[0] / theta, vec[1] / theta, vec[2] / theta};
+  double nx[9], nx2[9];
+  skew3(n, nx);
+  mat3_mul(nx, nx, nx2);
+  double s, c;
+  sincos(theta, &s, &c);
+  double f0, f1, f2;
+  if (m == 1) {
+    f0 = 1.0; f1 = (1.0 - c) / theta; f2 = (theta - s) / theta;
+  } else if (m == 2) {
+    const double t2 = theta * theta;
+    f0 = 0.5; f1 = (theta - s) / t2; f2 = (t2 + 2.0 * c - 2.0) / (2.0 * t2);
+  } else if (m == 3) {
+    const double t2 = theta * theta, t3 = t2 * theta;
+    f0 = 1.0 / 6.0; f1 = (t2 + 2.0 * c - 2.0) / (2.0 * t3); f2 = (t3 - 6.0 * theta + 6.0 * s) / (6.0 * t3);
+  } else {
+    f0 = 1.0; f1 = s; f2 = 1.0 - c;
+  }
+  for (int i = 0; i < 9; ++i) out[i] = f1 * nx[i] + f2 * nx2[i];
+  out[0] += f0; out[4] += f0; out[8] += f0;
+}
+
+// Psi1 / Psi2 (AuxGammaFunc.cpp:115-166, :168-225), reproduced as the reference evaluates them.
+__device__ inline void psi_func(const double* w, const double* a, double dt, int which, double* out) {
+  const double wn = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  if (wn * fabs(dt) < ((which == 1) ? 1e-8 : 1e-7)) {
+    for (int i = 0; i < 9; ++i) out[i] = 0.0;
+    return;
+  }
+  double W[9], A[9], Gm[9], M1[9], nw[3] = {-w[0] * dt, -w[1] * dt, -w[2] * dt};
+  skew3(w, W);
+  skew3(a, A);
+  gamma_func(nw, (which == 1) ? 2 : 3, Gm);
+  mat3_mul(A, Gm, M1);
+  const double sc = (which == 1) ? dt * dt : dt * dt * dt;
+  for (int i = 0; i < 9; ++i) M1[i] *= sc;
+  double WA[9], WAW[9], WAW2[9], W2A[9], W2AW[9], W2AW2[9];
+  mat3_mul(W, A, WA);
+  mat3_mul(WA, W, WAW);
+  mat3_mul(WAW, W, WAW2);
+  mat3_mul(W, WA, W2A);
+  mat3_mul(W2A, W, W2AW);
+  mat3_mul(W2AW, W, W2AW2);
+  const double eta = wn, xi = eta * dt, xi2 = xi * xi, xi3 = xi * xi2;
+  double s1, c1, s2, c2;
+  sincos(xi, &s1, &c1);
+  sincos(2.0 * xi, &s2, &c2);
+  const double e3 = eta * eta * eta, e4 = eta * e3, e5 = eta * e4, e6 = eta * e5, e7 = eta * e6;
+  double k1, k2, k3, k4, k5, k6;
+  if (which == 1) {
+    k1 = (s1 - xi * c1) / e3;
+    k2 = (c2 - 4 * c1 + 3) / (4 * e4);
+    k3 = (4 * s1 + s2 - 4 * xi * c1 - 2 * xi) / (4 * e5);
+    k4 = (xi2 - 2 * xi * s1 - 2 * c1 + 2) / (2 * e4);
+    k5 = (6 * xi - 8 * s1 + s2) / (4 * e5);
+    k6 = (2 * xi2 - 4 * xi * s1 - c2 + 1) / (4 * e6);
+  } else {
+    k1 = (xi * s1 + 2 * c1 - 2) / e4;
+    k2 = (6 * xi - 8 * s1 + s2) / (8 * e5);
+    k3 = (2 * xi2 + 8 * xi * s1 + 16 * c1 + c2 - 17) / (8 * e6);
+    k4 = (xi3 + 6 * xi - 12 * s1 + 6 * xi * c1) / (6 * e5);
+    k5 = (6 * xi2 + 16 * c1 - c2 - 15) / (8 * e6);
+    k6 = (4 * xi3 + 6 * xi - 24 * s1 - 3 * s2 + 24 * xi * c1) / (24 * e7);
+  }
+  double T[9];
+  for (int i = 0; i < 9; ++i)
+    T[i] = k1 * WA[i] + k2 * WAW[i] + k3 * WAW2[i] + k4 * W2A[i] + k5 * W2AW[i] + k6 * W2AW2[i];
+  mat3_mul(M1, T, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// box-plus on the packed mean (PoseState.cpp:79-88,174-186, VecState.cpp:27-47)
+// ---------------------------------------------------------------------------------------------
+__device__ inline void retract_pose(double* R, double* p1, double* p2, const double* dth, const double* d1,
+                                    const double* d2) {
+  double G0[9], G1[9], Rn[9], t[3], u[3];
+  gamma_func(dth, 0, G0);
+  gamma_func(dth, 1, G1);
+  mat3_mul(G0, R, Rn);
+  for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  mat3_vec(G0, p1, t);
+  mat3_vec(G1, d1, u);
+  for (int i = 0; i < 3; ++i) p1[i] = t[i] + u[i];
+  if (p2) {
+    mat3_vec(G0, p2, t);
+    mat3_vec(G1, d2, u);
+    for (int i = 0; i < 3; ++i) p2[i] = t[i] + u[i];
+  }
+}
+
+// One thread per variable applies x <- x [+] dx.  Call with at least (4 + 6 + n_clones) threads
+// active, or loop: `for (v = tid; v < nvar; v += nthreads)`.
+__device__ inline void boxplus_var(double* X, const double* dx, const IgvLayout& L, int v) {
+  if (v == 0) {
+    retract_pose(X, X + 9, X + 12, dx, dx + 3, dx + 6);
+  } else if (v == 1) {
+    for (int i = 0; i < 3; ++i) X[15 + i] += dx[9 + i];
+  } else if (v == 2) {
+    for (int i = 0; i < 3; ++i) X[18 + i] += dx[12 + i];
+  } else if (v == 3) {
+    retract_pose(X + 21, X + 30, nullptr, dx + 15, dx + 18, nullptr);
+  } else if (v < 10) {
+    const int g = v - 4;
+    if (L.idx_gnss[g] >= 0) X[33 + g] += dx[L.idx_gnss[g]];
+  } else {
+    const int s = v - 10;
+    if (s < L.n_clones) {
+      double* c = X + IGV_X_CORE + 12 * s;
+      const double* d = dx + L.idx_clone[s];
+      retract_pose(c, c + 9, nullptr, d, d + 3, nullptr);
+    }
+  }
+}
+__device__ inline void boxplus_all(double* X, const double* dx, const IgvLayout& L) {
+  for (int v = threadIdx.x; v < 10 + L.n_clones; v += blockDim.x) boxplus_var(X, dx, L, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-cooperative FP64 GEMM with functor operands:  C(i,j) (op)= sum_k A(i,k) * B(k,j)
+// Each thread owns a TM x TN register tile whose rows/cols are INTERLEAVED over the tile grid, so
+// that consecutive threads touch consecutive i (coalesced / conflict-free for i-contiguous storage).
+// ---------------------------------------------------------------------------------------------
+template <int TM, int TN, class FA, class FB, class FC>
+__device__ __forceinline__ void cta_gemm(int M, int N, int K, FA a, FB b, FC c) {
+  const int gm = (M + TM - 1) / TM, gn = (N + TN - 1) / TN;
+  for (int t = threadIdx.x; t < gm * gn; t += blockDim.x) {
+    const int ti = t % gm, tj = t / gm;
+    int ri[TM], cj[TN];
+#pragma unroll
+    for (int u = 0; u < TM; ++u) ri[u] = min(ti + u * gm, M - 1);
+#pragma unroll
+    for (int v = 0; v < TN; ++v) cj[v] = min(tj + v * gn, N - 1);
+    double acc[TM][TN];
+#pragma unroll
+    for (int u = 0; u < TM; ++u)
+#pragma unroll
+      for (int v = 0; v < TN; ++v) acc[u][v] = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double av[TM], bv[TN];
+#pragma unroll
+      for (int u = 0; u < TM; ++u) av[u] = a(ri[u], k);
+#pragma unroll
+      for (int v = 0; v < TN; ++v) bv[v] = b(k, cj[v]);
+#pragma unroll
+      for (int u = 0; u < TM; ++u)
+#pragma unroll
+        for (int v = 0; v < TN; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < TM; ++u)
+#pragma unroll
+      for (int v = 0; v < TN; ++v)
+        if (ti + u * gm < M && tj + v * gn < N) c(ti + u * gm, tj + v * gn, acc[u][v]);
+  }
+}
+
+// In-place lower Cholesky of the n x n matrix S (column-major, leading dim lds), CTA-cooperative,
+// right-looking. Returns false (uniformly) if a non-positive pivot appears. `s_ok` is a shared int.
+__device__ inline bool cta_cholesky(double* S, int n, int lds, int* s_ok) {
+  if (threadIdx.x == 0) *s_ok = 1;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = S[j + (long)j * lds];
+      if (!(d > 0.0)) *s_ok = 0;
+      S[j + (long)j * lds] = sqrt(d);
+    }
+    __syncthreads();
+    if (!*s_ok) return false;
+    const double dj = S[j + (long)j * lds];
+    for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) S[i + (long)j * lds] /= dj;
+    __syncthreads();
+    // trailing update of the lower triangle: S[i,c] -= L[i,j] L[c,j], j < c <= i < n
+    const int m = n - j - 1;
+    for (int t = threadIdx.x; t < m * m; t += blockDim.x) {
+      const int i = j + 1 + t % m, c = j + 1 + t / m;
+      if (c <= i) S[i + (long)c * lds] -= S[i + (long)j * lds] * S[c + (long)j * lds];
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// Z <- L^{-1} Z for a rows x ncol column-major Z (leading dim ldz): one thread per column.
+__device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int rows, int ncol, int ldz) {
+  for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+    double* z = Z + (long)c * ldz;
+    for (int i = 0; i < rows; ++i) {
+      double acc = z[i];
+      for (int k = 0; k < i; ++k) acc = fma(-L[i + (long)k * ldl], z[k], acc);
+      z[i] = acc / L[i + (long)i * ldl];
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace igv

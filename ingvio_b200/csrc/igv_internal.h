@@ -1,0 +1,139 @@
+// Internal declarations shared by the C-ABI host code and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ingvio_b200.h"
+
+#define IGV_MAX_CLONES 64
+#define IGV_MAX_BLOCKS 80
+#define IGV_X_CORE 39          // packed mean: 33 core doubles + 6 GNSS scalars, then 12 per clone
+
+// Variable layout of the batch, passed BY VALUE to kernels (all sequences share it).
+struct IgvLayout {
+  int N;                         // current state dimension
+  int ld;                        // leading dimension of P
+  int xsize;                     // doubles per sequence in the mean mirror
+  int n_clones;
+  int idx_clone[IGV_MAX_CLONES]; // Type::idx() of clone slot s (0 = oldest)
+  int idx_gnss[6];               // Type::idx() of GPS,GLO,GAL,BDS,FS,YOF or -1
+};
+
+struct IgvBlocks {               // a var_order as (idx,size) blocks
+  int n_blocks;
+  int n;                         // sum of sizes
+  int idx[IGV_MAX_BLOCKS];
+  int size[IGV_MAX_BLOCKS];
+};
+
+struct IgvDevParams {
+  double noise_g, noise_a, noise_bg, noise_ba, noise_cb, noise_cb_rw;
+  double g[3];
+  double Rc[9];                  // T_cl2cr rotation, row-major
+  double pc[3];
+};
+
+enum IgvVarKind { VK_SE23, VK_BG, VK_BA, VK_EXT, VK_GNSS, VK_CLONE, VK_OPAQUE };
+struct IgvVar {
+  IgvVarKind kind;
+  int idx, size;
+  int tag;                       // gnss type for VK_GNSS
+};
+
+struct igv_batch {
+  igv_config cfg{};
+  int B = 0, ld = 0, xsize = 0, max_rows = 0, qmax = 0, ncols_max = 0, rho = 2;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int ptr_mode = IGV_PTR_HOST;
+  std::string err;
+  long long launches = 0;
+  std::vector<IgvVar> vars;       // insertion order == covariance order (State::_err_variables)
+  int N = 0;
+  IgvDevParams params{};
+  // device memory
+  double* P[2] = {nullptr, nullptr};   // ping-pong covariance, B x ld x ld col-major
+  int cur = 0;
+  double* X[2] = {nullptr, nullptr};   // mean mirror, B x xsize
+  int xcur = 0;
+  int* flags = nullptr;                // B
+  double* chi2 = nullptr;              // table[d-1]
+  int chi2_n = 0;
+  // workspaces
+  double* Hs = nullptr;                // stacked projected blocks  B x F x qmax x (ncols_max+1) row-major
+  int* f_rows = nullptr;               // B x F rows written per feature (0 = rejected)
+  double* f_gamma = nullptr;           // B x F
+  int* n_acc = nullptr;                // B
+  double* Hc = nullptr;                // compressed [R | Q^T r]   B x ncols_max x (ncols_max+1) row-major
+  double* Rpart = nullptr;             // partial triangles for split QR
+  int qr_split_cap = 0;
+  double* Zws = nullptr;               // B x max_rows x (ld+1)
+  double* Sws = nullptr;               // B x max_rows x max_rows
+  double* dxws = nullptr;              // B x ld
+  double* Hg = nullptr;                // GNSS rows  B x (2*max_sats) x 16 col-major
+  double* rg = nullptr;                // B x 2*max_sats
+  double* Rg = nullptr;                // B x 2*max_sats
+  int* cnt_g = nullptr;                // B accepted GNSS rows
+  double* gam_ws = nullptr;            // B
+  double* Dws = nullptr;               // delayed-init workspace: B x (128*18 + 2)
+  std::vector<double> chi2_host;
+  // host->device staging arena
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
+
+  IgvLayout layout() const;
+  double* Pc() const { return P[cur]; }
+  double* Xc() const { return X[xcur]; }
+};
+
+// ---- kernel launchers (defined in the k_*.cu files) --------------------------------------------
+void igv_launch_state_init(igv_batch* h, const double* R, const double* p, const double* v, const double* bg,
+                           const double* ba, const double* Rext, const double* pext, const double* diag21);
+void igv_launch_cov_copy(igv_batch* h, double* user, int ld_user, bool to_user);
+void igv_launch_cov_blocks(igv_batch* h, const IgvBlocks& blk, double* dst);
+void igv_launch_add_variable(igv_batch* h, int size, const double* cov_block_dev);
+void igv_launch_marginalize(igv_batch* h, int start, int size, int clone_slot);
+void igv_launch_set_gnss_value(igv_batch* h, int gtype, const double* value_dev);
+void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const double* accel, const double* dt,
+                          const double* Phi, const double* G);
+void igv_launch_augment(igv_batch* h, const double* R_i2w, const double* clone_R, const double* clone_p);
+void igv_launch_boxplus(igv_batch* h, const double* dx);
+void igv_launch_trace(igv_batch* h, double* out);
+
+struct IgvEkfLaunch {
+  IgvBlocks blk;
+  int rows;
+  const double* H; long strideH; int h_ld; int h_rowmajor;
+  const double* res; long strideRes; int res_inc;
+  const double* R; long strideR; int r_kind;
+  double r_iso_value;        // used when r_kind == IGV_R_ISO and R == nullptr
+  const int* only_if;        // optional per-sequence mask: update only where nonzero
+  double* dx_out;            // device, B x N or null
+  int gamma_only; double* gamma_out;
+  const int* gate_rows;      // optional per-sequence row count for the joint chi^2 gate (GNSS strong reject)
+  int apply_boxplus;
+};
+void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& a);
+
+struct IgvMsckfLaunch {
+  int mode, F, obs_slots, max_valid;
+  const double* pf; const int* anchor; const double* obs; const unsigned char* mask; const int* dof;
+  double noise;
+};
+void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& a);
+void igv_launch_qr_compress(igv_batch* h, int F, int max_valid);
+
+struct IgvGnssLaunch {
+  int S; const double* unit; const double* res_pos; const double* res_vel; const double* sig_psr;
+  const double* sig_dopp; const int* sys; const double* R_enu2ecef; int adjust_yof; int chi2_test;
+  IgvBlocks blk;             // var_order used for the rows: SE23, YOF, present clock biases, FS
+  int col_of_gnss[6];        // column of each GNSS scalar in H (or -1)
+};
+void igv_launch_gnss_rows(igv_batch* h, const IgvGnssLaunch& a);
+
+void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
+                             const double* res, double noise_iso, double chi2_mult, int do_chi2,
+                             double prior_cov, int* accepted_dev);
+void igv_launch_replace_var_linear(igv_batch* h, int tidx, int tsize, const IgvBlocks& blk, const double* H);

@@ -1,0 +1,236 @@
+// IMU propagation: mean + analytic (Phi, G) + covariance strip update, all K steps of a frame in
+// one launch with the strip resident in shared memory.
+//
+// Reference: ImuPropagator::stateAndCovTransition (ImuPropagator.cpp:98-162, analytic branch),
+// the loop body of propagateUntil (:260-271) and StateManager::propagateStateCov
+// (StateManager.cpp:42-119).  The reference forms Phi_bar P Phi_bar^T on the full N x N matrix with
+// four N x N temporaries per IMU sample; only the rows/cols of the 15 IMU states and of the clock
+// biases change, plus the clock-drift row through Q, so this kernel keeps that (<= 20) x N strip
+// in SMEM across all steps and touches HBM once per frame: 2*nS*N*8 bytes read+write.
+#include "igv_device.cuh"
+
+using namespace igv;
+
+namespace {
+
+constexpr int kMaxStrip = 20;  // 15 IMU + 4 clock biases + clock drift
+
+struct PropArgs {
+  double* P; int ld; int N;
+  double* X; int xsize;
+  int n_steps;
+  const double* gyro; const double* accel; const double* dt;  // IMU mode (Phi == nullptr)
+  const double* Phi; const double* G;                         // covariance-only mode
+  IgvDevParams prm;
+  int idx_cb[4]; int idx_fs; int enable_gnss;
+};
+
+// thread 0: mean propagation and Phi (15x15, row-major in sPhi), Gs = G*diag(sigma) (15x12 row-major)
+__device__ void imu_step_mean(double* X, const double* wraw, const double* araw, double dt, const IgvDevParams& prm,
+                              const int* idx_cb, int idx_fs, double* sPhi, double* sG) {
+  double* R = X; double* p = X + 9; double* v = X + 12;
+  const double* bg = X + 15; const double* ba = X + 18;
+  for (int i = 0; i < 225; ++i) sPhi[i] = 0.0;
+  for (int i = 0; i < 15; ++i) sPhi[16 * i] = 1.0;
+  for (int i = 0; i < 180; ++i) sG[i] = 0.0;
+  double Rh[9], ph[3], vh[3], S[9], T[9];
+  for (int i = 0; i < 9; ++i) Rh[i] = R[i];
+  for (int i = 0; i < 3; ++i) { ph[i] = p[i]; vh[i] = v[i]; }
+  // G (ImuPropagator.cpp:112-117), scaled by the noise sigmas (StateManager.cpp:92-96)
+  skew3(ph, S); mat3_mul(S, Rh, T);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+    sG[r * 12 + c] = Rh[3 * r + c] * prm.noise_g;
+    sG[(3 + r) * 12 + c] = T[3 * r + c] * prm.noise_g;
+  }
+  skew3(vh, S); mat3_mul(S, Rh, T);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+    sG[(6 + r) * 12 + c] = T[3 * r + c] * prm.noise_g;
+    sG[(6 + r) * 12 + 3 + c] = Rh[3 * r + c] * prm.noise_a;
+  }
+  for (int r = 0; r < 3; ++r) { sG[(9 + r) * 12 + 6 + r] = prm.noise_bg; sG[(12 + r) * 12 + 9 + r] = prm.noise_ba; }
+  const double w[3] = {wraw[0] - bg[0], wraw[1] - bg[1], wraw[2] - bg[2]};
+  const double a[3] = {araw[0] - ba[0], araw[1] - ba[1], araw[2] - ba[2]};
+  const double wd[3] = {w[0] * dt, w[1] * dt, w[2] * dt};
+  double G0[9], G1[9], G2[9], RG1[9], RG2[9], Rn[9], t[3];
+  gamma_func(wd, 0, G0); gamma_func(wd, 1, G1); gamma_func(wd, 2, G2);
+  mat3_mul(Rh, G0, Rn); mat3_mul(Rh, G1, RG1); mat3_mul(Rh, G2, RG2);
+  const double* g = prm.g;
+  double vn[3], pn[3];
+  mat3_vec(RG1, a, t);
+  for (int i = 0; i < 3; ++i) vn[i] = vh[i] + g[i] * dt + t[i] * dt;
+  mat3_vec(RG2, a, t);
+  for (int i = 0; i < 3; ++i) pn[i] = ph[i] + vh[i] * dt + 0.5 * g[i] * dt * dt + t[i] * dt * dt;
+  for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  for (int i = 0; i < 3; ++i) { p[i] = pn[i]; v[i] = vn[i]; }
+  if (idx_fs >= 0)  // ImuPropagator.cpp:139-148
+    for (int i = 0; i < 4; ++i) if (idx_cb[i] >= 0) X[33 + i] += dt * X[33 + 4];
+  // Phi blocks (ImuPropagator.cpp:150-161)
+  double Sg[9];
+  skew3(g, Sg);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+    sPhi[(3 + r) * 15 + c] = 0.5 * Sg[3 * r + c] * dt * dt;
+    sPhi[(6 + r) * 15 + c] = Sg[3 * r + c] * dt;
+    sPhi[r * 15 + 9 + c] = -RG1[3 * r + c] * dt;
+    sPhi[(6 + r) * 15 + 12 + c] = -RG1[3 * r + c] * dt;
+    sPhi[(3 + r) * 15 + 12 + c] = -RG2[3 * r + c] * dt * dt;
+  }
+  for (int r = 0; r < 3; ++r) sPhi[(3 + r) * 15 + 6 + r] = dt;
+  double Ps1[9], Ps2[9], A1[9], A2[9];
+  psi_func(w, a, dt, 1, Ps1); psi_func(w, a, dt, 2, Ps2);
+  skew3(vn, S); mat3_mul(S, RG1, A1); mat3_mul(Rh, Ps1, A2);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) sPhi[(6 + r) * 15 + 9 + c] = -A1[3 * r + c] * dt + A2[3 * r + c];
+  skew3(pn, S); mat3_mul(S, RG1, A1); mat3_mul(Rh, Ps2, A2);
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) sPhi[(3 + r) * 15 + 9 + c] = -A1[3 * r + c] * dt + A2[3 * r + c];
+}
+
+__global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, N = a.N, ld = a.ld, tid = threadIdx.x;
+  double* Pb = a.P + (size_t)b * ld * ld;
+  double* Xb = a.X ? a.X + (size_t)b * a.xsize : nullptr;
+  __shared__ int cidx[kMaxStrip];
+  __shared__ int s_nC, s_nS, s_has_fs;
+  __shared__ double sPhi[225], sG[180], sT[kMaxStrip * kMaxStrip], sQ[kMaxStrip * kMaxStrip], sM[15 * 12];
+  __shared__ double sBlk[kMaxStrip * kMaxStrip];
+  __shared__ double s_dt;
+  if (tid == 0) {
+    int n = 0;
+    for (int i = 0; i < 15; ++i) cidx[n++] = i;
+    s_has_fs = 0;
+    if (a.enable_gnss)
+      for (int i = 0; i < 4; ++i) if (a.idx_cb[i] >= 0) cidx[n++] = a.idx_cb[i];
+    s_nC = n;
+    if (a.enable_gnss && a.idx_fs >= 0) { cidx[n++] = a.idx_fs; s_has_fs = 1; }
+    s_nS = n;
+  }
+  __syncthreads();
+  const int nC = s_nC, nS = s_nS;
+  const bool has_fs = s_has_fs != 0;
+  double* W = sm;  // nS x N row-major: W[r*N + j] = P[cidx[r], j]
+  for (int t = tid; t < nS * N; t += blockDim.x) {
+    const int r = t / N, j = t % N;
+    W[t] = Pb[j + (size_t)cidx[r] * ld];  // P symmetric: row cidx[r] == column cidx[r] (coalesced read)
+  }
+  __syncthreads();
+  for (int step = 0; step < a.n_steps; ++step) {
+    if (tid == 0) {
+      double dt;
+      if (a.Phi) {
+        dt = a.dt[b];
+        const double* Ph = a.Phi + (size_t)b * 225;
+        const double* Gg = a.G + (size_t)b * 180;
+        for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) sPhi[r * 15 + c] = Ph[r + 15 * c];
+        const double sg[4] = {a.prm.noise_g, a.prm.noise_a, a.prm.noise_bg, a.prm.noise_ba};
+        for (int r = 0; r < 15; ++r) for (int c = 0; c < 12; ++c) sG[r * 12 + c] = Gg[r + 15 * c] * sg[c / 3];
+      } else {
+        dt = a.dt[(size_t)b * a.n_steps + step];
+        if (dt >= 1e-6)  // ImuPropagator.cpp:262
+          imu_step_mean(Xb, a.gyro + ((size_t)b * a.n_steps + step) * 3, a.accel + ((size_t)b * a.n_steps + step) * 3,
+                        dt, a.prm, a.idx_cb, (a.enable_gnss ? a.idx_fs : -1), sPhi, sG);
+      }
+      s_dt = dt;
+    }
+    __syncthreads();
+    const double dt = s_dt;
+    if (!a.Phi && dt < 1e-6) { __syncthreads(); continue; }  // uniform
+    // small transition T (nC x nS): [Phi 0; 0 I] + dt on (cb, fs)
+    for (int t = tid; t < nC * nS; t += blockDim.x) {
+      const int r = t / nS, c = t % nS;
+      double val = (r == c) ? 1.0 : 0.0;
+      if (r < 15 && c < 15) val = sPhi[r * 15 + c];
+      else if (r >= 15 && c == nS - 1 && has_fs) val = dt;
+      sT[r * kMaxStrip + c] = val;
+    }
+    // M = Phi * Gs (15 x 12)
+    for (int t = tid; t < 180; t += blockDim.x) {
+      const int r = t / 12, c = t % 12;
+      double acc = 0.0;
+      for (int k = 0; k < 15; ++k) acc = fma(sPhi[r * 15 + k], sG[k * 12 + c], acc);
+      sM[t] = acc;
+    }
+    __syncthreads();
+    // Q block (nS x nS): dt * M M^T on the IMU part (StateManager.cpp:97) + clock terms (:99-116)
+    for (int t = tid; t < nS * nS; t += blockDim.x) {
+      const int r = t / nS, c = t % nS;
+      double q = 0.0;
+      if (r < 15 && c < 15) {
+        for (int k = 0; k < 12; ++k) q = fma(sM[r * 12 + k], sM[c * 12 + k], q);
+        q *= dt;
+      } else if (a.enable_gnss && r >= 15 && c >= 15) {
+        const bool rf = has_fs && (r == nS - 1), cf = has_fs && (c == nS - 1);
+        const double rw2 = a.prm.noise_cb_rw * a.prm.noise_cb_rw;
+        if (!rf && !cf) q = dt * a.prm.noise_cb * a.prm.noise_cb + dt * dt * dt * rw2;
+        else if (rf && cf) q = dt * rw2;
+        else q = dt * dt * rw2;
+      }
+      sQ[r * kMaxStrip + c] = q;
+    }
+    // (1) column update on the strip: W1[r, cidx[c]] = sum_k W[r, cidx[k]] T[c,k]   (c < nC)
+    for (int t = tid; t < nS * nC; t += blockDim.x) {
+      const int r = t / nC, c = t % nC;
+      double acc = 0.0;
+      for (int k = 0; k < nS; ++k) acc = fma(W[r * N + cidx[k]], sT[c * kMaxStrip + k], acc);
+      sBlk[r * kMaxStrip + c] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < nS * nC; t += blockDim.x) {
+      const int r = t / nC, c = t % nC;
+      W[r * N + cidx[c]] = sBlk[r * kMaxStrip + c];
+    }
+    __syncthreads();
+    // (2) row update: W2[c, j] = sum_k T[c,k] W1[k, j]   (c < nC), one thread per column j
+    for (int j = tid; j < N; j += blockDim.x) {
+      double col[kMaxStrip];
+      for (int k = 0; k < nS; ++k) col[k] = W[k * N + j];
+      for (int c = 0; c < nC; ++c) {
+        double acc = 0.0;
+        for (int k = 0; k < nS; ++k) acc = fma(sT[c * kMaxStrip + k], col[k], acc);
+        W[c * N + j] = acc;
+      }
+    }
+    __syncthreads();
+    // (3) + Q and (4) symmetrise the strip x strip block (StateManager.cpp:118)
+    for (int t = tid; t < nS * nS; t += blockDim.x) {
+      const int r = t / nS, c = t % nS;
+      sBlk[r * kMaxStrip + c] = 0.5 * ((W[r * N + cidx[c]] + sQ[r * kMaxStrip + c]) +
+                                       (W[c * N + cidx[r]] + sQ[c * kMaxStrip + r]));
+    }
+    __syncthreads();
+    for (int t = tid; t < nS * nS; t += blockDim.x) {
+      const int r = t / nS, c = t % nS;
+      W[r * N + cidx[c]] = sBlk[r * kMaxStrip + c];
+    }
+    __syncthreads();
+  }
+  // write back rows and mirrored columns
+  for (int t = tid; t < nS * N; t += blockDim.x) {
+    const int r = t / N, j = t % N;
+    const double val = W[t];
+    Pb[j + (size_t)cidx[r] * ld] = val;
+    Pb[cidx[r] + (size_t)j * ld] = val;
+  }
+}
+
+}  // namespace
+
+void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const double* accel, const double* dt,
+                          const double* Phi, const double* G) {
+  PropArgs a;
+  a.P = h->Pc(); a.ld = h->ld; a.N = h->N;
+  a.X = h->Xc(); a.xsize = h->xsize;
+  a.n_steps = n_steps;
+  a.gyro = gyro; a.accel = accel; a.dt = dt; a.Phi = Phi; a.G = G;
+  a.prm = h->params;
+  IgvLayout L = h->layout();
+  for (int i = 0; i < 4; ++i) a.idx_cb[i] = L.idx_gnss[i];
+  a.idx_fs = L.idx_gnss[IGV_GNSS_FS];
+  a.enable_gnss = 1;
+  const size_t smem = sizeof(double) * kMaxStrip * h->N;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  k_propagate<<<h->B, 128, smem, h->stream>>>(a);
+  h->launches++;
+}

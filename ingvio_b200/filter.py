@@ -1,0 +1,392 @@
+"""Host-side mirror of the reference's filter interface for a batch of sequences, on top of the C-ABI.
+
+Method names follow the reference (`StateManager::propagateStateCov`, `augmentSlidingWindowPose`,
+`marginalize`, `ekfUpdate`, `getFullCov`, `getMarginalCov`, `boxPlus`, `addGNSSVariable`, ...:
+/root/reference/ingvio_estimator/src/StateManager.h:38-127) with snake_case spelling; a variable is
+addressed by its (idx, size) exactly as `Type::idx()/size()` (VecState.h:32-54).
+
+Array arguments may be numpy arrays (HOST pointer mode: copied inside the call) or torch CUDA tensors
+(DEVICE pointer mode: consumed in place). torch is used only for device memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import IgvError
+from .frames import FramePacket
+
+
+def chi2_table(max_dof=150, thres=0.95):
+    """UpdateBase::setChiSquaredTable (Update.cpp:27-34): boost quantile -> scipy.stats.chi2.ppf."""
+    from scipy.stats import chi2
+    return np.array([chi2.ppf(thres, d) for d in range(1, max_dof + 1)], dtype=np.float64)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _Arg:
+    """Keeps the backing array alive and yields a void* for ctypes."""
+
+    def __init__(self, x, dtype):
+        self.is_dev = False
+        if x is None:
+            self.keep, self.ptr = None, None
+            return
+        if _is_torch(x):
+            import torch
+            tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8}[dtype]
+            if x.dtype != tdt or not x.is_contiguous():
+                x = x.to(tdt).contiguous()
+            self.keep = x
+            self.ptr = C.c_void_p(x.data_ptr())
+            self.is_dev = x.is_cuda
+        else:
+            a = np.ascontiguousarray(x, dtype=dtype)
+            self.keep = a
+            self.ptr = C.c_void_p(a.ctypes.data)
+
+
+class BatchFilter:
+    """B independent invariant-EKF filters on one GPU (B = 1: drop-in for the reference's single State)."""
+
+    def __init__(self, batch, max_clones, max_feats, max_sats, stereo=False, device=0, stream=None,
+                 max_dim=None, noise=None, gravity=(0.0, 0.0, -9.8), T_cl2cr=None, chi2_max_dof=150,
+                 chi2_thres=0.95):
+        self.lib = capi.load()
+        self.B = batch
+        self.stereo = bool(stereo)
+        self.rho = 4 if stereo else 2
+        max_dim = max_dim or (21 + 6 + 6 * max_clones)
+        cfg = capi.igv_config(batch, max_dim, max_clones, max_feats, max_sats, int(self.stereo), device,
+                              C.c_void_p(stream) if stream else None)
+        self.h = C.c_void_p()
+        st = self.lib.igv_create(C.byref(cfg), C.byref(self.h))
+        if st != capi.IGV_OK:
+            raise IgvError(st, "igv_create failed (is a CUDA device visible?)")
+        self.max_clones, self.max_feats, self.max_sats = max_clones, max_feats, max_sats
+        p = capi.igv_params()
+        nz = dict(noise_g=0.004, noise_a=0.08, noise_bg=0.0002, noise_ba=0.008, noise_clockbias=0.2,
+                  noise_cb_rw=0.2)
+        nz.update(noise or {})
+        for k, v in nz.items():
+            setattr(p, k, v)
+        p.gravity = (C.c_double * 3)(*gravity)
+        Rc, pc = (np.eye(3), np.zeros(3)) if T_cl2cr is None else T_cl2cr
+        p.T_cl2cr_R = (C.c_double * 9)(*np.asarray(Rc, float).reshape(9))
+        p.T_cl2cr_p = (C.c_double * 3)(*np.asarray(pc, float).reshape(3))
+        self._ck(self.lib.igv_set_params(self.h, C.byref(p)))
+        tab = chi2_table(max(chi2_max_dof, 16), chi2_thres)
+        self._ck(self.lib.igv_set_chi2_table(self.h, tab.ctypes.data_as(capi.c_dp), len(tab)))
+        self._mode = capi.IGV_PTR_HOST
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    def _ck(self, st):
+        if st != capi.IGV_OK:
+            raise IgvError(st, self.lib.igv_last_error(self.h).decode())
+
+    def _set_mode(self, args):
+        dev = [a.is_dev for a in args if a.ptr is not None]
+        mode = capi.IGV_PTR_DEVICE if (dev and all(dev)) else capi.IGV_PTR_HOST
+        if dev and any(dev) and not all(dev):
+            raise ValueError("mixing host and device arrays in one call")
+        if mode != self._mode:
+            self._ck(self.lib.igv_set_pointer_mode(self.h, mode))
+            self._mode = mode
+        return mode
+
+    def close(self):
+        if self.h:
+            self.lib.igv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._ck(self.lib.igv_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.igv_launch_count(self.h))
+
+    # ---- layout (Type::idx / size) ---------------------------------------------------------------
+    def curr_cov_size(self):
+        return self.lib.igv_dim(self.h)
+
+    def curr_err_variable_size(self):
+        return self.lib.igv_num_variables(self.h)
+
+    def num_clones(self):
+        return self.lib.igv_num_clones(self.h)
+
+    def clone_idx(self, slot):
+        return self.lib.igv_clone_idx(self.h, slot)
+
+    def gnss_idx(self, gtype):
+        return self.lib.igv_gnss_idx(self.h, gtype)
+
+    # ---- State::initStateAndCov ------------------------------------------------------------------
+    def init_state_and_cov(self, R_i2w, p, v, bg, ba, R_ext, p_ext, cov_diag21):
+        a = [_Arg(x, np.float64) for x in (R_i2w, p, v, bg, ba, R_ext, p_ext)]
+        self._set_mode(a)
+        d = np.ascontiguousarray(cov_diag21, dtype=np.float64)
+        assert d.shape == (21,)
+        self._ck(self.lib.igv_state_init(self.h, *[x.ptr for x in a], d.ctypes.data_as(capi.c_dp)))
+
+    def get_state(self):
+        n = self.lib.igv_state_size(self.h)
+        out = np.empty((self.B, n))
+        self._set_mode([_Arg(out, np.float64)])
+        self._ck(self.lib.igv_state_get(self.h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def set_state(self, x):
+        a = _Arg(x, np.float64)
+        self._set_mode([a])
+        self._ck(self.lib.igv_state_set(self.h, a.ptr))
+
+    # ---- StateManager statics --------------------------------------------------------------------
+    def get_full_cov(self):
+        n = self.curr_cov_size()
+        out = np.empty((self.B, n, n))
+        self._set_mode([_Arg(out, np.float64)])
+        self._ck(self.lib.igv_cov_get(self.h, C.c_void_p(out.ctypes.data), n))
+        return out  # symmetric: column-major == row-major
+
+    def set_full_cov(self, P):
+        P = np.ascontiguousarray(np.swapaxes(np.asarray(P, float), -1, -2))  # to column-major
+        n = self.curr_cov_size()
+        assert P.shape == (self.B, n, n)
+        a = _Arg(P, np.float64)
+        self._set_mode([a])
+        self._ck(self.lib.igv_cov_set(self.h, a.ptr, n))
+
+    @staticmethod
+    def _blocks(var_order):
+        idx = (C.c_int * len(var_order))(*[int(v[0]) for v in var_order])
+        size = (C.c_int * len(var_order))(*[int(v[1]) for v in var_order])
+        return idx, size, sum(int(v[1]) for v in var_order)
+
+    def get_marginal_cov(self, var_order):
+        idx, size, n = self._blocks(var_order)
+        out = np.empty((self.B, n, n))
+        self._set_mode([_Arg(out, np.float64)])
+        self._ck(self.lib.igv_cov_get_blocks(self.h, len(var_order), idx, size, C.c_void_p(out.ctypes.data)))
+        return np.swapaxes(out, -1, -2).copy()
+
+    def add_gnss_variable(self, gtype, value, cov):
+        v = np.broadcast_to(np.asarray(value, float), (self.B,)).copy()
+        a = _Arg(v, np.float64)
+        self._set_mode([a])
+        self._ck(self.lib.igv_add_gnss_variable(self.h, gtype, a.ptr, float(cov)))
+
+    def marg_gnss_variable(self, gtype):
+        self._ck(self.lib.igv_marg_gnss_variable(self.h, gtype))
+
+    def add_variable_independent(self, size, cov_block):
+        c = np.asfortranarray(np.asarray(cov_block, float).reshape(size, size))
+        self._ck(self.lib.igv_add_variable_independent(self.h, size, c.ctypes.data_as(capi.c_dp)))
+
+    def marginalize(self, idx):
+        self._ck(self.lib.igv_marginalize(self.h, idx))
+
+    def marg_sliding_window_pose(self, slot=0):
+        self._ck(self.lib.igv_marginalize_clone(self.h, slot))
+
+    def propagate_state_cov(self, Phi, G, dt):
+        """Phi: (B,15,15), G: (B,15,12) in the usual row/col meaning; dt: (B,)."""
+        if not _is_torch(Phi):
+            Phi = np.ascontiguousarray(np.swapaxes(np.asarray(Phi, float), -1, -2))   # column-major
+            G = np.ascontiguousarray(np.swapaxes(np.asarray(G, float), -1, -2))
+        a = [_Arg(Phi, np.float64), _Arg(G, np.float64), _Arg(dt, np.float64)]
+        self._set_mode(a)
+        self._ck(self.lib.igv_propagate_cov(self.h, a[0].ptr, a[1].ptr, a[2].ptr))
+
+    def propagate_imu(self, gyro, accel, dt):
+        a = [_Arg(gyro, np.float64), _Arg(accel, np.float64), _Arg(dt, np.float64)]
+        self._set_mode(a)
+        n_steps = int(a[2].keep.shape[-1])
+        self._ck(self.lib.igv_propagate_imu(self.h, n_steps, a[0].ptr, a[1].ptr, a[2].ptr))
+
+    def augment_sliding_window_pose(self):
+        self._ck(self.lib.igv_augment_clone(self.h))
+
+    def augment_sliding_window_pose_cov(self, R_i2w, clone_R=None, clone_p=None):
+        a = [_Arg(R_i2w, np.float64), _Arg(clone_R, np.float64), _Arg(clone_p, np.float64)]
+        self._set_mode(a)
+        self._ck(self.lib.igv_augment_clone_cov(self.h, a[0].ptr, a[1].ptr, a[2].ptr))
+
+    def _r_arg(self, R, rows):
+        R = np.asarray(R, float)
+        if R.ndim == 0 or R.shape == (self.B,):
+            return np.broadcast_to(R, (self.B,)).copy(), capi.R_ISO
+        if R.shape[-1] == rows and (R.ndim == 1 or R.shape == (self.B, rows)):
+            return np.broadcast_to(R, (self.B, rows)).copy(), capi.R_DIAG
+        R = np.broadcast_to(R, (self.B, rows, rows))
+        return np.ascontiguousarray(np.swapaxes(R, -1, -2)), capi.R_FULL
+
+    def ekf_update(self, var_order, H, res, R, return_dx=True):
+        """StateManager::ekfUpdate. H: (B,rows,n) row/col meaning; res: (B,rows); R: scalar sigma^2,
+        (rows,) diagonal or (rows,rows) dense (optionally with a leading batch dim)."""
+        H = np.asarray(H, float)
+        rows, n = H.shape[-2], H.shape[-1]
+        Hc = np.ascontiguousarray(np.swapaxes(np.broadcast_to(H, (self.B, rows, n)), -1, -2))
+        idx, size, nn = self._blocks(var_order)
+        assert nn == n
+        Rv, kind = self._r_arg(R, rows)
+        dx = np.zeros((self.B, self.curr_cov_size())) if return_dx else None
+        a = [_Arg(Hc, np.float64), _Arg(np.broadcast_to(np.asarray(res, float), (self.B, rows)).copy(), np.float64),
+             _Arg(Rv, np.float64)]
+        self._set_mode(a)
+        self._ck(self.lib.igv_ekf_update(self.h, len(var_order), idx, size, rows, a[0].ptr, rows, a[1].ptr, a[2].ptr,
+                                         kind, C.c_void_p(dx.ctypes.data) if return_dx else None))
+        return dx
+
+    def whiten_residual(self, var_order, H, res, R):
+        """UpdateBase::whitenResidual -> gamma (B,)."""
+        H = np.asarray(H, float)
+        rows, n = H.shape[-2], H.shape[-1]
+        Hc = np.ascontiguousarray(np.swapaxes(np.broadcast_to(H, (self.B, rows, n)), -1, -2))
+        idx, size, _ = self._blocks(var_order)
+        Rv, kind = self._r_arg(R, rows)
+        g = np.zeros(self.B)
+        a = [_Arg(Hc, np.float64), _Arg(np.broadcast_to(np.asarray(res, float), (self.B, rows)).copy(), np.float64),
+             _Arg(Rv, np.float64)]
+        self._set_mode(a)
+        self._ck(self.lib.igv_chi2_whiten(self.h, len(var_order), idx, size, rows, a[0].ptr, rows, a[1].ptr, a[2].ptr,
+                                          kind, C.c_void_p(g.ctypes.data)))
+        return g
+
+    def box_plus(self, dx):
+        a = _Arg(dx, np.float64)
+        self._set_mode([a])
+        self._ck(self.lib.igv_box_plus(self.h, a.ptr))
+
+    def add_variable_delayed(self, gtype, value, var_old_order, H_old, H_new, res, noise_iso, chi2_mult=0.95,
+                             do_chi2=True, prior_cov_if_rejected=1.0):
+        H_old = np.asarray(H_old, float)
+        rows, n = H_old.shape[-2], H_old.shape[-1]
+        Ho = np.ascontiguousarray(np.swapaxes(np.broadcast_to(H_old, (self.B, rows, n)), -1, -2))
+        Hn = np.broadcast_to(np.asarray(H_new, float).reshape(-1, rows), (self.B, rows)).copy()
+        rr = np.broadcast_to(np.asarray(res, float), (self.B, rows)).copy()
+        val = np.broadcast_to(np.asarray(value, float), (self.B,)).copy()
+        idx, size, nn = self._blocks(var_old_order)
+        assert nn == n
+        acc = np.zeros(self.B, dtype=np.int32)
+        a = [_Arg(Ho, np.float64), _Arg(Hn, np.float64), _Arg(rr, np.float64), _Arg(val, np.float64)]
+        self._set_mode(a)
+        self._ck(self.lib.igv_add_variable_delayed(self.h, gtype, a[3].ptr, len(var_old_order), idx, size, rows,
+                                                   a[0].ptr, a[1].ptr, a[2].ptr, float(noise_iso), float(chi2_mult),
+                                                   int(do_chi2), float(prior_cov_if_rejected),
+                                                   C.c_void_p(acc.ctypes.data)))
+        return acc.astype(bool)
+
+    def replace_var_linear(self, target, dependence_order, H):
+        H = np.asarray(H, float)
+        ts, n = H.shape[-2], H.shape[-1]
+        Hc = np.ascontiguousarray(np.swapaxes(np.broadcast_to(H, (self.B, ts, n)), -1, -2))
+        idx, size, nn = self._blocks(dependence_order)
+        assert nn == n and ts == target[1]
+        a = _Arg(Hc, np.float64)
+        self._set_mode([a])
+        self._ck(self.lib.igv_replace_var_linear(self.h, target[0], target[1], len(dependence_order), idx, size, a.ptr))
+
+    # ---- fused updaters ------------------------------------------------------------------------------
+    def msckf_update(self, mode, pf_w, anchor_slot, obs, obs_mask, chi2_dof, noise, max_valid=0, want_dx=False,
+                     want_gamma=False, want_accepted=False):
+        """RemoveLostUpdate / KeyframeUpdate / SwMargUpdate ::updateState* after track selection."""
+        a = [_Arg(pf_w, np.float64), _Arg(anchor_slot, np.int32), _Arg(obs, np.float64), _Arg(obs_mask, np.uint8),
+             _Arg(chi2_dof, np.int32)]
+        mode_ptr = self._set_mode(a)
+        F = int(a[0].keep.shape[1])
+        SW = int(a[3].keep.shape[2])
+        args = capi.igv_msckf_args()
+        args.mode = mode
+        args.n_feats = F
+        args.pf_w, args.anchor_slot, args.obs, args.obs_mask, args.chi2_dof = [x.ptr for x in a]
+        args.obs_slots = SW
+        args.noise = float(noise)
+        args.max_valid = int(max_valid)
+        outs = {}
+        host = mode_ptr == capi.IGV_PTR_HOST
+        if want_dx and host:
+            outs["dx"] = np.zeros((self.B, self.curr_cov_size()))
+            args.dx_out = C.c_void_p(outs["dx"].ctypes.data)
+        if want_gamma and host:
+            outs["gamma"] = np.zeros((self.B, F))
+            args.gamma_out = C.c_void_p(outs["gamma"].ctypes.data)
+        if want_accepted and host:
+            outs["accepted"] = np.zeros(self.B, dtype=np.int32)
+            args.n_accepted_out = C.c_void_p(outs["accepted"].ctypes.data)
+        self._ck(self.lib.igv_msckf_update(self.h, C.byref(args)))
+        return outs
+
+    def gnss_update(self, unit, res_pos, res_vel, sigma_psr, sigma_dopp, sys, R_enu2ecef, is_adjust_yof=0,
+                    chi2_test=0, strong_reject=1, want_dx=False):
+        """GnssUpdate::updateTrackedSys from the psr_res/dopp_res boundary."""
+        a = [_Arg(unit, np.float64), _Arg(res_pos, np.float64), _Arg(res_vel, np.float64),
+             _Arg(sigma_psr, np.float64), _Arg(sigma_dopp, np.float64), _Arg(sys, np.int32),
+             _Arg(R_enu2ecef, np.float64)]
+        mode_ptr = self._set_mode(a)
+        args = capi.igv_gnss_args()
+        args.n_sats = int(a[1].keep.shape[1])
+        (args.unit, args.res_pos, args.res_vel, args.sigma_psr, args.sigma_dopp, args.sys,
+         args.R_enu2ecef) = [x.ptr for x in a]
+        args.is_adjust_yof, args.chi2_test, args.strong_reject = int(is_adjust_yof), int(chi2_test), int(strong_reject)
+        dx = None
+        if want_dx and mode_ptr == capi.IGV_PTR_HOST:
+            dx = np.zeros((self.B, self.curr_cov_size()))
+            args.dx_out = C.c_void_p(dx.ctypes.data)
+        self._ck(self.lib.igv_gnss_update(self.h, C.byref(args)))
+        return dx
+
+    # ---- one frame cycle (IngvioFilter.cpp:143-231 order) ----------------------------------------------
+    def step(self, fr: FramePacket, noise=0.12, psr_amp=1.0, dopp_amp=1.0, is_adjust_yof=0, gnss_chi2_test=0,
+             gnss_strong_reject=1, want=False):
+        out = {}
+        self.propagate_imu(fr.gyro, fr.accel, fr.dt)
+        self.augment_sliding_window_pose()
+        if fr.visual_mode is not None and fr.pf_w.shape[1] > 0:
+            ncl = self.num_clones()
+            mask = fr.obs_mask
+            if fr.visual_mode == "all_obs":
+                mode = capi.VIS_ALL_OBS
+                dof = fr.obs_total.astype(np.int32) - 1                      # RemoveLostUpdate.cpp:95-96
+                max_valid = fr.max_valid
+            else:
+                mode = capi.VIS_SELECTED
+                sel = np.zeros(mask.shape[-1], dtype=np.uint8)
+                sel[list(fr.selected_slots)] = 1
+                mask = mask * sel
+                d = 2 if fr.visual_mode == "keyframe" else len(fr.selected_slots) - 1
+                dof = np.full(mask.shape[:2], d, dtype=np.int32)
+                max_valid = 0
+            out["visual"] = self.msckf_update(mode, fr.pf_w, fr.anchor_slot, fr.obs, mask, dof, noise, max_valid,
+                                              want_dx=want, want_gamma=want, want_accepted=want)
+            assert ncl <= mask.shape[-1]
+        for s in sorted(fr.marg_slots, reverse=True):
+            self.marg_sliding_window_pose(s)
+        if fr.gnss is not None:
+            g = fr.gnss
+            out["gnss_dx"] = self.gnss_update(g.unit, g.res_pos, g.res_vel, g.sigma_psr(psr_amp), g.sigma_dopp(dopp_amp),
+                                              g.sys, g.R_enu2ecef, is_adjust_yof, gnss_chi2_test, gnss_strong_reject,
+                                              want_dx=want)
+        return out
+
+    def flags(self, clear=True):
+        f = np.zeros(self.B, dtype=np.int32)
+        self._set_mode([_Arg(f, np.int32)])
+        self._ck(self.lib.igv_get_flags(self.h, C.c_void_p(f.ctypes.data), int(clear)))
+        return f
+
+    def cov_trace(self):
+        t = np.zeros(self.B)
+        self._set_mode([_Arg(t, np.float64)])
+        self._ck(self.lib.igv_cov_trace(self.h, C.c_void_p(t.ctypes.data)))
+        return t

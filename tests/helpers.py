@@ -1,0 +1,108 @@
+"""Shared helpers for the parity tests: build an oracle filter and a CUDA BatchFilter in the same state."""
+import numpy as np
+
+import ingvio_oracle as o
+from ingvio_oracle import BDS, FS, GAL, GLO, GPS, YOF, StateManager as SM
+
+from ingvio_b200 import synth
+from ingvio_b200.synth import WORKLOADS, SyntheticStream
+
+
+def rand_rot(rng):
+    q = rng.standard_normal(4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def filter_params(wl, **kw):
+    fp = o.FilterParams(max_sw_clones=wl.sw, enable_gnss=1 if wl.sats > 0 else 0, cam_nums=2 if wl.stereo else 1)
+    fp.T_cl2i_R, fp.T_cl2i_p = synth.R_C2I.copy(), synth.P_C2I.copy()
+    fp.T_cl2cr_R, fp.T_cl2cr_p = synth.R_CL2CR.copy(), synth.P_CL2CR.copy()
+    for k, v in kw.items():
+        setattr(fp, k, v)
+    return fp
+
+
+GNSS_INIT = ((GPS, 1.0, 4.0), (GLO, -2.0, 4.0), (GAL, 0.5, 4.0), (BDS, 3.0, 4.0), (FS, 0.1, 1.0), (YOF, 0.3, 0.015 ** 2))
+
+
+def make_oracles(wl, stream, fp, with_gnss=True):
+    """One OracleFilter per sequence, initialised like State::initStateAndCov + addGNSSVariable."""
+    ini = stream.initial_state()
+    fs = []
+    for b in range(stream.B):
+        f = o.OracleFilter(fp, stereo=wl.stereo, max_valid_ids=wl.feats)
+        f.init(0.0, ini["R"][b], ini["p"][b], ini["v"][b], ini["bg"][b], ini["ba"][b])
+        if with_gnss and wl.sats > 0:
+            for g, val, cov in GNSS_INIT:
+                SM.add_gnss_variable(f.state, g, val, cov)
+        fs.append(f)
+    return fs
+
+
+def cov_diag21(fp):
+    sp = o.StateParams(fp)
+    return np.array([sp.init_cov_rot] * 3 + [sp.init_cov_pos] * 3 + [sp.init_cov_vel] * 3 + [sp.init_cov_bg] * 3 +
+                    [sp.init_cov_ba] * 3 + [sp.init_cov_ext_rot] * 3 + [sp.init_cov_ext_pos] * 3) ** 2.0
+
+
+def make_gpu(wl, stream, fp, with_gnss=True, max_feats=None, max_clones=None):
+    from ingvio_b200.filter import BatchFilter
+    sp = o.StateParams(fp)
+    B = stream.B
+    g = BatchFilter(B, max_clones or wl.sw, max_feats or max(wl.feats, 1), max(wl.sats, 1), stereo=wl.stereo,
+                    noise=dict(noise_g=sp.noise_g, noise_a=sp.noise_a, noise_bg=sp.noise_bg, noise_ba=sp.noise_ba,
+                               noise_clockbias=sp.noise_clockbias, noise_cb_rw=sp.noise_cb_rw),
+                    gravity=(0.0, 0.0, -fp.gravity_norm), T_cl2cr=(fp.T_cl2cr_R, fp.T_cl2cr_p),
+                    chi2_max_dof=max(fp.chi2_max_dof, 160), chi2_thres=fp.chi2_thres)
+    ini = stream.initial_state()
+    g.init_state_and_cov(ini["R"].reshape(B, 9), ini["p"], ini["v"], ini["bg"], ini["ba"],
+                         np.tile(fp.T_cl2i_R.reshape(1, 9), (B, 1)), np.tile(fp.T_cl2i_p, (B, 1)), cov_diag21(fp))
+    if with_gnss and wl.sats > 0:
+        for gt, val, cov in GNSS_INIT:
+            g.add_gnss_variable(gt, val, cov)
+    return g
+
+
+def oracle_packed_state(f, max_clones):
+    """The packed mean of include/ingvio_b200.h for one oracle filter."""
+    st = f.state
+    x = np.zeros(39 + 12 * max_clones)
+    e = st.extended_pose
+    x[0:9] = e.rot.reshape(9)
+    x[9:12], x[12:15] = e.vec1, e.vec2
+    x[15:18], x[18:21] = st.bg.value(), st.ba.value()
+    x[21:30] = st.camleft_imu_extrinsics.rot.reshape(9)
+    x[30:33] = st.camleft_imu_extrinsics.vec
+    for gt in range(6):
+        if gt in st.gnss:
+            x[33 + gt] = st.gnss[gt].value()
+    for s, t in enumerate(st.sw_times()):
+        c = st.sw_camleft_poses[t]
+        x[39 + 12 * s:39 + 12 * s + 9] = c.rot.reshape(9)
+        x[39 + 12 * s + 9:39 + 12 * s + 12] = c.vec
+    return x
+
+
+def assert_state_close(g, oracles, max_clones, tol_P=1e-8, tol_x=1e-9, what=""):
+    P = g.get_full_cov()
+    X = g.get_state()
+    for b, f in enumerate(oracles):
+        Po = f.cov()
+        assert P[b].shape == Po.shape, (what, P[b].shape, Po.shape)
+        err = np.linalg.norm(P[b] - Po) / max(1.0, np.linalg.norm(Po))
+        assert err <= tol_P, f"{what}: seq {b}: |dP|_F/max(1,|P|_F) = {err:.3e}"
+        xo = oracle_packed_state(f, max_clones)
+        n_used = 39 + 12 * len(f.state.sw_camleft_poses)
+        ex = np.max(np.abs(X[b, :n_used] - xo[:n_used]) / np.maximum(1.0, np.abs(xo[:n_used])))
+        assert ex <= tol_x, f"{what}: seq {b}: state mismatch {ex:.3e}"
+
+
+def gstep(g, fr, fp, want=False):
+    """BatchFilter.step with the updater options of `fp` (IngvioParams)."""
+    return g.step(fr, noise=fp.visual_noise, psr_amp=fp.psr_noise_amp, dopp_amp=fp.dopp_noise_amp,
+                  is_adjust_yof=fp.is_adjust_yof, gnss_chi2_test=fp.gnss_chi2_test,
+                  gnss_strong_reject=fp.gnss_strong_reject, want=want)
