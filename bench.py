@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- EKF updates/sec (propagate + MSCKF visual + GNSS) on B200, BASELINE.json's metric.
+
+One "step" = one frame cycle (10 IMU propagation steps, clone augmentation, MSCKF visual update over
+F tracks seen in all SW clones, marginalisation of the oldest clone, GNSS pseudo-range/Doppler update;
+call order of IngvioFilter::callbackMonoFrame, /root/reference/ingvio_estimator/src/IngvioFilter.cpp:143-231)
+for EVERY one of the B independent sequences resident on each GPU. value = N_gpus * B * K / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload c2]
+    python bench.py --impl reference ...       # CPU port of the reference path on all host cores
+
+Timing: CUDA events on the handle's stream, barrier + synchronize on both sides, max over ranks.
+`value`: inputs resident in HBM (device-pointer mode of the C-ABI). `e2e`: the same frames from pinned
+HOST buffers through the same C-ABI (host-pointer mode: H2D copies inside the calls) plus a D2H read of
+the per-sequence mean and trace(P) every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+from ingvio_b200.synth import WORKLOADS, SyntheticStream, R_C2I, P_C2I, R_CL2CR, P_CL2CR
+
+METRIC = "ekf_updates_per_sec"
+UNIT = "updates/s"
+VISUAL_NOISE = 0.12
+NOISE = dict(noise_g=0.004, noise_a=0.08, noise_bg=0.0002, noise_ba=0.008, noise_clockbias=0.2, noise_cb_rw=0.2)
+GNSS_INIT = ((0, 1.0, 4.0), (1, -2.0, 4.0), (2, 0.5, 4.0), (3, 3.0, 4.0), (4, 0.1, 1.0), (5, 0.3, 0.015 ** 2))
+COV_DIAG21 = np.array([0.0] * 3 + [0.0] * 3 + [0.25] * 3 + [0.01] * 3 + [0.01] * 3 + [1.8e-2] * 3 + [2e-3] * 3) ** 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1184, help="independent sequences per GPU (148 SMs x 8)")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic streams per GPU, tiled to --batch")
+    ap.add_argument("--cpu-sample-frames", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# frames -> flat arrays the C-ABI consumes
+# ------------------------------------------------------------------------------------------------
+def frame_arrays(fr):
+    g = fr.gnss
+    d = dict(gyro=fr.gyro, accel=fr.accel, dt=fr.dt, pf=fr.pf_w, anchor=fr.anchor_slot.astype(np.int32), obs=fr.obs,
+             mask=fr.obs_mask.astype(np.uint8), dof=(fr.obs_total.astype(np.int32) - 1))
+    if g is not None:
+        d.update(unit=g.unit, res_pos=g.res_pos, res_vel=g.res_vel, sig_psr=g.sigma_psr(), sig_dopp=g.sigma_dopp(),
+                 sys=g.sys.astype(np.int32), Renu=g.R_enu2ecef.reshape(-1, 9))
+    meta = dict(visual=fr.visual_mode is not None, marg=list(fr.marg_slots), max_valid=fr.max_valid, gnss=g is not None)
+    return d, meta
+
+
+def tile_to(a, B):
+    reps = (B + a.shape[0] - 1) // a.shape[0]
+    return np.ascontiguousarray(np.concatenate([a] * reps, 0)[:B])
+
+
+def run_step(g, t, meta):
+    """One frame cycle through the public host API (ingvio_b200.filter.BatchFilter -> C-ABI)."""
+    from ingvio_b200 import capi
+    g.propagate_imu(t["gyro"], t["accel"], t["dt"])
+    g.augment_sliding_window_pose()
+    if meta["visual"]:
+        g.msckf_update(capi.VIS_ALL_OBS, t["pf"], t["anchor"], t["obs"], t["mask"], t["dof"], VISUAL_NOISE,
+                       meta["max_valid"])
+    for s in sorted(meta["marg"], reverse=True):
+        g.marg_sliding_window_pose(s)
+    if meta["gnss"]:
+        g.gnss_update(t["unit"], t["res_pos"], t["res_vel"], t["sig_psr"], t["sig_dopp"], t["sys"], t["Renu"], 0, 0, 1)
+
+
+def make_filter(wl, B, stream_obj, torch_stream, device):
+    from ingvio_b200.filter import BatchFilter
+    g = BatchFilter(B, wl.sw, max(wl.feats, 1), max(wl.sats, 1), stereo=wl.stereo, device=device,
+                    stream=torch_stream.cuda_stream, noise=NOISE, T_cl2cr=(R_CL2CR, P_CL2CR), chi2_max_dof=160)
+    ini = stream_obj.initial_state()
+    t = lambda a: tile_to(a, B)
+    g.init_state_and_cov(t(ini["R"].reshape(-1, 9)), t(ini["p"]), t(ini["v"]), t(ini["bg"]), t(ini["ba"]),
+                         np.tile(R_C2I.reshape(1, 9), (B, 1)), np.tile(P_C2I, (B, 1)), COV_DIAG21)
+    if wl.sats > 0:
+        for gt, val, cov in GNSS_INIT:
+            g.add_gnss_variable(gt, val, cov)
+    return g
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("uuid,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.uuid = uuid
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        mine = [r for r in rows if len(r) >= 9 and (self.uuid is None or self.uuid in r[0])] or rows
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in mine:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].strip().lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(smax)) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C++ port of the reference path (the reference itself cannot be built here)
+# ------------------------------------------------------------------------------------------------
+def _port_filter(wl, st):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from cpu_port.port import CpuPortFilter
+    from ingvio_b200.filter import chi2_table
+    f = CpuPortFilter([NOISE["noise_g"], NOISE["noise_a"], NOISE["noise_bg"], NOISE["noise_ba"], NOISE["noise_clockbias"],
+                       NOISE["noise_cb_rw"]], [0, 0, -9.8], (R_CL2CR, P_CL2CR), wl.stereo, chi2_table(160, 0.95))
+    ini = st.initial_state()
+    f.init(ini["R"][0], ini["p"][0], ini["v"][0], ini["bg"][0], ini["ba"][0], R_C2I, P_C2I, COV_DIAG21)
+    if wl.sats > 0:
+        for gt, val, cov in GNSS_INIT:
+            f.add_gnss(gt, val, cov)
+    return f
+
+
+def cpu_single_thread(wl, n_frames, seq0=0):
+    """updates/s of ONE sequence on ONE host core (the reference is single-threaded, IngvioNode.cpp:36)."""
+    st = SyntheticStream(wl, 1, seq0=seq0)
+    f = _port_filter(wl, st)
+    for _ in range(wl.sw - 1 + 2):
+        f.step(st.next_frame().seq(0), VISUAL_NOISE)
+    frames = [st.next_frame().seq(0) for _ in range(n_frames)]
+    t0 = time.perf_counter()
+    for fr in frames:
+        f.step(fr, VISUAL_NOISE)
+    dt = time.perf_counter() - t0
+    return n_frames / dt, dt
+
+
+def _ref_worker(args):
+    wname, seq, warm, steps, barrier = args
+    wl = WORKLOADS[wname]
+    st = SyntheticStream(wl, 1, seq0=seq)
+    f = _port_filter(wl, st)
+    for _ in range(wl.sw - 1 + warm):
+        f.step(st.next_frame().seq(0), VISUAL_NOISE)
+    frames = [st.next_frame().seq(0) for _ in range(steps)]
+    barrier.wait()
+    t0 = time.perf_counter()
+    for fr in frames:
+        f.step(fr, VISUAL_NOISE)
+    t1 = time.perf_counter()
+    barrier.wait()
+    return t0, t1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    wl = WORKLOADS[args.workload]
+    cores = max(1, min(len(os.sched_getaffinity(0)), 128))
+    steps, warm = args.steps, max(args.warmup, 3)
+    ctx = mp.get_context("fork")
+    mgr = ctx.Manager()
+    barrier = mgr.Barrier(cores)
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(args.workload, i, warm, steps, barrier) for i in range(cores)], chunksize=1)
+    t0 = min(r[0] for r in res)
+    t1 = max(r[1] for r in res)
+    wall = t1 - t0
+    value = cores * steps / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{wl.name}: {'stereo' if wl.stereo else 'mono'} SW={wl.sw} F={wl.feats} S={wl.sats} "
+                               f"(N={wl.dim}), one sequence per host core, {cores} sequences",
+                   "step": "one frame cycle of every sequence"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} sequences x {steps} frames after {wl.sw - 1 + warm} untimed frames; "
+                                   "C++ port oracle/cpu_port (the reference needs Eigen/SuiteSparse/Boost/ROS, absent here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from ingvio_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the CUDA path is the product; no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    wl = WORKLOADS[args.workload]
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    D = max(1, min(args.distinct, B))
+    prefill = wl.sw - 1
+
+    # ---- synthetic streams (distinct seeds per rank), tiled to B sequences ----
+    st = SyntheticStream(wl, D, seq0=rank * B)
+    n_frames = prefill + 3 * (W + K)
+    frames = [frame_arrays(st.next_frame()) for _ in range(n_frames)]
+    ts = torch.cuda.Stream(device=dev)
+    tdt = {np.dtype("float64"): torch.float64, np.dtype("int32"): torch.int32, np.dtype("uint8"): torch.uint8}
+
+    def to_dev(d):
+        return {k: torch.from_numpy(tile_to(v, B)).to(dev, non_blocking=False) for k, v in d.items()}
+
+    def to_pinned(d):
+        return {k: torch.from_numpy(tile_to(v, B)).pin_memory() for k, v in d.items()}
+
+    with torch.cuda.stream(ts):
+        g = make_filter(wl, B, st, ts, local)
+        # fill the sliding window (untimed)
+        for i in range(prefill):
+            run_step(g, to_dev(frames[i][0]), frames[i][1])
+        g.synchronize()
+        seg = lambda k: list(range(prefill + k * (W + K), prefill + (k + 1) * (W + K)))
+        dev_frames = {i: to_dev(frames[i][0]) for i in seg(0) + seg(2)}
+        pin_frames = {i: to_pinned(frames[i][0]) for i in seg(1)}
+        h2d_bytes = sum(v.numel() * v.element_size() for v in pin_frames[seg(1)[0]].values())
+
+        def barrier():
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        def timed(idx, table, after_step=None):
+            for i in idx[:W]:
+                run_step(g, table[i], frames[i][1])
+                if after_step:
+                    after_step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = g.launch_count
+            e0.record(ts)
+            for i in idx[W:]:
+                run_step(g, table[i], frames[i][1])
+                if after_step:
+                    after_step()
+            e1.record(ts)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, g.launch_count - l0
+
+        uuid = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(dev).uuid)
+        except Exception:
+            pass
+        # ---- (1) value: inputs resident in HBM ----
+        clk = ClockSampler(uuid)
+        clk.start()
+        ms_dev, launches = timed(seg(0), dev_frames)
+        clocks = clk.stop()
+        # ---- (2) e2e: pinned host inputs through the same API + D2H read of mean and trace(P) ----
+        d2h = {"n": 0}
+
+        def read_back():
+            x = g.get_state()
+            tr = g.cov_trace()
+            d2h["n"] = x.nbytes + tr.nbytes
+
+        ms_e2e, _ = timed(seg(1), pin_frames, after_step=read_back)
+        # ---- (3) per-kernel-family device times (CUDA events on the launching stream) ----
+        lib = g.lib
+        import ctypes as C
+        for i in seg(2)[:W]:
+            run_step(g, dev_frames[i], frames[i][1])
+        g.synchronize()
+        lib.igv_profile_enable(g.h, 1)
+        acc_out = torch.zeros(B, dtype=torch.int32, device=dev)
+        for i in seg(2)[W:]:
+            run_step(g, dev_frames[i], frames[i][1])
+        ms_arr = (C.c_double * 8)()
+        cnt_arr = (C.c_longlong * 8)()
+        lib.igv_profile_read(g.h, ms_arr, cnt_arr, 1)
+        lib.igv_profile_enable(g.h, 0)
+        fam = {n: dict(ms=ms_arr[k], launches=int(cnt_arr[k])) for k, n in enumerate(capi.KERNEL_FAMILIES)}
+        flags = g.flags()
+        tr = g.cov_trace()
+        assert np.all(np.isfinite(tr)) and np.all(tr > 0), "filter diverged"
+        n_flag = int(np.count_nonzero(flags & 3))
+
+    total_updates = world * B * K
+    value = total_updates / (ms_dev * 1e-3)
+    e2e_value = total_updates / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (QR compression) ----
+    n = 6 * wl.sw
+    q = wl.rho * wl.sw - 3
+    m = wl.feats * q
+    qr_launches = max(1, fam["qr"]["launches"])
+    qr_ms = fam["qr"]["ms"] / qr_launches
+    qr_bytes = B * (8.0 * m * (n + 1) + 8.0 * n * (n + 1))          # SURVEY.md §8d "QR compress" bytes x B
+    qr_flops = B * (2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 4.0 * m * n)  # SURVEY.md §8d FLOPs x B
+    hbm_peak, peak_src = peaks()
+    achieved_gbs = qr_bytes / (qr_ms * 1e-3) / 1e9
+    fp64_peak = C.c_double(0.0)
+    lib.igv_measure_fp64_peak(local, C.byref(fp64_peak))
+    total_prof_ms = sum(v["ms"] for v in fam.values())
+    roofline = {"kernel": "k_qr_compress", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": qr_bytes, "avg_launch_ms": qr_ms,
+                "share_of_step": fam["qr"]["ms"] / total_prof_ms if total_prof_ms else None,
+                "note": "FP64 dense kernel: the binding roof is the DFMA pipe, see roofline_fp64"}
+    roofline_fp64 = {"kernel": "k_qr_compress", "bound": "fp64_dfma", "achieved": qr_flops / (qr_ms * 1e-3) / 1e12,
+                     "peak": fp64_peak.value, "unit": "TFLOP/s",
+                     "frac": (qr_flops / (qr_ms * 1e-3) / 1e12) / fp64_peak.value if fp64_peak.value else None,
+                     "peak_source": "igv_measure_fp64_peak (DFMA probe on this GPU, this run)",
+                     "algorithmic_flops_per_launch": qr_flops}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{wl.name}: {'stereo' if wl.stereo else 'mono'} SW={wl.sw} F={wl.feats} S={wl.sats} "
+                               f"(N={wl.dim}), B={B} independent sequences per GPU",
+                   "batch_per_gpu": B, "distinct_streams_per_gpu": D, "imu_steps_per_frame": 10,
+                   "step": "one frame cycle (propagate x10, augment, MSCKF update, marginalise, GNSS update) of every sequence",
+                   "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective",
+                   "l2": "per-step working set (stacked Jacobians + covariances) >> 126 MB L2; no explicit flush needed"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h["n"]),
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_fp64": roofline_fp64,
+        "kernel_ms_per_step": {k: v["ms"] / K for k, v in fam.items()},
+        "flagged_sequences": n_flag,
+    }
+
+    if rank == 0 and world == 1 and not args.no_latency:
+        # single-sequence latency (BASELINE configs[1] as one filter): B = 1 handle, row-split QR
+        with torch.cuda.stream(ts):
+            st1 = SyntheticStream(wl, 1, seq0=777)
+            g1 = make_filter(wl, 1, st1, ts, local)
+            fr1 = [frame_arrays(st1.next_frame()) for _ in range(prefill + W + K)]
+            t1 = [({k: torch.from_numpy(v).to(dev) for k, v in f[0].items()}, f[1]) for f in fr1]
+            for a, mta in t1[:prefill + W]:
+                run_step(g1, a, mta)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            for a, mta in t1[prefill + W:]:
+                run_step(g1, a, mta)
+            e1.record(ts)
+            torch.cuda.synchronize(dev)
+            line["single_sequence"] = {"ms_per_update": e0.elapsed_time(e1) / K, "updates_per_sec": K / (e0.elapsed_time(e1) * 1e-3)}
+            g1.close()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, secs = cpu_single_thread(wl, args.cpu_sample_frames)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"1 sequence, {args.cpu_sample_frames} steady-state frames of the same workload "
+                                          f"({secs:.1f} s) on one host core; C++ port oracle/cpu_port "
+                                          "(reference needs Eigen/SuiteSparse/Boost/ROS, absent here)"}
+    g.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

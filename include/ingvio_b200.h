@@ -222,6 +222,19 @@ igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size,
 igv_status igv_get_flags(igv_batch* h, int* flags_out /* B */, int clear);
 igv_status igv_cov_trace(igv_batch* h, double* trace_out /* B */);
 
+/* ---- measurement utilities (no reference counterpart; used by bench.py) --------------------------
+ * Per-kernel-family CUDA-event timing on the handle's stream. While enabled every launch is
+ * bracketed by an event pair; igv_profile_read synchronises and returns the accumulated device
+ * milliseconds and launch counts per family. */
+enum { IGV_K_PROPAGATE = 0, IGV_K_AUGMENT = 1, IGV_K_FEATURES = 2, IGV_K_QR = 3, IGV_K_EKF = 4,
+       IGV_K_GNSS_ROWS = 5, IGV_K_MARG = 6, IGV_K_OTHER = 7, IGV_K_COUNT = 8 };
+igv_status igv_profile_enable(igv_batch* h, int on);
+igv_status igv_profile_read(igv_batch* h, double* ms_out /* IGV_K_COUNT */, long long* launches_out /* IGV_K_COUNT */,
+                            int reset);
+/* Sustained FP64 FMA throughput of the device (dependent-chain-free DFMA loop on every SM), in
+ * TFLOP/s: the denominator for the FP64-pipe roofline of the dense kernels. */
+igv_status igv_measure_fp64_peak(int device, double* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

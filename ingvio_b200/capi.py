@@ -89,7 +89,11 @@ SIGNATURES = {
     "igv_replace_var_linear": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_ip, c_ip, _VP]),
     "igv_get_flags": (C.c_int, [_H, _VP, C.c_int]),
     "igv_cov_trace": (C.c_int, [_H, _VP]),
+    "igv_profile_enable": (C.c_int, [_H, C.c_int]),
+    "igv_profile_read": (C.c_int, [_H, c_dp, C.POINTER(C.c_longlong), C.c_int]),
+    "igv_measure_fp64_peak": (C.c_int, [C.c_int, c_dp]),
 }
+KERNEL_FAMILIES = ["propagate", "augment", "features", "qr", "ekf", "gnss_rows", "marginalize", "other"]
 
 _lib = None
 

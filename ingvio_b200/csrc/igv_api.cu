@@ -392,7 +392,12 @@ static igv_status marginalize_var(igv_batch* h, size_t vi) {
 igv_status igv_marg_gnss_variable(igv_batch* h, int gtype) {
   if (!h || gtype < 0 || gtype > 5) return IGV_ERR_INVALID;
   for (size_t i = 0; i < h->vars.size(); ++i)
-    if (h->vars[i].kind == VK_GNSS && h->vars[i].tag == gtype) return marginalize_var(h, i);
+    if (h->vars[i].kind == VK_GNSS && h->vars[i].tag == gtype) {
+      igv_status s = marginalize_var(h, i);
+      if (s != IGV_OK) return s;
+      igv_launch_set_gnss_value(h, gtype, nullptr);   // state->_gnss.erase(gtype): mirror slot back to 0
+      return check_launch(h);
+    }
   return fail(h, IGV_ERR_STATE, "GNSS variable not in the state");
 }
 
@@ -701,6 +706,29 @@ igv_status igv_cov_trace(igv_batch* h, double* trace_out) {
   IGV_TRY(check_launch(h));
   IGV_TRY(fetch(h, trace_out, dev, (size_t)h->B));
   if (h->ptr_mode == IGV_PTR_DEVICE) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
+igv_status igv_profile_enable(igv_batch* h, int on) {
+  if (!h) return IGV_ERR_INVALID;
+  h->prof_on = on != 0;
+  return IGV_OK;
+}
+
+igv_status igv_profile_read(igv_batch* h, double* ms_out, long long* launches_out, int reset) {
+  if (!h || !ms_out || !launches_out) return IGV_ERR_INVALID;
+  IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (auto& ev : h->prof_events) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev.e0, ev.e1);
+    h->prof_ms[ev.kind] += ms;
+    h->prof_cnt[ev.kind] += 1;
+    cudaEventDestroy(ev.e0);
+    cudaEventDestroy(ev.e1);
+  }
+  h->prof_events.clear();
+  for (int k = 0; k < IGV_K_COUNT; ++k) { ms_out[k] = h->prof_ms[k]; launches_out[k] = h->prof_cnt[k]; }
+  if (reset) for (int k = 0; k < IGV_K_COUNT; ++k) { h->prof_ms[k] = 0.0; h->prof_cnt[k] = 0; }
   return IGV_OK;
 }
 

@@ -79,6 +79,12 @@ struct igv_batch {
   double* gam_ws = nullptr;            // B
   double* Dws = nullptr;               // delayed-init workspace: B x (128*18 + 2)
   std::vector<double> chi2_host;
+  // profiling (igv_profile_*)
+  bool prof_on = false;
+  struct ProfEv { int kind; cudaEvent_t e0, e1; };
+  std::vector<ProfEv> prof_events;
+  double prof_ms[IGV_K_COUNT] = {0};
+  long long prof_cnt[IGV_K_COUNT] = {0};
   // host->device staging arena
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
@@ -86,6 +92,16 @@ struct igv_batch {
   IgvLayout layout() const;
   double* Pc() const { return P[cur]; }
   double* Xc() const { return X[xcur]; }
+};
+
+struct IgvProfScope {
+  igv_batch* h; int kind; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
+  IgvProfScope(igv_batch* h_, int kind_) : h(h_), kind(kind_), on(h_->prof_on) {
+    if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
+  }
+  ~IgvProfScope() {
+    if (on) { cudaEventRecord(e1, h->stream); h->prof_events.push_back({kind, e0, e1}); }
+  }
 };
 
 // ---- kernel launchers (defined in the k_*.cu files) --------------------------------------------

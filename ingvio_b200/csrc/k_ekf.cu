@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
 }  // namespace
 
 void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& l) {
+  IgvProfScope prof_scope_(h, IGV_K_EKF);
   EkfArgs a;
   a.P = h->Pc(); a.ld = h->ld; a.N = h->N;
   a.X = h->Xc(); a.xsize = h->xsize; a.L = h->layout();

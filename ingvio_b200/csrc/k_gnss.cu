@@ -108,6 +108,7 @@ __global__ void k_gnss_rows(GnssArgs a) {
 }  // namespace
 
 void igv_launch_gnss_rows(igv_batch* h, const IgvGnssLaunch& l) {
+  IgvProfScope prof_scope_(h, IGV_K_GNSS_ROWS);
   GnssArgs a;
   a.P = h->Pc(); a.ld = h->ld; a.X = h->Xc(); a.xsize = h->xsize;
   a.S = l.S; a.unit = l.unit; a.res_pos = l.res_pos; a.res_vel = l.res_vel; a.sig_psr = l.sig_psr;

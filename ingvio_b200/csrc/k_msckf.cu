@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_msckf_features(FeatArgs a) {
 }  // namespace
 
 void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
+  IgvProfScope prof_scope_(h, IGV_K_FEATURES);
   FeatArgs a;
   a.P = h->Pc(); a.ld = h->ld;
   a.X = h->Xc(); a.xsize = h->xsize; a.L = h->layout();

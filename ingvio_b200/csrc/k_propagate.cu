@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
 
 void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const double* accel, const double* dt,
                           const double* Phi, const double* G) {
+  IgvProfScope prof_scope_(h, IGV_K_PROPAGATE);
   PropArgs a;
   a.P = h->Pc(); a.ld = h->ld; a.N = h->N;
   a.X = h->Xc(); a.xsize = h->xsize;

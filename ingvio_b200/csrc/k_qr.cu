@@ -220,6 +220,7 @@ void launch_qr(const QrArgs& a, int split, int B, int max_frange, cudaStream_t s
 }  // namespace
 
 void igv_launch_qr_compress(igv_batch* h, int F, int max_valid) {
+  IgvProfScope prof_scope_(h, IGV_K_QR);
   IgvLayout L = h->layout();
   const int n = 6 * L.n_clones;
   // enough CTAs to cover the chip: split the rows of each sequence when the batch is small

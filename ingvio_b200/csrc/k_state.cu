@@ -177,23 +177,28 @@ __global__ void k_trace(const double* P, int ld, int N, double* out) {
 
 void igv_launch_state_init(igv_batch* h, const double* R, const double* p, const double* v, const double* bg,
                            const double* ba, const double* Rext, const double* pext, const double* diag21) {
+  IgvProfScope prof_scope_(h, IGV_K_OTHER);
   k_state_init<<<h->B, 128, 0, h->stream>>>(h->Pc(), h->ld, h->Xc(), h->xsize, R, p, v, bg, ba, Rext, pext, diag21);
   h->launches++;
 }
 void igv_launch_cov_copy(igv_batch* h, double* user, int ld_user, bool to_user) {
+  IgvProfScope prof_scope_(h, IGV_K_OTHER);
   dim3 grid(max(1, min(64, (h->N * h->N + 255) / 256)), h->B);
   k_cov_copy<<<grid, 256, 0, h->stream>>>(h->Pc(), h->ld, h->N, user, ld_user, to_user ? 1 : 0);
   h->launches++;
 }
 void igv_launch_cov_blocks(igv_batch* h, const IgvBlocks& blk, double* dst) {
+  IgvProfScope prof_scope_(h, IGV_K_OTHER);
   k_cov_blocks<<<h->B, 256, 0, h->stream>>>(h->Pc(), h->ld, blk, dst);
   h->launches++;
 }
 void igv_launch_add_variable(igv_batch* h, int size, const double* cov_block_dev) {
+  IgvProfScope prof_scope_(h, IGV_K_OTHER);
   k_add_variable<<<h->B, 128, 0, h->stream>>>(h->Pc(), h->ld, h->N, size, cov_block_dev);
   h->launches++;
 }
 void igv_launch_marginalize(igv_batch* h, int start, int size, int clone_slot) {
+  IgvProfScope prof_scope_(h, IGV_K_MARG);
   const int Nn = h->N - size;
   dim3 grid(max(1, min(32, (Nn * Nn + 255) / 256)), h->B);
   IgvLayout L = h->layout();
@@ -204,10 +209,12 @@ void igv_launch_marginalize(igv_batch* h, int start, int size, int clone_slot) {
   h->launches++;
 }
 void igv_launch_set_gnss_value(igv_batch* h, int gtype, const double* value_dev) {
+  IgvProfScope prof_scope_(h, IGV_K_OTHER);
   k_set_gnss_value<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->Xc(), h->xsize, gtype, value_dev, h->B);
   h->launches++;
 }
 void igv_launch_augment(igv_batch* h, const double* R_i2w, const double* clone_R, const double* clone_p) {
+  IgvProfScope prof_scope_(h, IGV_K_AUGMENT);
   IgvLayout L = h->layout();
   const size_t smem = sizeof(double) * 6 * (h->N + 6);
   k_augment<<<h->B, 128, smem, h->stream>>>(h->Pc(), h->ld, h->N, h->Xc(), h->xsize, L.n_clones, R_i2w, clone_R,
@@ -215,10 +222,12 @@ void igv_launch_augment(igv_batch* h, const double* R_i2w, const double* clone_R
   h->launches++;
 }
 void igv_launch_boxplus(igv_batch* h, const double* dx) {
+  IgvProfScope prof_scope_(h, IGV_K_OTHER);
   k_boxplus<<<h->B, 64, 0, h->stream>>>(h->Xc(), h->xsize, dx, h->N, h->layout());
   h->launches++;
 }
 void igv_launch_trace(igv_batch* h, double* out) {
+  IgvProfScope prof_scope_(h, IGV_K_OTHER);
   k_trace<<<h->B, 32, 0, h->stream>>>(h->Pc(), h->ld, h->N, out);
   h->launches++;
 }
