@@ -188,6 +188,21 @@ def cpu_single_thread(wl, n_frames, seq0=0):
     return n_frames / dt, dt
 
 
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    env = os.environ.get("IGV_REF_CORES")
+    if env:
+        n = min(n, int(env))
+    return max(1, n)
+
+
 def _ref_worker(args):
     wname, seq, warm, steps, barrier = args
     wl = WORKLOADS[wname]
@@ -211,7 +226,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     wl = WORKLOADS[args.workload]
-    cores = max(1, min(len(os.sched_getaffinity(0)), 128))
+    cores = usable_cores()
     steps, warm = args.steps, max(args.warmup, 3)
     ctx = mp.get_context("fork")
     mgr = ctx.Manager()

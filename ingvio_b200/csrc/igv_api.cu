@@ -33,27 +33,40 @@ igv_status check_launch(igv_batch* h) {
   return IGV_OK;
 }
 
+// Reserve `bytes` in the staging arena. On growth the old block is RETIRED, not freed: pointers handed
+// out earlier in the same API call (and kernels already enqueued on them) stay valid; retired blocks are
+// released by arena_reset() at the start of a later call (cudaFree synchronises with the device).
+igv_status arena_reserve(igv_batch* h, size_t bytes, char** out) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (h->arena_off + bytes > h->arena_cap) {
+    const size_t ncap = std::max(h->arena_cap * 2, bytes + (size_t(4) << 20));
+    char* n = nullptr;
+    IGV_CUDA(h, cudaMalloc(&n, ncap));
+    if (h->arena) h->retired.push_back(h->arena);
+    h->arena = n;
+    h->arena_cap = ncap;
+    h->arena_off = 0;
+  }
+  *out = h->arena + h->arena_off;
+  h->arena_off += bytes;
+  return IGV_OK;
+}
+
+void arena_reset(igv_batch* h) {
+  h->arena_off = 0;
+  for (char* p : h->retired) cudaFree(p);
+  h->retired.clear();
+}
+
 // Device view of a bulk argument: the pointer itself in DEVICE mode, else a copy in the arena.
 template <class T>
 igv_status stage(igv_batch* h, const T* src, size_t count, const T** out) {
   if (!src) { *out = nullptr; return IGV_OK; }
   if (h->ptr_mode == IGV_PTR_DEVICE) { *out = src; return IGV_OK; }
-  const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
-  if (h->arena_off + bytes > h->arena_cap) {
-    // grow: previous contents may still be in flight -> synchronise first
-    IGV_CUDA(h, cudaStreamSynchronize(h->stream));
-    const size_t ncap = std::max(h->arena_cap * 2, h->arena_off + bytes + (size_t(1) << 20));
-    char* n = nullptr;
-    IGV_CUDA(h, cudaMalloc(&n, ncap));
-    if (h->arena) {
-      IGV_CUDA(h, cudaMemcpy(n, h->arena, h->arena_off, cudaMemcpyDeviceToDevice));
-      cudaFree(h->arena);
-    }
-    h->arena = n;
-    h->arena_cap = ncap;
-  }
-  T* dst = reinterpret_cast<T*>(h->arena + h->arena_off);
-  h->arena_off += bytes;
+  char* mem = nullptr;
+  igv_status s = arena_reserve(h, count * sizeof(T), &mem);
+  if (s != IGV_OK) return s;
+  T* dst = reinterpret_cast<T*>(mem);
   IGV_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   *out = dst;
   return IGV_OK;
@@ -64,24 +77,10 @@ template <class T>
 igv_status out_buf(igv_batch* h, T* user, size_t count, T** dev) {
   if (!user) { *dev = nullptr; return IGV_OK; }
   if (h->ptr_mode == IGV_PTR_DEVICE) { *dev = user; return IGV_OK; }
-  const T* tmp = nullptr;
-  // reserve arena space without copying
-  const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
-  if (h->arena_off + bytes > h->arena_cap) {
-    IGV_CUDA(h, cudaStreamSynchronize(h->stream));
-    const size_t ncap = std::max(h->arena_cap * 2, h->arena_off + bytes + (size_t(1) << 20));
-    char* n = nullptr;
-    IGV_CUDA(h, cudaMalloc(&n, ncap));
-    if (h->arena) {
-      IGV_CUDA(h, cudaMemcpy(n, h->arena, h->arena_off, cudaMemcpyDeviceToDevice));
-      cudaFree(h->arena);
-    }
-    h->arena = n;
-    h->arena_cap = ncap;
-  }
-  (void)tmp;
-  *dev = reinterpret_cast<T*>(h->arena + h->arena_off);
-  h->arena_off += bytes;
+  char* mem = nullptr;
+  igv_status s = arena_reserve(h, count * sizeof(T), &mem);
+  if (s != IGV_OK) return s;
+  *dev = reinterpret_cast<T*>(mem);
   return IGV_OK;
 }
 template <class T>
@@ -215,6 +214,7 @@ igv_status igv_destroy(igv_batch* h) {
   void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
                   h->Hc, h->Rpart, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->arena};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (char* p : h->retired) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return IGV_OK;
@@ -259,7 +259,7 @@ igv_status igv_set_chi2_table(igv_batch* h, const double* table, int max_dof) {
 igv_status igv_state_init(igv_batch* h, const double* R_i2w, const double* p, const double* v, const double* bg,
                           const double* ba, const double* R_ext, const double* p_ext, const double* cov_diag21) {
   if (!h || !R_i2w || !p || !v || !bg || !ba || !R_ext || !p_ext || !cov_diag21) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   const size_t B = h->B;
   const double *dR, *dp, *dv, *dbg, *dba, *dRe, *dpe, *dd;
   IGV_TRY(stage(h, R_i2w, B * 9, &dR)); IGV_TRY(stage(h, p, B * 3, &dp)); IGV_TRY(stage(h, v, B * 3, &dv));
@@ -317,7 +317,7 @@ igv_status igv_state_set(igv_batch* h, const double* src) {
 // ---- covariance -------------------------------------------------------------------------------------
 igv_status igv_cov_get(igv_batch* h, double* dst, int ld) {
   if (!h || !dst || ld < h->N) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   double* dev;
   IGV_TRY(out_buf(h, dst, (size_t)h->B * ld * h->N, &dev));
   igv_launch_cov_copy(h, dev, ld, true);
@@ -328,7 +328,7 @@ igv_status igv_cov_get(igv_batch* h, double* dst, int ld) {
 }
 igv_status igv_cov_set(igv_batch* h, const double* src, int ld) {
   if (!h || !src || ld < h->N) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   const double* dev;
   IGV_TRY(stage(h, src, (size_t)h->B * ld * h->N, &dev));
   igv_launch_cov_copy(h, const_cast<double*>(dev), ld, false);
@@ -336,7 +336,7 @@ igv_status igv_cov_set(igv_batch* h, const double* src, int ld) {
 }
 igv_status igv_cov_get_blocks(igv_batch* h, int n_blocks, const int* idx, const int* size, double* dst) {
   if (!h || !dst) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   IgvBlocks blk;
   IGV_TRY(make_blocks(h, n_blocks, idx, size, &blk));
   double* dev;
@@ -365,7 +365,7 @@ static igv_status add_variable(igv_batch* h, IgvVarKind kind, int tag, int size,
 
 igv_status igv_add_gnss_variable(igv_batch* h, int gtype, const double* value, double cov) {
   if (!h || gtype < 0 || gtype > 5) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   if (h->layout().idx_gnss[gtype] >= 0) return fail(h, IGV_ERR_STATE, "GNSS variable already in the state");
   const double* dv;
   IGV_TRY(stage(h, value, (size_t)h->B, &dv));
@@ -403,7 +403,7 @@ igv_status igv_marg_gnss_variable(igv_batch* h, int gtype) {
 
 igv_status igv_add_variable_independent(igv_batch* h, int size, const double* cov_block) {
   if (!h || size < 1 || size > 6 || !cov_block) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   return add_variable(h, VK_OPAQUE, 0, size, cov_block);
 }
 
@@ -428,7 +428,7 @@ igv_status igv_marginalize_clone(igv_batch* h, int slot) {
 // ---- propagation ------------------------------------------------------------------------------------
 igv_status igv_propagate_cov(igv_batch* h, const double* Phi, const double* G, const double* dt) {
   if (!h || !Phi || !G || !dt) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   const double *dP, *dG, *ddt;
   IGV_TRY(stage(h, Phi, (size_t)h->B * 225, &dP));
   IGV_TRY(stage(h, G, (size_t)h->B * 180, &dG));
@@ -440,7 +440,7 @@ igv_status igv_propagate_cov(igv_batch* h, const double* Phi, const double* G, c
 igv_status igv_propagate_imu(igv_batch* h, int n_steps, const double* gyro, const double* accel, const double* dt) {
   if (!h || n_steps < 0 || !gyro || !accel || !dt) return IGV_ERR_INVALID;
   if (n_steps == 0) return IGV_OK;
-  h->arena_off = 0;
+  arena_reset(h);
   const double *dg, *da, *ddt;
   IGV_TRY(stage(h, gyro, (size_t)h->B * n_steps * 3, &dg));
   IGV_TRY(stage(h, accel, (size_t)h->B * n_steps * 3, &da));
@@ -464,7 +464,7 @@ igv_status igv_augment_clone(igv_batch* h) {
 }
 igv_status igv_augment_clone_cov(igv_batch* h, const double* R_i2w, const double* clone_R, const double* clone_p) {
   if (!h || !R_i2w || ((clone_R == nullptr) != (clone_p == nullptr))) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   const double *dR, *dcR, *dcp;
   IGV_TRY(stage(h, R_i2w, (size_t)h->B * 9, &dR));
   IGV_TRY(stage(h, clone_R, (size_t)h->B * 9, &dcR));
@@ -480,7 +480,7 @@ static igv_status ekf_common(igv_batch* h, int n_blocks, const int* blk_idx, con
   if (r_kind != IGV_R_ISO && r_kind != IGV_R_DIAG && r_kind != IGV_R_FULL) return IGV_ERR_INVALID;
   if (!R) return IGV_ERR_INVALID;
   if (rows > h->max_rows) return fail(h, IGV_ERR_CAPACITY, "rows exceed the EKF workspace (max_rows)");
-  h->arena_off = 0;
+  arena_reset(h);
   IgvEkfLaunch e{};
   IGV_TRY(make_blocks(h, n_blocks, blk_idx, blk_size, &e.blk));
   const size_t B = h->B;
@@ -514,7 +514,7 @@ igv_status igv_chi2_whiten(igv_batch* h, int n_blocks, const int* blk_idx, const
 
 igv_status igv_box_plus(igv_batch* h, const double* dx) {
   if (!h || !dx) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   const double* d;
   IGV_TRY(stage(h, dx, (size_t)h->B * h->N, &d));
   igv_launch_boxplus(h, d);
@@ -531,7 +531,7 @@ igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a) {
   if (a->n_feats == 0 || L.n_clones == 0) return IGV_OK;   // `if (update_ids.size() == 0) return;`
   if (!a->pf_w || !a->anchor_slot || !a->obs || !a->obs_mask || !a->chi2_dof) return IGV_ERR_INVALID;
   if (h->chi2_n < 1) return fail(h, IGV_ERR_STATE, "chi^2 table not set (igv_set_chi2_table)");
-  h->arena_off = 0;
+  arena_reset(h);
   const size_t B = h->B, F = a->n_feats, SW = a->obs_slots;
   IgvMsckfLaunch m{};
   m.mode = a->mode; m.F = a->n_feats; m.obs_slots = a->obs_slots; m.max_valid = a->max_valid; m.noise = a->noise;
@@ -588,7 +588,7 @@ igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
     return IGV_ERR_INVALID;
   if ((a->chi2_test || a->strong_reject) && h->chi2_n < 14)
     return fail(h, IGV_ERR_STATE, "chi^2 table not set (igv_set_chi2_table)");
-  h->arena_off = 0;
+  arena_reset(h);
   const size_t B = h->B, S = a->n_sats;
   IgvGnssLaunch g{};
   g.S = a->n_sats; g.adjust_yof = a->is_adjust_yof; g.chi2_test = a->chi2_test;
@@ -639,7 +639,7 @@ igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value
   if (h->N + 1 > h->cfg.max_dim) return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds max_dim");
   if (rows - 1 > h->max_rows) return fail(h, IGV_ERR_CAPACITY, "rows exceed the EKF workspace");
   if (do_chi2 && h->chi2_n < rows) return fail(h, IGV_ERR_STATE, "chi^2 table too short");
-  h->arena_off = 0;
+  arena_reset(h);
   IgvBlocks blk;
   IGV_TRY(make_blocks(h, n_blocks, blk_idx, blk_size, &blk));
   const size_t B = h->B;
@@ -678,7 +678,7 @@ igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size,
   bool found = false;
   for (const auto& v : h->vars) if (v.idx == target_idx && v.size == target_size) found = true;
   if (!found) return fail(h, IGV_ERR_STATE, "Target var not in state, cannot linearly replace");
-  h->arena_off = 0;
+  arena_reset(h);
   IgvBlocks blk;
   IGV_TRY(make_blocks(h, n_blocks, blk_idx, blk_size, &blk));
   const double* dH;
@@ -699,7 +699,7 @@ igv_status igv_get_flags(igv_batch* h, int* flags_out, int clear) {
 
 igv_status igv_cov_trace(igv_batch* h, double* trace_out) {
   if (!h || !trace_out) return IGV_ERR_INVALID;
-  h->arena_off = 0;
+  arena_reset(h);
   double* dev;
   IGV_TRY(out_buf(h, trace_out, (size_t)h->B, &dev));
   igv_launch_trace(h, dev);

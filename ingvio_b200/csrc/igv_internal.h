@@ -88,6 +88,7 @@ struct igv_batch {
   // host->device staging arena
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
+  std::vector<char*> retired;
 
   IgvLayout layout() const;
   double* Pc() const { return P[cur]; }
