@@ -40,13 +40,14 @@ struct FeatArgs {
   size_t hs_seq_stride; int F_alloc; // per-sequence strides of Hs and of f_rows / f_gamma
   int* f_rows; double* f_gamma;
   int Mmax;                          // rho * n_clones
+  int ps_in_smem;                    // clone block of P staged in shared memory (n*n doubles)
 };
 
 __device__ __forceinline__ int tri(int i, int j) {  // packed lower index, i >= j
   return i * (i + 1) / 2 + j;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) k_msckf_features(FeatArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_msckf_features(FeatArgs a) {
   double* sPose = sm;
   const int per_warp = Mmax * 6 /*A,B*/ + Mmax * 3 /*V*/ + Mmax /*r*/ + 16 /*T, tau*/ + Mmax * (Mmax + 1) / 2 /*M0*/ +
                        3 * Mmax /*Y*/ + 2 * Mmax /*slot/k maps as doubles? no: ints below*/;
-  double* ws = sm + 12 * IGV_MAX_CLONES + (size_t)warp * per_warp;
+  double* sPs = sm + 12 * IGV_MAX_CLONES;   // [n][n] clone block of P (symmetric), if staged
+  double* ws = sPs + (a.ps_in_smem ? n * n : 0) + (size_t)warp * per_warp;
   double* sA = ws;                     // [M][3]   rows of A_k  (== H_f)
   double* sB = sA + Mmax * 3;          // [M][3]   rows of B_k = A_k [pf]x
   double* sV = sB + Mmax * 3;          // [M][3]   Householder vectors (unit leading entries implicit-explicit)
@@ -66,8 +68,21 @@ __global__ void __launch_bounds__(kWarps * 32) k_msckf_features(FeatArgs a) {
   int* sSlot = reinterpret_cast<int*>(sY + 3 * Mmax);  // [ncl] obs k -> slot ; then [ncl] slot -> obs k
   const double* Xb = a.X + (size_t)b * a.xsize;
   for (int t = threadIdx.x; t < 12 * ncl; t += blockDim.x) sPose[t] = Xb[IGV_X_CORE + t];
-  __syncthreads();
   const double* Pb = a.P + (size_t)b * a.ld * a.ld;
+  if (a.ps_in_smem) {
+    // getMarginalCov of the window (StateManager.cpp:128-153), once per CTA; i is the fast index so the
+    // column-major global reads are contiguous, and P's symmetry makes the transposed store exact.
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+      const int i = t % n, j = t / n;
+      sPs[t] = Pb[(a.L.idx_clone[i / 6] + i % 6) + (size_t)(a.L.idx_clone[j / 6] + j % 6) * a.ld];
+    }
+  }
+  __syncthreads();
+  // P element between (clone slot s1, component i) and (clone slot s2, component j)
+  auto Pel = [&](int s1, int i, int s2, int j) -> double {
+    if (a.ps_in_smem) return sPs[(6 * s1 + i) * n + 6 * s2 + j];
+    return __ldg(&Pb[(a.L.idx_clone[s1] + i) + (size_t)(a.L.idx_clone[s2] + j) * a.ld]);
+  };
 
   for (int f = blockIdx.x * nwarps + warp; f < a.F; f += gridDim.x * nwarps) {
     const size_t bf = (size_t)b * a.F + f;          // index into the caller's arrays
@@ -204,8 +219,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_msckf_features(FeatArgs a) {
         while (k1 * (k1 + 1) / 2 > pr) --k1;
         while ((k1 + 1) * (k1 + 2) / 2 <= pr) ++k1;
         const int k2 = pr - k1 * (k1 + 1) / 2;  // k1 >= k2
-        const int c1 = a.L.idx_clone[k2slot[k1]], c2 = a.L.idx_clone[k2slot[k2]];
-        const int ca = (anc >= 0 && anc < ncl) ? a.L.idx_clone[anc] : -1;
+        const int c1 = k2slot[k1], c2 = k2slot[k2];          // clone slots
+        const int ca = (anc >= 0 && anc < ncl) ? anc : -1;
         for (int t1 = 0; t1 < rho; ++t1) {
           const int r1 = k1 * rho + t1;
           // row vector of H_x at r1: u1 (6 on clone c1), w1 (3 on anchor rot)
@@ -220,15 +235,15 @@ __global__ void __launch_bounds__(kWarps * 32) k_msckf_features(FeatArgs a) {
           double g[6], ga[3];
           for (int j = 0; j < 6; ++j) {
             double acc = 0.0;
-            for (int i = 0; i < 6; ++i) acc = fma(u1[i], __ldg(&Pb[(c1 + i) + (size_t)(c2 + j) * a.ld]), acc);
-            if (ca >= 0) for (int i = 0; i < 3; ++i) acc = fma(w1[i], __ldg(&Pb[(ca + i) + (size_t)(c2 + j) * a.ld]), acc);
+            for (int i = 0; i < 6; ++i) acc = fma(u1[i], Pel(c1, i, c2, j), acc);
+            if (ca >= 0) for (int i = 0; i < 3; ++i) acc = fma(w1[i], Pel(ca, i, c2, j), acc);
             g[j] = acc;
           }
           for (int j = 0; j < 3; ++j) {
             double acc = 0.0;
             if (ca >= 0) {
-              for (int i = 0; i < 6; ++i) acc = fma(u1[i], __ldg(&Pb[(c1 + i) + (size_t)(ca + j) * a.ld]), acc);
-              for (int i = 0; i < 3; ++i) acc = fma(w1[i], __ldg(&Pb[(ca + i) + (size_t)(ca + j) * a.ld]), acc);
+              for (int i = 0; i < 6; ++i) acc = fma(u1[i], Pel(c1, i, ca, j), acc);
+              for (int i = 0; i < 3; ++i) acc = fma(w1[i], Pel(ca, i, ca, j), acc);
             }
             ga[j] = acc;
           }
@@ -431,15 +446,20 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   a.Mmax = h->rho * a.L.n_clones;
   const int Mmax = a.Mmax;
   const size_t per_warp = (size_t)Mmax * 6 + Mmax * 3 + Mmax + 16 + (size_t)Mmax * (Mmax + 1) / 2 + 3 * Mmax + 2 * Mmax;
+  const int n = 6 * a.L.n_clones;
+  a.ps_in_smem = ((size_t)n * n * sizeof(double) <= 72 * 1024) ? 1 : 0;
+  const size_t fixed = 12 * IGV_MAX_CLONES + (a.ps_in_smem ? (size_t)n * n : 0);
   int W = kWarps;
-  while (W > 1 && sizeof(double) * (12 * IGV_MAX_CLONES + W * per_warp) > 200 * 1024) --W;
-  size_t smem = sizeof(double) * (12 * IGV_MAX_CLONES + W * per_warp);
+  while (W > 1 && sizeof(double) * (fixed + W * per_warp) > 200 * 1024) --W;
+  size_t smem = sizeof(double) * (fixed + W * per_warp);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_msckf_features, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_set = true;
   }
-  const int blocks_x = max(1, min((l.F + W - 1) / W, 64));
+  // each CTA stages P_s once and its warps loop over tracks: a few CTAs per sequence are enough
+  const int per_cta = (h->B >= 296) ? 4 * W : W;
+  const int blocks_x = max(1, min((l.F + per_cta - 1) / per_cta, 64));
   dim3 grid(blocks_x, h->B);
   k_msckf_features<<<grid, W * 32, smem, h->stream>>>(a);
   h->launches++;

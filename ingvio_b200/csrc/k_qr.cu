@@ -7,9 +7,16 @@
 // Kernel: a running upper-triangular factor R (packed, in shared memory) is updated with successive
 // row chunks of the stack ("triangle-on-top-of-rectangle" Householder, as LAPACK tpqrt). A chunk of
 // W*ROWS rows lives entirely in REGISTERS: thread (warp w, lane l) holds rows [w*ROWS,(w+1)*ROWS) of
-// columns {l, l+32, l+64, ...}. A reflector for column j therefore needs no cross-lane reduction for
-// the rank-1 update: the owner lane publishes v through SMEM, every thread forms the partial dot
-// products of its own columns over its own rows, partials are combined across warps through SMEM.
+// NSLOT columns. A reflector for column j needs no cross-lane reduction for the rank-1 update: the
+// owner lane publishes its raw column through SMEM, every thread forms the partial dot products of its
+// own columns over its own rows, partials are combined across warps through SMEM (2 barriers/column).
+//
+// Column -> (slot, lane) map: columns are dealt to slots from the TOP slot down, in elimination
+// order, so that the slot holding the columns eliminated first is the partially filled one and the
+// residual column (never eliminated, updated by every reflector) shares slot 0 with the columns
+// eliminated last. At step j only slots <= slot(j) are live; for n+1 = 67 columns this cuts the
+// executed slot-steps from 162 (cyclic map) to 104 (ideal 69).
+//
 // Flops are the minimum 2 m n^2 (no TSQR tree inflation) and HBM traffic is one coalesced read of
 // the stack + one write of the n x (n+1) result: 8 m (n+1) + 8 n (n+1) bytes per sequence.
 // For few sequences the rows are split over `split` CTAs and a second launch folds the partial
@@ -30,23 +37,24 @@ struct QrArgs {
   int src_mode;
   int n;                    // columns to eliminate; ncols1 = n + 1 (last column = residual)
   double* out; long out_stride;   // [b][part] n x (n+1) row-major
-  int* n_acc;               // accepted-feature count per sequence (written by part 0, source 0)
+  int* n_acc;               // accepted-feature count per sequence (written by the last part, source 0)
   int F_alloc;              // leading dimension of f_rows per sequence
   size_t hs_seq_stride;     // elements per sequence in Hs
 };
 
-template <int NSLOT, int ROWS, int W>
-__global__ void __launch_bounds__(W * 32) k_qr_compress(QrArgs a) {
+template <int NSLOT, int ROWS, int W, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB) k_qr_compress(QrArgs a) {
+  static_assert(ROWS % 2 == 0 && ROWS <= 32, "ROWS must be even and <= 32");
   extern __shared__ double sm[];
   const int b = blockIdx.y, part = blockIdx.x, nparts = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = a.n, nc1 = n + 1, ldo = a.ldo;
+  const int r0 = nc1 - 32 * (NSLOT - 1);        // columns in the top slot (1..32)
   const int npk = n * (n + 3) / 2;              // packed upper rows 0..n-1, cols j..n
   double* Rp = sm;                              // [npk]
-  double* vbuf = Rp + npk;                      // [W*ROWS]
-  double* s_part = vbuf + W * ROWS;             // [W][32*NSLOT]
-  double* s_norm = s_part + W * 32 * NSLOT;     // [2][W]
-  int* rowstart = reinterpret_cast<int*>(s_norm + 2 * W + 2);  // [F_range + 1]
+  double* vbuf = Rp + npk + (npk & 1);          // [2][W*ROWS], 16-byte aligned
+  double* s_part = vbuf + 2 * W * ROWS;         // [W][NSLOT][32]
+  int* rowstart = reinterpret_cast<int*>(s_part + W * 32 * NSLOT);  // [F_range + 1]
   __shared__ int s_total, s_f0;
   for (int t = tid; t < npk; t += blockDim.x) Rp[t] = 0.0;
   // ---- row enumeration -------------------------------------------------------------------------
@@ -80,8 +88,16 @@ __global__ void __launch_bounds__(W * 32) k_qr_compress(QrArgs a) {
   const int nfr = (a.src_mode == 0) ? ((int)((long)a.F * (part + 1) / nparts) - s_f0) : 0;
 
   auto off = [&](int j) { return j * nc1 - (j * (j - 1)) / 2; };  // packed offset of R[j][j]
+  // natural column held by (slot s, lane) ; -1 if none
+  int mycol[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) {
+    if (s == NSLOT - 1) mycol[s] = (lane < r0) ? lane : -1;
+    else mycol[s] = r0 + 32 * (NSLOT - 2 - s) + lane;
+  }
 
   double tile[ROWS][NSLOT];
+  unsigned it = 0;  // reflector counter (parity selects the vbuf half)
   for (int base = 0; base < total; base += W * ROWS) {
     // ---- load chunk: lane r < ROWS resolves the physical row of virtual row base + warp*ROWS + r ----
     long phys = -1;
@@ -104,80 +120,86 @@ __global__ void __launch_bounds__(W * 32) k_qr_compress(QrArgs a) {
     for (int r = 0; r < ROWS; ++r) {
       const long o = __shfl_sync(0xffffffffu, phys, r);
 #pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        const int c = lane + 32 * s;
-        tile[r][s] = (o >= 0 && c < nc1) ? __ldg(src_base + o + c) : 0.0;
-      }
+      for (int s = 0; s < NSLOT; ++s)
+        tile[r][s] = (o >= 0 && mycol[s] >= 0) ? __ldg(src_base + o + mycol[s]) : 0.0;
     }
-    // ---- eliminate columns 0..n-1 of the chunk against R -----------------------------------------
+    // ---- eliminate columns 0..n-1 of the chunk against R, top slot first ---------------------------
 #pragma unroll
-    for (int sj = 0; sj < NSLOT; ++sj) {
-      for (int lj = 0; lj < 32; ++lj) {
-        const int j = sj * 32 + lj;
-        if (j >= n) break;
-        double* nb = s_norm + (j & 1) * W;
+    for (int sj = NSLOT - 1; sj >= 0; --sj) {
+      const int nl = (sj == NSLOT - 1) ? r0 : 32;
+      for (int lj = 0; lj < nl; ++lj) {
+        const int j = (sj == NSLOT - 1) ? lj : r0 + 32 * (NSLOT - 2 - sj) + lj;
+        if (j >= n) break;  // the residual column is never eliminated
+        double* vb = vbuf + (it & 1u) * (W * ROWS);
+        ++it;
         if (lane == lj) {
-          double ss = 0.0;
 #pragma unroll
-          for (int r = 0; r < ROWS; ++r) ss = fma(tile[r][sj], tile[r][sj], ss);
-          nb[warp] = ss;
+          for (int r = 0; r < ROWS; r += 2)
+            *reinterpret_cast<double2*>(vb + warp * ROWS + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
         }
-        __syncthreads();  // A
-        double sigma = 0.0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) sigma += nb[w];
+        __syncthreads();  // A: raw column visible
+        double ss = 0.0;
+        for (int i = lane; i < W * ROWS; i += 32) ss = fma(vb[i], vb[i], ss);
+        const double sigma = warp_sum(ss);
         if (sigma == 0.0) continue;  // nothing below the diagonal in this chunk (uniform branch)
+        // Householder with the UN-normalised vector v' = [alpha - beta ; raw column]:
+        //   H = I - tau' v' v'^T,  tau' = 1 / (beta^2 - alpha beta) = 1 / (nrm2 + |alpha| |beta|)
+        // (one rsqrt + one reciprocal on the critical path instead of sqrt + two divisions)
         const double alpha = Rp[off(j)];
-        const double beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-        const double tau = (beta - alpha) / beta;
-        const double scale = 1.0 / (alpha - beta);
-        if (lane == lj) {
-#pragma unroll
-          for (int r = 0; r < ROWS; ++r) vbuf[warp * ROWS + r] = tile[r][sj] * scale;
-        }
+        const double nrm2 = fma(alpha, alpha, sigma);
+        const double absb = nrm2 * rsqrt(nrm2);
+        const double beta = -copysign(absb, alpha);
+        const double amb = alpha - beta;
+        const double taup = __drcp_rn(fma(fabs(alpha), absb, nrm2));
+        bool act[NSLOT];
         double rjk[NSLOT];
+        constexpr int ACC = (ROWS % 4 == 0) ? 4 : 2;   // independent accumulator chains per slot (DFMA latency)
+        double d[NSLOT][ACC];
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-          const int k = lane + 32 * s;
-          rjk[s] = (k > j && k < nc1) ? Rp[off(j) + (k - j)] : 0.0;
+          act[s] = (s < sj) || (s == sj && lane > lj && mycol[s] >= 0);
+          rjk[s] = (s <= sj && act[s]) ? Rp[off(j) + (mycol[s] - j)] : 0.0;
+#pragma unroll
+          for (int q = 0; q < ACC; ++q) d[s][q] = 0.0;
         }
-        __syncthreads();  // B
-        const double* vw = vbuf + warp * ROWS;
-        double d[NSLOT];
+        const double* vw = vb + warp * ROWS;
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) d[s] = 0.0;
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const double v = vw[r];
+        for (int r = 0; r < ROWS; r += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(vw + r);
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s)
-            if (s >= sj) d[s] = fma(v, tile[r][s], d[s]);
+            if (s <= sj) {
+              d[s][r % ACC] = fma(v.x, tile[r][s], d[s][r % ACC]);
+              d[s][(r + 1) % ACC] = fma(v.y, tile[r + 1][s], d[s][(r + 1) % ACC]);
+            }
         }
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-          const int k = lane + 32 * s;
-          if (s >= sj && k > j && k < nc1) s_part[warp * 32 * NSLOT + k] = d[s];
-        }
-        __syncthreads();  // C
-        double wk[NSLOT];
+        for (int s = 0; s < NSLOT; ++s)
+          if (s <= sj && act[s]) {
+            double t = d[s][0] + d[s][1];
+            if (ACC == 4) t += d[s][2] + d[s][3];
+            s_part[(warp * NSLOT + s) * 32 + lane] = t;
+          }
+        __syncthreads();  // C: partial dots visible
+        double wks[NSLOT];
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-          const int k = lane + 32 * s;
-          wk[s] = 0.0;
-          if (s >= sj && k > j && k < nc1) {
-            double dot = rjk[s];
+          wks[s] = 0.0;
+          if (s <= sj && act[s]) {
+            double acc = 0.0;
 #pragma unroll
-            for (int w = 0; w < W; ++w) dot += s_part[w * 32 * NSLOT + k];
-            wk[s] = tau * dot;
-            if (warp == 0) Rp[off(j) + (k - j)] = rjk[s] - wk[s];
+            for (int w = 0; w < W; ++w) acc += s_part[(w * NSLOT + s) * 32 + lane];
+            const double wk = taup * fma(amb, rjk[s], acc);
+            if (warp == 0) Rp[off(j) + (mycol[s] - j)] = fma(-wk, amb, rjk[s]);
+            wks[s] = wk;
           }
         }
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const double v = vw[r];
+        for (int r = 0; r < ROWS; r += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(vw + r);
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s)
-            if (s >= sj) tile[r][s] = fma(-wk[s], v, tile[r][s]);
+            if (s <= sj) { tile[r][s] = fma(-wks[s], v.x, tile[r][s]); tile[r + 1][s] = fma(-wks[s], v.y, tile[r + 1][s]); }
         }
         if (warp == 0 && lane == lj) Rp[off(j)] = beta;
       }
@@ -192,29 +214,37 @@ __global__ void __launch_bounds__(W * 32) k_qr_compress(QrArgs a) {
   }
 }
 
-template <int NSLOT, int ROWS, int W>
+template <int NSLOT, int ROWS, int W, int MINB>
 void launch_one(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st) {
   const int n = a.n;
-  size_t smem = sizeof(double) * ((size_t)n * (n + 3) / 2 + W * ROWS + (size_t)W * 32 * NSLOT + 2 * W + 2) +
-                sizeof(int) * (max_frange + 2);
+  const size_t npk = (size_t)n * (n + 3) / 2;
+  size_t smem = sizeof(double) * (npk + (npk & 1) + 2 * W * ROWS + (size_t)W * 32 * NSLOT) + sizeof(int) * (max_frange + 2);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_qr_compress<NSLOT, ROWS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_qr_compress<NSLOT, ROWS, W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_set = true;
   }
   dim3 grid(split, B);
-  k_qr_compress<NSLOT, ROWS, W><<<grid, W * 32, smem, st>>>(a);
+  k_qr_compress<NSLOT, ROWS, W, MINB><<<grid, W * 32, smem, st>>>(a);
 }
 
 void launch_qr(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st) {
   const int nslot = (a.n + 1 + 31) / 32;
-  if (nslot <= 1) launch_one<1, 32, 4>(a, split, B, max_frange, st);
-  else if (nslot <= 2) launch_one<2, 32, 4>(a, split, B, max_frange, st);
-  else if (nslot <= 3) launch_one<3, 32, 4>(a, split, B, max_frange, st);
-  else if (nslot <= 4) launch_one<4, 24, 4>(a, split, B, max_frange, st);
-  else if (nslot <= 6) launch_one<6, 16, 4>(a, split, B, max_frange, st);
-  else if (nslot <= 8) launch_one<8, 12, 4>(a, split, B, max_frange, st);
-  else launch_one<13, 7, 4>(a, split, B, max_frange, st);
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("IGV_QR_CFG"); cfg = e ? atoi(e) : 0; }
+  if (nslot <= 1) launch_one<1, 32, 4, 2>(a, split, B, max_frange, st);
+  else if (nslot <= 2) launch_one<2, 32, 4, 2>(a, split, B, max_frange, st);
+  else if (nslot <= 3) {
+    if (cfg == 1) launch_one<3, 16, 4, 3>(a, split, B, max_frange, st);
+    else if (cfg == 2) launch_one<3, 16, 8, 1>(a, split, B, max_frange, st);
+    else if (cfg == 3) launch_one<3, 32, 8, 1>(a, split, B, max_frange, st);
+    else if (cfg == 4) launch_one<3, 24, 4, 2>(a, split, B, max_frange, st);
+    else launch_one<3, 32, 4, 2>(a, split, B, max_frange, st);
+  }
+  else if (nslot <= 4) launch_one<4, 24, 4, 2>(a, split, B, max_frange, st);
+  else if (nslot <= 6) launch_one<6, 16, 4, 2>(a, split, B, max_frange, st);
+  else if (nslot <= 8) launch_one<8, 12, 4, 2>(a, split, B, max_frange, st);
+  else launch_one<13, 6, 4, 2>(a, split, B, max_frange, st);
 }
 
 }  // namespace
