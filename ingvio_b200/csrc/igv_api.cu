@@ -212,7 +212,7 @@ igv_status igv_destroy(igv_batch* h) {
   if (!h) return IGV_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
-                  h->Hc, h->Rpart, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->arena};
+                  h->Hc, h->Rpart, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws, h->arena};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (char* p : h->retired) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

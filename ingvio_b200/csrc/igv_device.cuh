@@ -235,6 +235,126 @@ __device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int r
   }
 }
 
+// Blocked right-looking Cholesky fused with the forward substitution of the right-hand sides:
+//   S = L L^T (lower, in place; S is r x r column-major, leading dim r) and
+//   Z[:, c0:c0+nc] <- L^-1 Z[:, c0:c0+nc]   (Z is r x * column-major, leading dim ldz).
+// Per block of NB columns: (a) warp 0 factors the NB x NB diagonal block, (b) one thread per row of the
+// panel / per right-hand side solves against it, (c) the trailing update of [S | Z] is a K = NB
+// register-tiled GEMM over all threads.  3 barriers per block; the right-hand sides ride along, so
+// there is no separate triangular solve.  Returns false (uniformly) on a non-positive pivot.
+template <int NB>
+__device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz, int c0, int nc, int* s_ok) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *s_ok = 1;
+  __syncthreads();
+  for (int jb = 0; jb < r; jb += NB) {
+    const int nb = min(NB, r - jb);
+    double* D = S + jb + (long)jb * r;   // diagonal block, element (i,k) at D[i + k*r]
+    // (a) unblocked Cholesky of the diagonal block by warp 0 (lane = row)
+    if (warp == 0) {
+      for (int k = 0; k < nb; ++k) {
+        const double d = D[k + (long)k * r];
+        if (!(d > 0.0)) { if (lane == 0) *s_ok = 0; break; }
+        const double inv = rsqrt(d);
+        __syncwarp();
+        if (lane > k && lane < nb) D[lane + (long)k * r] *= inv;
+        if (lane == k) D[k + (long)k * r] = d * inv;
+        __syncwarp();
+        if (lane > k && lane < nb) {
+          const double lik = D[lane + (long)k * r];
+          for (int c = k + 1; c <= lane; ++c) D[lane + (long)c * r] = fma(-lik, D[c + (long)k * r], D[lane + (long)c * r]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (!*s_ok) break;
+    const int i0 = jb + nb, m = r - i0;  // trailing rows
+    // (b) panel rows: L21[i,:] = A21[i,:] L11^-T ; right-hand sides: Y1 = L11^-1 Z1
+    for (int t = tid; t < m + nc; t += blockDim.x) {
+      double x[NB];
+      if (t < m) {
+        double* row = S + (i0 + t) + (long)jb * r;   // element k at row[k*r]
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+          if (k < nb) {
+            double acc = row[(long)k * r];
+#pragma unroll
+            for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-x[p], D[k + (long)p * r], acc);
+            x[k] = acc / D[k + (long)k * r];
+          }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) if (k < nb) row[(long)k * r] = x[k];
+      } else {
+        double* col = Z + jb + (long)(c0 + t - m) * ldz;   // element k at col[k]
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+          if (k < nb) {
+            double acc = col[k];
+#pragma unroll
+            for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-D[k + (long)p * r], x[p], acc);
+            x[k] = acc / D[k + (long)k * r];
+          }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) if (k < nb) col[k] = x[k];
+      }
+    }
+    __syncthreads();
+    // (c) trailing update, 4x4 register tiles over rows [i0, r) x columns [S: i0..r-1 | Z: c0..c0+nc-1]
+    if (m > 0) {
+      const int ncol = m + nc;
+      const int gm = (m + 3) / 4, gn = (ncol + 3) / 4;
+      for (int t = tid; t < gm * gn; t += blockDim.x) {
+        const int ti = t % gm, tj = t / gm;
+        int ri[4], cj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { ri[u] = i0 + min(ti + u * gm, m - 1); cj[u] = min(tj + u * gn, ncol - 1); }
+        const double* bp[4];
+        int bs[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (cj[v] < m) { bp[v] = S + (i0 + cj[v]) + (long)jb * r; bs[v] = r; }      // L[c][jb+k]
+          else { bp[v] = Z + jb + (long)(c0 + cj[v] - m) * ldz; bs[v] = 1; }          // Y1[k][cz]
+        }
+        double acc[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+        for (int k = 0; k < nb; ++k) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) av[u] = S[ri[u] + (long)(jb + k) * r];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) bv[v] = bp[v][(long)k * bs[v]];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int il = ti + u * gm, cl = tj + v * gn;
+            if (il < m && cl < ncol) {
+              const int i = i0 + il;
+              if (cl < m) {
+                const int c = i0 + cl;
+                if (c <= i) S[i + (long)c * r] -= acc[u][v];
+              } else {
+                Z[i + (long)(c0 + cl - m) * ldz] -= acc[u][v];
+              }
+            }
+          }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  return *s_ok != 0;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -78,6 +78,8 @@ struct igv_batch {
   int* cnt_g = nullptr;                // B accepted GNSS rows
   double* gam_ws = nullptr;            // B
   double* Dws = nullptr;               // delayed-init workspace: B x (128*18 + 2)
+  double* pre_ws = nullptr;            // per (sequence, IMU step) Phi (225) + G*sigma (180), row-major
+  size_t pre_cap = 0;
   std::vector<double> chi2_host;
   // profiling (igv_profile_*)
   bool prof_on = false;

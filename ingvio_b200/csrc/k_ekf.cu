@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
   }
   __syncthreads();
   // (3) S = L L^T
-  const bool ok = cta_cholesky(S, r, r, &s_ok);
+  // (3)+(4)+(5) S = L L^T fused with Y = L^-1 Z (all N columns) and w = L^-1 res (column N)
+  const bool ok = a.gamma_only ? cta_chol_solve_fused<8>(S, r, Z, ldz, N, 1, &s_ok)
+                               : cta_chol_solve_fused<8>(S, r, Z, ldz, 0, N + 1, &s_ok);
   if (!ok) {
     if (tid == 0) {
       atomicOr(&a.flags[b], IGV_FLAG_CHOL_FAIL);
@@ -98,18 +100,12 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
     if (a.dx_out) for (int i = tid; i < N; i += blockDim.x) a.dx_out[(size_t)b * N + i] = 0.0;
     return;
   }
-  // (4) w = L^-1 res, gamma = |w|^2 ; optional gates
-  if (tid == 0) {
-    double* z = Z + (size_t)N * ldz;
+  if (tid < 32) {  // gamma = |w|^2
+    const double* w = Z + (size_t)N * ldz;
     double g = 0.0;
-    for (int i = 0; i < r; ++i) {
-      double acc = z[i];
-      for (int k = 0; k < i; ++k) acc = fma(-S[i + (size_t)k * r], z[k], acc);
-      z[i] = acc / S[i + (size_t)i * r];
-      g = fma(z[i], z[i], g);
-    }
-    s_red[0] = g;
-    if (a.gamma_out) a.gamma_out[b] = g;
+    for (int i = tid; i < r; i += 32) g = fma(w[i], w[i], g);
+    g = warp_sum(g);
+    if (tid == 0) { s_red[0] = g; if (a.gamma_out) a.gamma_out[b] = g; }
   }
   __syncthreads();
   if (a.gamma_only) return;
@@ -127,9 +123,6 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
       return;
     }
   }
-  // (5) Y = L^-1 Z (columns 0..N-1), in place
-  cta_trsm_lower(S, r, Z, r, N, ldz);
-  __syncthreads();
   // (6) dx = Y^T w
   double* dxb = a.dxws + (size_t)b * ld;
   for (int i = tid; i < N; i += blockDim.x) {

@@ -21,18 +21,21 @@ struct PropArgs {
   int n_steps;
   const double* gyro; const double* accel; const double* dt;  // IMU mode (Phi == nullptr)
   const double* Phi; const double* G;                         // covariance-only mode
+  const double* pre;                                          // IMU mode: per (b, step) 225 Phi + 180 G*sigma, row-major
   IgvDevParams prm;
   int idx_cb[4]; int idx_fs; int enable_gnss;
 };
 
 // thread 0: mean propagation and Phi (15x15, row-major in sPhi), Gs = G*diag(sigma) (15x12 row-major)
 __device__ void imu_step_mean(double* X, const double* wraw, const double* araw, double dt, const IgvDevParams& prm,
-                              const int* idx_cb, int idx_fs, double* sPhi, double* sG) {
+                              const int* idx_cb, int idx_fs, double* sPhi, double* sG, bool zero_fill = true) {
   double* R = X; double* p = X + 9; double* v = X + 12;
   const double* bg = X + 15; const double* ba = X + 18;
-  for (int i = 0; i < 225; ++i) sPhi[i] = 0.0;
+  if (zero_fill) {  // the (b, step) workspace is zeroed once at allocation: the sparsity pattern never changes
+    for (int i = 0; i < 225; ++i) sPhi[i] = 0.0;
+    for (int i = 0; i < 180; ++i) sG[i] = 0.0;
+  }
   for (int i = 0; i < 15; ++i) sPhi[16 * i] = 1.0;
-  for (int i = 0; i < 180; ++i) sG[i] = 0.0;
   double Rh[9], ph[3], vh[3], S[9], T[9];
   for (int i = 0; i < 9; ++i) Rh[i] = R[i];
   for (int i = 0; i < 3; ++i) { ph[i] = p[i]; vh[i] = v[i]; }
@@ -83,15 +86,36 @@ __device__ void imu_step_mean(double* X, const double* wraw, const double* araw,
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) sPhi[(3 + r) * 15 + 9 + c] = -A1[3 * r + c] * dt + A2[3 * r + c];
 }
 
+// One THREAD per sequence: the K mean-propagation steps are sequential within a sequence but independent
+// across sequences; Phi_k and G_k*sigma go to a workspace that the strip kernel consumes.
+__global__ void __launch_bounds__(64) k_imu_mean(double* X, int xsize, int B, int n_steps, const double* gyro,
+                                                   const double* accel, const double* dt, IgvDevParams prm,
+                                                   int idx_cb0, int idx_cb1, int idx_cb2, int idx_cb3, int idx_fs,
+                                                   double* pre) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int idx_cb[4] = {idx_cb0, idx_cb1, idx_cb2, idx_cb3};
+  double* Xb = X + (size_t)b * xsize;
+  double Xl[IGV_X_CORE];  // R, p, v, bg, ba, (extrinsics untouched), GNSS scalars: keep on chip across the K steps
+  for (int i = 0; i < IGV_X_CORE; ++i) Xl[i] = Xb[i];
+  for (int step = 0; step < n_steps; ++step) {
+    const size_t o = (size_t)b * n_steps + step;
+    const double d = dt[o];
+    if (d >= 1e-6)  // ImuPropagator.cpp:262
+      imu_step_mean(Xl, gyro + o * 3, accel + o * 3, d, prm, idx_cb, idx_fs, pre + o * 405, pre + o * 405 + 225, false);
+  }
+  for (int i = 0; i < 15; ++i) Xb[i] = Xl[i];          // R, p, v
+  for (int i = 33; i < 37; ++i) Xb[i] = Xl[i];         // clock biases (ImuPropagator.cpp:139-148)
+}
+
 __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
   extern __shared__ double sm[];
+  constexpr int S = kMaxStrip;  // fixed stride of every small matrix: index math folds to shifts/multiplies
   const int b = blockIdx.x, N = a.N, ld = a.ld, tid = threadIdx.x;
   double* Pb = a.P + (size_t)b * ld * ld;
-  double* Xb = a.X ? a.X + (size_t)b * a.xsize : nullptr;
-  __shared__ int cidx[kMaxStrip];
+  __shared__ int cidx[S];
   __shared__ int s_nC, s_nS, s_has_fs;
-  __shared__ double sPhi[225], sG[180], sT[kMaxStrip * kMaxStrip], sQ[kMaxStrip * kMaxStrip], sM[15 * 12];
-  __shared__ double sBlk[kMaxStrip * kMaxStrip];
+  __shared__ __align__(16) double sPhi[225], sG[180], sT[S * S], sQ[S * S], sM[15 * 12], sBlk[S * S];
   __shared__ double s_dt;
   if (tid == 0) {
     int n = 0;
@@ -102,113 +126,123 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
     s_nC = n;
     if (a.enable_gnss && a.idx_fs >= 0) { cidx[n++] = a.idx_fs; s_has_fs = 1; }
     s_nS = n;
+    for (int i = n; i < S; ++i) cidx[i] = 0;
   }
   __syncthreads();
   const int nC = s_nC, nS = s_nS;
   const bool has_fs = s_has_fs != 0;
-  double* W = sm;  // nS x N row-major: W[r*N + j] = P[cidx[r], j]
-  for (int t = tid; t < nS * N; t += blockDim.x) {
-    const int r = t / N, j = t % N;
-    W[t] = Pb[j + (size_t)cidx[r] * ld];  // P symmetric: row cidx[r] == column cidx[r] (coalesced read)
-  }
+  double* W = sm;  // S x N row-major (rows >= nS are zero): W[r*N + j] = P[cidx[r], j]
+  for (int r = 0; r < S; ++r)
+    for (int j = tid; j < N; j += blockDim.x)
+      W[r * N + j] = (r < nS) ? Pb[j + (size_t)cidx[r] * ld] : 0.0;  // P symmetric: row == column (coalesced)
   __syncthreads();
   for (int step = 0; step < a.n_steps; ++step) {
-    if (tid == 0) {
-      double dt;
-      if (a.Phi) {
-        dt = a.dt[b];
-        const double* Ph = a.Phi + (size_t)b * 225;
-        const double* Gg = a.G + (size_t)b * 180;
-        for (int r = 0; r < 15; ++r) for (int c = 0; c < 15; ++c) sPhi[r * 15 + c] = Ph[r + 15 * c];
-        const double sg[4] = {a.prm.noise_g, a.prm.noise_a, a.prm.noise_bg, a.prm.noise_ba};
-        for (int r = 0; r < 15; ++r) for (int c = 0; c < 12; ++c) sG[r * 12 + c] = Gg[r + 15 * c] * sg[c / 3];
-      } else {
-        dt = a.dt[(size_t)b * a.n_steps + step];
-        if (dt >= 1e-6)  // ImuPropagator.cpp:262
-          imu_step_mean(Xb, a.gyro + ((size_t)b * a.n_steps + step) * 3, a.accel + ((size_t)b * a.n_steps + step) * 3,
-                        dt, a.prm, a.idx_cb, (a.enable_gnss ? a.idx_fs : -1), sPhi, sG);
-      }
-      s_dt = dt;
+    // load this step's Phi (15x15) and G*diag(sigma) (15x12), row-major, all threads
+    if (a.Phi) {
+      const double* Ph = a.Phi + (size_t)b * 225;
+      const double* Gg = a.G + (size_t)b * 180;
+      const double sg[4] = {a.prm.noise_g, a.prm.noise_a, a.prm.noise_bg, a.prm.noise_ba};
+      for (int t = tid; t < 225; t += blockDim.x) sPhi[t] = Ph[(t / 15) + 15 * (t % 15)];
+      for (int t = tid; t < 180; t += blockDim.x) sG[t] = Gg[(t / 12) + 15 * (t % 12)] * sg[(t % 12) / 3];
+      if (tid == 0) s_dt = a.dt[b];
+    } else {
+      const double* pr = a.pre + ((size_t)b * a.n_steps + step) * 405;
+      for (int t = tid; t < 225; t += blockDim.x) sPhi[t] = pr[t];
+      for (int t = tid; t < 180; t += blockDim.x) sG[t] = pr[225 + t];
+      if (tid == 0) s_dt = a.dt[(size_t)b * a.n_steps + step];
     }
     __syncthreads();
     const double dt = s_dt;
-    if (!a.Phi && dt < 1e-6) { __syncthreads(); continue; }  // uniform
-    // small transition T (nC x nS): [Phi 0; 0 I] + dt on (cb, fs)
-    for (int t = tid; t < nC * nS; t += blockDim.x) {
-      const int r = t / nS, c = t % nS;
-      double val = (r == c) ? 1.0 : 0.0;
+    if (!a.Phi && dt < 1e-6) { __syncthreads(); continue; }  // uniform (ImuPropagator.cpp:262)
+    // small transition T (S x S, zero padded): [Phi 0; 0 I] + dt on (cb, fs); rows >= nC are identity rows
+    for (int t = tid; t < S * S; t += blockDim.x) {
+      const int r = t / S, c = t % S;
+      double val = (r == c && r < nS) ? 1.0 : 0.0;
       if (r < 15 && c < 15) val = sPhi[r * 15 + c];
-      else if (r >= 15 && c == nS - 1 && has_fs) val = dt;
-      sT[r * kMaxStrip + c] = val;
+      else if (r >= 15 && r < nC && c == nS - 1 && has_fs) val = dt;
+      sT[t] = val;
     }
     // M = Phi * Gs (15 x 12)
     for (int t = tid; t < 180; t += blockDim.x) {
       const int r = t / 12, c = t % 12;
       double acc = 0.0;
+#pragma unroll
       for (int k = 0; k < 15; ++k) acc = fma(sPhi[r * 15 + k], sG[k * 12 + c], acc);
       sM[t] = acc;
     }
     __syncthreads();
-    // Q block (nS x nS): dt * M M^T on the IMU part (StateManager.cpp:97) + clock terms (:99-116)
-    for (int t = tid; t < nS * nS; t += blockDim.x) {
-      const int r = t / nS, c = t % nS;
+    // Q block: dt * M M^T on the IMU part (StateManager.cpp:97) + clock terms (:99-116)
+    for (int t = tid; t < S * S; t += blockDim.x) {
+      const int r = t / S, c = t % S;
       double q = 0.0;
       if (r < 15 && c < 15) {
+#pragma unroll
         for (int k = 0; k < 12; ++k) q = fma(sM[r * 12 + k], sM[c * 12 + k], q);
         q *= dt;
-      } else if (a.enable_gnss && r >= 15 && c >= 15) {
+      } else if (a.enable_gnss && r >= 15 && c >= 15 && r < nS && c < nS) {
         const bool rf = has_fs && (r == nS - 1), cf = has_fs && (c == nS - 1);
         const double rw2 = a.prm.noise_cb_rw * a.prm.noise_cb_rw;
         if (!rf && !cf) q = dt * a.prm.noise_cb * a.prm.noise_cb + dt * dt * dt * rw2;
         else if (rf && cf) q = dt * rw2;
         else q = dt * dt * rw2;
       }
-      sQ[r * kMaxStrip + c] = q;
+      sQ[t] = q;
     }
-    // (1) column update on the strip: W1[r, cidx[c]] = sum_k W[r, cidx[k]] T[c,k]   (c < nC)
-    for (int t = tid; t < nS * nC; t += blockDim.x) {
-      const int r = t / nC, c = t % nC;
+    // (1) column update on the strip: W1[r, cidx[c]] = sum_k W[r, cidx[k]] T[c,k]
+    for (int t = tid; t < S * S; t += blockDim.x) {
+      const int r = t / S, c = t % S;
       double acc = 0.0;
-      for (int k = 0; k < nS; ++k) acc = fma(W[r * N + cidx[k]], sT[c * kMaxStrip + k], acc);
-      sBlk[r * kMaxStrip + c] = acc;
+      if (r < nS && c < nS) {
+        for (int k = 0; k < nS; ++k) acc = fma(W[r * N + cidx[k]], sT[c * S + k], acc);
+      }
+      sBlk[t] = acc;
     }
     __syncthreads();
-    for (int t = tid; t < nS * nC; t += blockDim.x) {
-      const int r = t / nC, c = t % nC;
-      W[r * N + cidx[c]] = sBlk[r * kMaxStrip + c];
+    for (int t = tid; t < S * S; t += blockDim.x) {
+      const int r = t / S, c = t % S;
+      if (r < nS && c < nS) W[r * N + cidx[c]] = sBlk[t];
     }
     __syncthreads();
-    // (2) row update: W2[c, j] = sum_k T[c,k] W1[k, j]   (c < nC), one thread per column j
+    // (2) row update: W2[c, j] = sum_k T[c,k] W1[k, j], one thread per column j; the column lives in
+    //     registers and T is zero padded, so both loops are fully unrolled (no predicates, no local memory)
     for (int j = tid; j < N; j += blockDim.x) {
-      double col[kMaxStrip];
-      for (int k = 0; k < nS; ++k) col[k] = W[k * N + j];
-      for (int c = 0; c < nC; ++c) {
-        double acc = 0.0;
-        for (int k = 0; k < nS; ++k) acc = fma(sT[c * kMaxStrip + k], col[k], acc);
-        W[c * N + j] = acc;
+      double col[S];
+#pragma unroll
+      for (int k = 0; k < S; ++k) col[k] = W[k * N + j];
+#pragma unroll 4
+      for (int c = 0; c < S; ++c) {
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < S; k += 2) {
+          const double2 tv = *reinterpret_cast<const double2*>(&sT[c * S + k]);
+          acc0 = fma(tv.x, col[k], acc0);
+          acc1 = fma(tv.y, col[k + 1], acc1);
+        }
+        if (c < nS) W[c * N + j] = acc0 + acc1;
       }
     }
     __syncthreads();
     // (3) + Q and (4) symmetrise the strip x strip block (StateManager.cpp:118)
-    for (int t = tid; t < nS * nS; t += blockDim.x) {
-      const int r = t / nS, c = t % nS;
-      sBlk[r * kMaxStrip + c] = 0.5 * ((W[r * N + cidx[c]] + sQ[r * kMaxStrip + c]) +
-                                       (W[c * N + cidx[r]] + sQ[c * kMaxStrip + r]));
+    for (int t = tid; t < S * S; t += blockDim.x) {
+      const int r = t / S, c = t % S;
+      double v = 0.0;
+      if (r < nS && c < nS) v = 0.5 * ((W[r * N + cidx[c]] + sQ[r * S + c]) + (W[c * N + cidx[r]] + sQ[c * S + r]));
+      sBlk[t] = v;
     }
     __syncthreads();
-    for (int t = tid; t < nS * nS; t += blockDim.x) {
-      const int r = t / nS, c = t % nS;
-      W[r * N + cidx[c]] = sBlk[r * kMaxStrip + c];
+    for (int t = tid; t < S * S; t += blockDim.x) {
+      const int r = t / S, c = t % S;
+      if (r < nS && c < nS) W[r * N + cidx[c]] = sBlk[t];
     }
     __syncthreads();
   }
   // write back rows and mirrored columns
-  for (int t = tid; t < nS * N; t += blockDim.x) {
-    const int r = t / N, j = t % N;
-    const double val = W[t];
-    Pb[j + (size_t)cidx[r] * ld] = val;
-    Pb[cidx[r] + (size_t)j * ld] = val;
-  }
+  for (int r = 0; r < nS; ++r)
+    for (int j = tid; j < N; j += blockDim.x) {
+      const double val = W[r * N + j];
+      Pb[j + (size_t)cidx[r] * ld] = val;
+      Pb[cidx[r] + (size_t)j * ld] = val;
+    }
 }
 
 }  // namespace
@@ -220,12 +254,26 @@ void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const d
   a.P = h->Pc(); a.ld = h->ld; a.N = h->N;
   a.X = h->Xc(); a.xsize = h->xsize;
   a.n_steps = n_steps;
-  a.gyro = gyro; a.accel = accel; a.dt = dt; a.Phi = Phi; a.G = G;
+  a.gyro = gyro; a.accel = accel; a.dt = dt; a.Phi = Phi; a.G = G; a.pre = nullptr;
   a.prm = h->params;
   IgvLayout L = h->layout();
   for (int i = 0; i < 4; ++i) a.idx_cb[i] = L.idx_gnss[i];
   a.idx_fs = L.idx_gnss[IGV_GNSS_FS];
   a.enable_gnss = 1;
+  if (!Phi) {
+    const size_t need = (size_t)h->B * n_steps * 405;
+    if (need > h->pre_cap) {
+      if (h->pre_ws) { cudaStreamSynchronize(h->stream); cudaFree(h->pre_ws); }
+      cudaMalloc(reinterpret_cast<void**>(&h->pre_ws), sizeof(double) * need);
+      cudaMemsetAsync(h->pre_ws, 0, sizeof(double) * need, h->stream);
+      h->pre_cap = need;
+    }
+    a.pre = h->pre_ws;
+    k_imu_mean<<<(h->B + 63) / 64, 64, 0, h->stream>>>(h->Xc(), h->xsize, h->B, n_steps, gyro, accel, dt, h->params,
+                                                      a.idx_cb[0], a.idx_cb[1], a.idx_cb[2], a.idx_cb[3], a.idx_fs,
+                                                      h->pre_ws);
+    h->launches++;
+  }
   const size_t smem = sizeof(double) * kMaxStrip * h->N;
   static bool attr_set = false;
   if (!attr_set) {

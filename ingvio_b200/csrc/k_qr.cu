@@ -132,15 +132,31 @@ __global__ void __launch_bounds__(W * 32, MINB) k_qr_compress(QrArgs a) {
         if (j >= n) break;  // the residual column is never eliminated
         double* vb = vbuf + (it & 1u) * (W * ROWS);
         ++it;
-        if (lane == lj) {
+        double sigma;
+        if constexpr (W == 1) {
+          // single-warp stream: the owner lane holds the whole column of this chunk -> local norm, no barrier
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          if (lane == lj) {
 #pragma unroll
-          for (int r = 0; r < ROWS; r += 2)
-            *reinterpret_cast<double2*>(vb + warp * ROWS + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
+            for (int r = 0; r < ROWS; r += 2) {
+              *reinterpret_cast<double2*>(vb + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
+              if (r % 4 == 0) { s0 = fma(tile[r][sj], tile[r][sj], s0); s1 = fma(tile[r + 1][sj], tile[r + 1][sj], s1); }
+              else { s2 = fma(tile[r][sj], tile[r][sj], s2); s3 = fma(tile[r + 1][sj], tile[r + 1][sj], s3); }
+            }
+          }
+          sigma = __shfl_sync(0xffffffffu, (s0 + s1) + (s2 + s3), lj);
+          __syncwarp();
+        } else {
+          if (lane == lj) {
+#pragma unroll
+            for (int r = 0; r < ROWS; r += 2)
+              *reinterpret_cast<double2*>(vb + warp * ROWS + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
+          }
+          __syncthreads();  // A: raw column visible
+          double ss = 0.0;
+          for (int i = lane; i < W * ROWS; i += 32) ss = fma(vb[i], vb[i], ss);
+          sigma = warp_sum(ss);
         }
-        __syncthreads();  // A: raw column visible
-        double ss = 0.0;
-        for (int i = lane; i < W * ROWS; i += 32) ss = fma(vb[i], vb[i], ss);
-        const double sigma = warp_sum(ss);
         if (sigma == 0.0) continue;  // nothing below the diagonal in this chunk (uniform branch)
         // Householder with the UN-normalised vector v' = [alpha - beta ; raw column]:
         //   H = I - tau' v' v'^T,  tau' = 1 / (beta^2 - alpha beta) = 1 / (nrm2 + |alpha| |beta|)
@@ -173,22 +189,31 @@ __global__ void __launch_bounds__(W * 32, MINB) k_qr_compress(QrArgs a) {
               d[s][(r + 1) % ACC] = fma(v.y, tile[r + 1][s], d[s][(r + 1) % ACC]);
             }
         }
+        double dsum[NSLOT];
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-          if (s <= sj && act[s]) {
-            double t = d[s][0] + d[s][1];
-            if (ACC == 4) t += d[s][2] + d[s][3];
-            s_part[(warp * NSLOT + s) * 32 + lane] = t;
-          }
-        __syncthreads();  // C: partial dots visible
+        for (int s = 0; s < NSLOT; ++s) {
+          double t = d[s][0] + d[s][1];
+          if (ACC == 4) t += d[s][2] + d[s][3];
+          dsum[s] = t;
+        }
+        if constexpr (W > 1) {
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s)
+            if (s <= sj && act[s]) s_part[(warp * NSLOT + s) * 32 + lane] = dsum[s];
+          __syncthreads();  // C: partial dots visible
+        }
         double wks[NSLOT];
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
           wks[s] = 0.0;
           if (s <= sj && act[s]) {
             double acc = 0.0;
+            if constexpr (W > 1) {
 #pragma unroll
-            for (int w = 0; w < W; ++w) acc += s_part[(w * NSLOT + s) * 32 + lane];
+              for (int w = 0; w < W; ++w) acc += s_part[(w * NSLOT + s) * 32 + lane];
+            } else {
+              acc = dsum[s];
+            }
             const double wk = taup * fma(amb, rjk[s], acc);
             if (warp == 0) Rp[off(j) + (mycol[s] - j)] = fma(-wk, amb, rjk[s]);
             wks[s] = wk;
@@ -235,7 +260,12 @@ void launch_qr(const QrArgs& a, int split, int B, int max_frange, cudaStream_t s
   if (nslot <= 1) launch_one<1, 32, 4, 2>(a, split, B, max_frange, st);
   else if (nslot <= 2) launch_one<2, 32, 4, 2>(a, split, B, max_frange, st);
   else if (nslot <= 3) {
-    if (cfg == 1) launch_one<3, 16, 4, 3>(a, split, B, max_frange, st);
+    // one independent single-warp stream per CTA when there are enough CTAs to fill the chip
+    if (cfg == 0 && a.src_mode == 0 && (long)B * split >= 1000) launch_one<3, 32, 1, 8>(a, split, B, max_frange, st);
+    else if (cfg == 5) launch_one<3, 32, 1, 8>(a, split, B, max_frange, st);
+    else if (cfg == 6) launch_one<3, 16, 1, 12>(a, split, B, max_frange, st);
+    else if (cfg == 7) launch_one<3, 24, 1, 10>(a, split, B, max_frange, st);
+    else if (cfg == 1) launch_one<3, 16, 4, 3>(a, split, B, max_frange, st);
     else if (cfg == 2) launch_one<3, 16, 8, 1>(a, split, B, max_frange, st);
     else if (cfg == 3) launch_one<3, 32, 8, 1>(a, split, B, max_frange, st);
     else if (cfg == 4) launch_one<3, 24, 4, 2>(a, split, B, max_frange, st);
