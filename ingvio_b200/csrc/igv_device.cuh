@@ -177,6 +177,7 @@ __device__ __forceinline__ void cta_gemm(int M, int N, int K, FA a, FB b, FC c) 
     for (int u = 0; u < TM; ++u)
 #pragma unroll
       for (int v = 0; v < TN; ++v) acc[u][v] = 0.0;
+#pragma unroll 2
     for (int k = 0; k < K; ++k) {
       double av[TM], bv[TN];
 #pragma unroll
@@ -245,6 +246,7 @@ __device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int r
 template <int NB>
 __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz, int c0, int nc, int* s_ok) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_rdiag[NB];   // 1 / L[k][k] of the current diagonal block
   if (tid == 0) *s_ok = 1;
   __syncthreads();
   for (int jb = 0; jb < r; jb += NB) {
@@ -258,7 +260,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz
         const double inv = rsqrt(d);
         __syncwarp();
         if (lane > k && lane < nb) D[lane + (long)k * r] *= inv;
-        if (lane == k) D[k + (long)k * r] = d * inv;
+        if (lane == k) { D[k + (long)k * r] = d * inv; s_rdiag[k] = inv; }
         __syncwarp();
         if (lane > k && lane < nb) {
           const double lik = D[lane + (long)k * r];
@@ -281,7 +283,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz
             double acc = row[(long)k * r];
 #pragma unroll
             for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-x[p], D[k + (long)p * r], acc);
-            x[k] = acc / D[k + (long)k * r];
+            x[k] = acc * s_rdiag[k];
           }
 #pragma unroll
         for (int k = 0; k < NB; ++k) if (k < nb) row[(long)k * r] = x[k];
@@ -293,7 +295,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz
             double acc = col[k];
 #pragma unroll
             for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-D[k + (long)p * r], x[p], acc);
-            x[k] = acc / D[k + (long)k * r];
+            x[k] = acc * s_rdiag[k];
           }
 #pragma unroll
         for (int k = 0; k < NB; ++k) if (k < nb) col[k] = x[k];
