@@ -96,12 +96,19 @@ def _null_project(Hf, H, res, row_cnt):
 
 
 def _spqr_thin(H_large, res_large, keep_rows):
-    """RemoveLostUpdate.cpp:139-160 etc.: Q^T [H, r] with natural ordering, keep the top rows."""
-    if H_large.shape[0] > H_large.shape[1]:
-        Q, _ = np.linalg.qr(H_large, mode="complete")
-        H_temp = Q.T @ H_large
-        r_temp = Q.T @ res_large
-        return H_temp[:keep_rows, :], r_temp[:keep_rows]
+    """RemoveLostUpdate.cpp:139-160 etc.: Q^T [H, r] with natural ordering, keep the top rows.
+
+    Only Q^T H and Q^T r are consumed by the reference, never Q itself, so the economy factor of
+    [H | r] carries everything: its first n columns are Q^T H (upper triangular, zero below row n) and
+    its last column is Q^T r with the whole tail of the residual folded into entry n. Keeping more than
+    n rows (RemoveLost keeps all of them, :153) only appends rows whose H part is zero, which change
+    neither the posterior nor dx; they are returned as that single folded row. This avoids the m x m Q
+    that `mode="complete"` would allocate (4 GB at config c5)."""
+    m, n = H_large.shape
+    if m > n:
+        R = np.linalg.qr(np.hstack([H_large, res_large.reshape(-1, 1)]), mode="r")
+        rows = n if keep_rows <= n else min(n + 1, R.shape[0])
+        return R[:rows, :n], R[:rows, n]
     return H_large, res_large
 
 

@@ -477,3 +477,25 @@ def test_full_size_properties_c2_batch():
     g.synchronize()
     assert np.array_equal(g.get_full_cov(), P_post)
     assert np.array_equal(g.get_state(), X_post)
+
+
+def test_c5_stress_frames_against_oracle():
+    """BASELINE config c5 (SW=30, 400 feats, 20 sats, N=207; stack 22800 x 180): exercises the general-size
+    paths (P_s read from global memory, 6 column slots in the QR kernel, EKF operands spilled to the
+    global workspace) while the window fills and for two steady-state frames, FP64 bars as everywhere."""
+    wl = WORKLOADS["c5"]
+    fp = filter_params(wl, chi2_max_dof=200)
+    st = SyntheticStream(wl, 1)
+    orc = make_oracles(wl, st, fp)
+    g = make_gpu(wl, st, fp)
+    for i in range(32):
+        fr = st.next_frame()
+        out = gstep(g, fr, fp, want=(i >= 29))
+        orc[0].step(fr.seq(0))
+        if i in (4, 12, 20, 26) or i >= 29:
+            assert_state_close(g, orc, wl.sw, what=f"c5 frame {i}")
+        if i >= 29:
+            gl = orc[0].last["gammas"]
+            assert out["visual"]["accepted"][0] == sum(1 for x in gl if x[3])
+    assert g.curr_cov_size() == 21 + 6 + 6 * 29
+    assert np.all((g.flags() & 3) == 0)
