@@ -208,12 +208,13 @@ igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a);
  * H_old: B x (rows x n_old) col-major (ld = rows), H_new: B x rows, res: B x rows.
  * accepted_out: B ints (0/1); sequences that fail the chi^2 keep a decoupled variable with the
  * supplied prior_cov_if_rejected so that the batch keeps one layout. gtype >= 0 registers the new
- * scalar as that GNSS state (value: B doubles), gtype < 0 adds an opaque scalar. */
+ * scalar as that GNSS state (value: B doubles), gtype < 0 adds an opaque scalar. dx_out (optional,
+ * B x (N+1)) receives the correction of the residual EKF for the caller's Type objects. */
 igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value, int n_blocks,
                                     const int* blk_idx, const int* blk_size, int rows, const double* H_old,
                                     const double* H_new, const double* res, double noise_iso,
                                     double chi2_mult, int do_chi2, double prior_cov_if_rejected,
-                                    int* accepted_out);
+                                    int* accepted_out, double* dx_out);
 /* StateManager::replaceVarLinear (StateManager.cpp:632-693). H: size(target) x n, col-major, B x ... */
 igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size, int n_blocks,
                                   const int* blk_idx, const int* blk_size, const double* H);

@@ -85,7 +85,7 @@ SIGNATURES = {
     "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
     "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
     "igv_add_variable_delayed": (C.c_int, [_H, C.c_int, _VP, C.c_int, c_ip, c_ip, C.c_int, _VP, _VP, _VP,
-                                           C.c_double, C.c_double, C.c_int, C.c_double, _VP]),
+                                           C.c_double, C.c_double, C.c_int, C.c_double, _VP, _VP]),
     "igv_replace_var_linear": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_ip, c_ip, _VP]),
     "igv_get_flags": (C.c_int, [_H, _VP, C.c_int]),
     "igv_cov_trace": (C.c_int, [_H, _VP]),

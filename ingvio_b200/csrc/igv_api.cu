@@ -632,7 +632,7 @@ igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
 igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value, int n_blocks, const int* blk_idx,
                                     const int* blk_size, int rows, const double* H_old, const double* H_new,
                                     const double* res, double noise_iso, double chi2_mult, int do_chi2,
-                                    double prior_cov_if_rejected, int* accepted_out) {
+                                    double prior_cov_if_rejected, int* accepted_out, double* dx_out) {
   if (!h || !H_old || !H_new || !res || rows < 1 || rows > 128 || gtype > 5) return IGV_ERR_INVALID;
   if (rows <= 1) return fail(h, IGV_ERR_INVALID, "H_new rows should be larger than H_new cols");  // StateManager.cpp:574-578
   if (gtype >= 0 && h->layout().idx_gnss[gtype] >= 0) return fail(h, IGV_ERR_STATE, "New var already in state");
@@ -662,8 +662,12 @@ igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value
   e.res = h->Dws + B * rows * blk.n + 1; e.strideRes = rows; e.res_inc = 1;
   e.R = nullptr; e.strideR = 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
   e.only_if = dacc; e.apply_boxplus = 1;
+  double* ddx = nullptr;
+  IGV_TRY(out_buf(h, dx_out, B * h->N, &ddx));
+  e.dx_out = ddx;
   igv_launch_ekf(h, e);
   IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, dx_out, ddx, B * h->N));
   if (accepted_out) {
     if (h->ptr_mode == IGV_PTR_DEVICE)
       IGV_CUDA(h, cudaMemcpyAsync(accepted_out, dacc, sizeof(int) * B, cudaMemcpyDeviceToDevice, h->stream));

@@ -284,7 +284,7 @@ class BatchFilter:
         self._ck(self.lib.igv_add_variable_delayed(self.h, gtype, a[3].ptr, len(var_old_order), idx, size, rows,
                                                    a[0].ptr, a[1].ptr, a[2].ptr, float(noise_iso), float(chi2_mult),
                                                    int(do_chi2), float(prior_cov_if_rejected),
-                                                   C.c_void_p(acc.ctypes.data)))
+                                                   C.c_void_p(acc.ctypes.data), None))
         return acc.astype(bool)
 
     def replace_var_linear(self, target, dependence_order, H):
