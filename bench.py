@@ -364,6 +364,22 @@ def main():
         lib.igv_profile_read(g.h, ms_arr, cnt_arr, 1)
         lib.igv_profile_enable(g.h, 0)
         fam = {n: dict(ms=ms_arr[k], launches=int(cnt_arr[k])) for k, n in enumerate(capi.KERNEL_FAMILIES)}
+        # ---- (4) extra (not part of the metric): the "next" row, device-side triangulation of the same tracks ----
+        fi = seg(2)[-1]
+        pf_d = torch.zeros((B, wl.feats, 3), dtype=torch.float64, device=dev)
+        ok_d = torch.zeros((B, wl.feats), dtype=torch.uint8, device=dev)
+        tri_ms = None
+        if wl.feats > 0 and g.num_clones() >= 5:
+            for _ in range(2):
+                g.triangulate(dev_frames[fi]["obs"], dev_frames[fi]["mask"], dev_frames[fi]["anchor"], pf_out=pf_d, ok_out=ok_d)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            for _ in range(5):
+                g.triangulate(dev_frames[fi]["obs"], dev_frames[fi]["mask"], dev_frames[fi]["anchor"], pf_out=pf_d, ok_out=ok_d)
+            e1.record(ts)
+            torch.cuda.synchronize(dev)
+            tri_ms = e0.elapsed_time(e1) / 5
+            tri_ok = float(ok_d.float().mean().item())
         flags = g.flags()
         tr = g.cov_trace()
         assert np.all(np.isfinite(tr)) and np.all(tr > 0), "filter diverged"
@@ -415,6 +431,10 @@ def main():
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in fam.items()},
         "flagged_sequences": n_flag,
     }
+    if tri_ms is not None:
+        line["triangulation_extra"] = {"ms_per_step": tri_ms, "tracks_per_sec": B * wl.feats / (tri_ms * 1e-3),
+                                       "accepted_fraction": tri_ok,
+                                       "note": "igv_triangulate on the same tracks; outside the metric (SURVEY 8f-1)"}
 
     if rank == 0 and world == 1 and not args.no_latency:
         # single-sequence latency (BASELINE configs[1] as one filter): B = 1 handle, row-split QR

@@ -181,8 +181,31 @@ typedef struct {
   double* dx_out;            /* optional B x N                                                    */
   int* n_accepted_out;       /* optional B                                                        */
   double* gamma_out;         /* optional B x F chi^2 statistics (NaN for tracks with < 2 usable obs) */
+  const unsigned char* feat_ok; /* optional B x F: 0 skips the track (e.g. ok_out of igv_triangulate)   */
 } igv_msckf_args;
 igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a);
+
+/* ---- triangulation ("next" row) ----------------------------------------
+ * Triangulator::triangulateMonoObs / triangulateStereoObs (Triangulator.cpp:173-359) for every track
+ * of every sequence, over the clone poses of the device mean mirror, followed by the anchor-depth
+ * check of FeatureInfoManager::triangulateFeatureInfo{Mono,Stereo} (MapServerManager.cpp:275-341).
+ * pf_out / ok_out can be fed to igv_msckf_update (pf_w / feat_ok) without leaving the device. */
+typedef struct {
+  double trans_thres, huber_epsilon, conv_precision, init_damping;   /* Triangulator.h:38-41 */
+  int outer_loop_max_iter, inner_loop_max_iter;                      /* :42-43 */
+  double max_depth, min_depth;                                       /* :45-46 */
+} igv_tri_params;
+typedef struct {
+  int n_feats;                   /* F <= max_feats                                                    */
+  const double* obs;             /* B x F x SW x rho                                                  */
+  const unsigned char* obs_mask; /* B x F x SW                                                        */
+  int obs_slots;                 /* SW                                                                */
+  const int* anchor_slot;        /* optional B x F: landmark must lie in front of this clone's camera */
+  igv_tri_params prm;
+  double* pf_out;                /* B x F x 3 world position (zeros when not ok)                      */
+  unsigned char* ok_out;         /* B x F                                                             */
+} igv_tri_args;
+igv_status igv_triangulate(igv_batch* h, const igv_tri_args* a);
 
 /* ---- fused GNSS update ------------------------------------------------------------------------
  * GnssUpdate::updateTrackedSys (GnssUpdate.cpp:84-293) from the psr_res / dopp_res output

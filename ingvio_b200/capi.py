@@ -36,7 +36,18 @@ class igv_msckf_args(C.Structure):
     _fields_ = [("mode", C.c_int), ("n_feats", C.c_int), ("pf_w", C.c_void_p), ("anchor_slot", C.c_void_p),
                 ("obs", C.c_void_p), ("obs_mask", C.c_void_p), ("chi2_dof", C.c_void_p), ("obs_slots", C.c_int),
                 ("noise", C.c_double), ("max_valid", C.c_int), ("dx_out", C.c_void_p),
-                ("n_accepted_out", C.c_void_p), ("gamma_out", C.c_void_p)]
+                ("n_accepted_out", C.c_void_p), ("gamma_out", C.c_void_p), ("feat_ok", C.c_void_p)]
+
+
+class igv_tri_params(C.Structure):
+    _fields_ = [("trans_thres", C.c_double), ("huber_epsilon", C.c_double), ("conv_precision", C.c_double),
+                ("init_damping", C.c_double), ("outer_loop_max_iter", C.c_int), ("inner_loop_max_iter", C.c_int),
+                ("max_depth", C.c_double), ("min_depth", C.c_double)]
+
+
+class igv_tri_args(C.Structure):
+    _fields_ = [("n_feats", C.c_int), ("obs", C.c_void_p), ("obs_mask", C.c_void_p), ("obs_slots", C.c_int),
+                ("anchor_slot", C.c_void_p), ("prm", igv_tri_params), ("pf_out", C.c_void_p), ("ok_out", C.c_void_p)]
 
 
 class igv_gnss_args(C.Structure):
@@ -84,6 +95,7 @@ SIGNATURES = {
     "igv_box_plus": (C.c_int, [_H, _VP]),
     "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
     "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
+    "igv_triangulate": (C.c_int, [_H, C.POINTER(igv_tri_args)]),
     "igv_add_variable_delayed": (C.c_int, [_H, C.c_int, _VP, C.c_int, c_ip, c_ip, C.c_int, _VP, _VP, _VP,
                                            C.c_double, C.c_double, C.c_int, C.c_double, _VP, _VP]),
     "igv_replace_var_linear": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_ip, c_ip, _VP]),

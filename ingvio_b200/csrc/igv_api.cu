@@ -540,6 +540,7 @@ igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a) {
   IGV_TRY(stage(h, a->obs, B * F * SW * h->rho, &m.obs));
   IGV_TRY(stage(h, a->obs_mask, B * F * SW, &m.mask));
   IGV_TRY(stage(h, a->chi2_dof, B * F, &m.dof));
+  IGV_TRY(stage(h, a->feat_ok, B * F, &m.feat_ok));
   igv_launch_msckf_features(h, m);
   IGV_TRY(check_launch(h));
   igv_launch_qr_compress(h, a->n_feats, a->max_valid);
@@ -570,6 +571,30 @@ igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a) {
                                   sizeof(double) * F, B, k, h->stream));
     if (h->ptr_mode == IGV_PTR_HOST) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
   }
+  return IGV_OK;
+}
+
+// ---- triangulation ----------------------------------------------------------------------------------------
+igv_status igv_triangulate(igv_batch* h, const igv_tri_args* a) {
+  if (!h || !a || !a->obs || !a->obs_mask || !a->pf_out || !a->ok_out) return IGV_ERR_INVALID;
+  if (a->n_feats < 0 || a->n_feats > h->cfg.max_feats) return fail(h, IGV_ERR_CAPACITY, "n_feats exceeds max_feats");
+  IgvLayout L = h->layout();
+  if (a->obs_slots < L.n_clones) return fail(h, IGV_ERR_INVALID, "obs_slots smaller than the clone count");
+  if (L.n_clones > 64) return fail(h, IGV_ERR_CAPACITY, "triangulation supports at most 64 clones");
+  if (a->n_feats == 0) return IGV_OK;
+  arena_reset(h);
+  const size_t B = h->B, F = a->n_feats, SW = a->obs_slots;
+  const double* dobs; const unsigned char* dmask; const int* danc;
+  IGV_TRY(stage(h, a->obs, B * F * SW * h->rho, &dobs));
+  IGV_TRY(stage(h, a->obs_mask, B * F * SW, &dmask));
+  IGV_TRY(stage(h, a->anchor_slot, B * F, &danc));
+  double* dpf; unsigned char* dok;
+  IGV_TRY(out_buf(h, a->pf_out, B * F * 3, &dpf));
+  IGV_TRY(out_buf(h, a->ok_out, B * F, &dok));
+  igv_launch_triangulate(h, a->n_feats, a->obs_slots, dobs, dmask, danc, a->prm, dpf, dok);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, a->pf_out, dpf, B * F * 3));
+  IGV_TRY(fetch(h, a->ok_out, dok, B * F));
   return IGV_OK;
 }
 

@@ -139,10 +139,13 @@ void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& a);
 struct IgvMsckfLaunch {
   int mode, F, obs_slots, max_valid;
   const double* pf; const int* anchor; const double* obs; const unsigned char* mask; const int* dof;
+  const unsigned char* feat_ok;
   double noise;
 };
 void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& a);
 void igv_launch_qr_compress(igv_batch* h, int F, int max_valid);
+void igv_launch_triangulate(igv_batch* h, int F, int obs_slots, const double* obs, const unsigned char* mask,
+                            const int* anchor, const igv_tri_params& prm, double* pf_out, unsigned char* ok_out);
 
 struct IgvGnssLaunch {
   int S; const double* unit; const double* res_pos; const double* res_vel; const double* sig_psr;

@@ -35,6 +35,7 @@ struct FeatArgs {
   const double* X; int xsize; IgvLayout L;
   int mode, F, obs_slots;
   const double* pf; const int* anchor; const double* obs; const unsigned char* mask; const int* dof;
+  const unsigned char* feat_ok;
   double noise2;
   IgvDevParams prm;
   const double* chi2; int chi2_n;
@@ -87,6 +88,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
   for (int f = blockIdx.x * nwarps + warp; f < a.F; f += gridDim.x * nwarps) {
     const size_t bf = (size_t)b * a.F + f;          // index into the caller's arrays
     const size_t bo = (size_t)b * a.F_alloc + f;    // index into f_rows / f_gamma
+    if (a.feat_ok && !a.feat_ok[bf]) {              // track rejected upstream (e.g. triangulation failed)
+      if (lane == 0) { a.f_rows[bo] = 0; a.f_gamma[bo] = nan(""); }
+      continue;
+    }
     const double pf[3] = {a.pf[bf * 3], a.pf[bf * 3 + 1], a.pf[bf * 3 + 2]};
     const int anc = a.anchor[bf];
     const unsigned char* mk = a.mask + bf * a.obs_slots;
@@ -501,7 +506,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   a.P = h->Pc(); a.ld = h->ld;
   a.X = h->Xc(); a.xsize = h->xsize; a.L = h->layout();
   a.mode = l.mode; a.F = l.F; a.obs_slots = l.obs_slots;
-  a.pf = l.pf; a.anchor = l.anchor; a.obs = l.obs; a.mask = l.mask; a.dof = l.dof;
+  a.pf = l.pf; a.anchor = l.anchor; a.obs = l.obs; a.mask = l.mask; a.dof = l.dof; a.feat_ok = l.feat_ok;
   a.noise2 = l.noise * l.noise;
   a.prm = h->params;
   a.chi2 = h->chi2; a.chi2_n = h->chi2_n;

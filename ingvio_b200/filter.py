@@ -299,17 +299,17 @@ class BatchFilter:
 
     # ---- fused updaters ------------------------------------------------------------------------------
     def msckf_update(self, mode, pf_w, anchor_slot, obs, obs_mask, chi2_dof, noise, max_valid=0, want_dx=False,
-                     want_gamma=False, want_accepted=False):
+                     want_gamma=False, want_accepted=False, feat_ok=None):
         """RemoveLostUpdate / KeyframeUpdate / SwMargUpdate ::updateState* after track selection."""
         a = [_Arg(pf_w, np.float64), _Arg(anchor_slot, np.int32), _Arg(obs, np.float64), _Arg(obs_mask, np.uint8),
-             _Arg(chi2_dof, np.int32)]
+             _Arg(chi2_dof, np.int32), _Arg(feat_ok, np.uint8)]
         mode_ptr = self._set_mode(a)
         F = int(a[0].keep.shape[1])
         SW = int(a[3].keep.shape[2])
         args = capi.igv_msckf_args()
         args.mode = mode
         args.n_feats = F
-        args.pf_w, args.anchor_slot, args.obs, args.obs_mask, args.chi2_dof = [x.ptr for x in a]
+        args.pf_w, args.anchor_slot, args.obs, args.obs_mask, args.chi2_dof, args.feat_ok = [x.ptr for x in a]
         args.obs_slots = SW
         args.noise = float(noise)
         args.max_valid = int(max_valid)
@@ -326,6 +326,33 @@ class BatchFilter:
             args.n_accepted_out = C.c_void_p(outs["accepted"].ctypes.data)
         self._ck(self.lib.igv_msckf_update(self.h, C.byref(args)))
         return outs
+
+    def triangulate(self, obs, obs_mask, anchor_slot=None, pf_out=None, ok_out=None, **prm):
+        """Triangulator::triangulate{Mono,Stereo}Obs for every track (+ the anchor-depth check).
+        Host arrays in -> (pf (B,F,3), ok (B,F)) host arrays out; with torch CUDA tensors pass pf_out/ok_out."""
+        a = [_Arg(obs, np.float64), _Arg(obs_mask, np.uint8), _Arg(anchor_slot, np.int32)]
+        dev_out = pf_out is not None
+        if dev_out:
+            a += [_Arg(pf_out, np.float64), _Arg(ok_out, np.uint8)]
+        mode_ptr = self._set_mode(a)
+        F, SW = int(a[1].keep.shape[1]), int(a[1].keep.shape[2])
+        args = capi.igv_tri_args()
+        args.n_feats, args.obs, args.obs_mask, args.obs_slots, args.anchor_slot = F, a[0].ptr, a[1].ptr, SW, a[2].ptr
+        d = dict(trans_thres=0.1, huber_epsilon=0.01, conv_precision=5e-7, init_damping=1e-3, outer_loop_max_iter=10,
+                 inner_loop_max_iter=10, max_depth=60.0, min_depth=0.2)
+        d.update(prm)
+        for k, v in d.items():
+            setattr(args.prm, k, v)
+        if dev_out:
+            args.pf_out, args.ok_out = a[3].ptr, a[4].ptr
+            self._ck(self.lib.igv_triangulate(self.h, C.byref(args)))
+            return pf_out, ok_out
+        assert mode_ptr == capi.IGV_PTR_HOST
+        pf = np.zeros((self.B, F, 3))
+        ok = np.zeros((self.B, F), dtype=np.uint8)
+        args.pf_out, args.ok_out = C.c_void_p(pf.ctypes.data), C.c_void_p(ok.ctypes.data)
+        self._ck(self.lib.igv_triangulate(self.h, C.byref(args)))
+        return pf, ok.astype(bool)
 
     def gnss_update(self, unit, res_pos, res_vel, sigma_psr, sigma_dopp, sys, R_enu2ecef, is_adjust_yof=0,
                     chi2_test=0, strong_reject=1, want_dx=False):

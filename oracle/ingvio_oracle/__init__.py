@@ -20,4 +20,5 @@ from .imu_propagator import ImuCtrl, ImuPropagator  # noqa: F401
 from .visual_update import (FeatureInfo, KeyframeUpdate, RemoveLostUpdate, SwMargUpdate,  # noqa: F401
                             UpdateBase)
 from .gnss_update import GnssEpoch, GnssUpdate, calc_R_w2enu, dot_R_w2enu  # noqa: F401
+from .triangulator import TriParams, Triangulator  # noqa: F401
 from .frame import OracleFilter  # noqa: F401

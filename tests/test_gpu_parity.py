@@ -499,3 +499,70 @@ def test_c5_stress_frames_against_oracle():
             assert out["visual"]["accepted"][0] == sum(1 for x in gl if x[3])
     assert g.curr_cov_size() == 21 + 6 + 6 * 29
     assert np.all((g.flags() & 3) == 0)
+
+
+@pytest.mark.parametrize("wname", ["c1", "tiny_stereo"])
+def test_triangulate_matches_oracle(wname):
+    """igv_triangulate (Triangulator.cpp:173-359 + the anchor-depth check) vs the oracle on the filter's own
+    clone poses: same accept/reject decisions, world positions to 1e-7 m (both iterate to conv_precision)."""
+    import ingvio_oracle as o
+    wl = WORKLOADS[wname]
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 2)
+    orc = make_oracles(wl, st, fp)
+    g = make_gpu(wl, st, fp)
+    for _ in range(wl.sw + 1):
+        fr = st.next_frame()
+        gstep(g, fr, fp)
+        for b, f in enumerate(orc):
+            f.step(fr.seq(b))
+    fr = st.next_frame()
+    g.propagate_imu(fr.gyro, fr.accel, fr.dt)
+    g.augment_sliding_window_pose()
+    for b, f in enumerate(orc):
+        f.propagate_augment(fr.seq(b))
+    rng = np.random.default_rng(3)
+    mask = fr.obs_mask.copy()
+    mask[:, 0, :2] = 0                       # fewer views
+    mask[:, 1, :] = 0
+    mask[:, 1, :2] = 1                       # <= 4 mono views -> reject (:183)
+    obs = fr.obs.copy()
+    obs[:, 2] += rng.normal(0, 0.3, obs[:, 2].shape)   # garbage track: may not converge / fail depth gates
+    anchor = fr.anchor_slot.copy()
+    prm = dict(trans_thres=0.1, conv_precision=5e-7, max_depth=60.0)
+    pf, ok = g.triangulate(obs, mask, anchor, **prm)
+    tri = o.Triangulator(o.TriParams(**prm))
+    n_ok = 0
+    for b, f in enumerate(orc):
+        times = f.state.sw_times()
+        poses = [(f.state.sw_camleft_poses[t].rot, f.state.sw_camleft_poses[t].vec) for t in times]
+        for k in range(wl.feats):
+            oko, pfo = tri.triangulate_feature(obs[b, k], mask[b, k], poses, int(anchor[b, k]), wl.stereo,
+                                               (fp.T_cl2cr_R, fp.T_cl2cr_p))
+            assert bool(ok[b, k]) == bool(oko), (b, k)
+            if oko:
+                n_ok += 1
+                assert np.linalg.norm(pf[b, k] - pfo) <= 1e-7 * max(1.0, np.linalg.norm(pfo)), (b, k, pf[b, k], pfo)
+    assert n_ok > wl.feats and not ok[:, 1].any()
+    # device-resident chain: triangulate -> msckf_update(pf_w = pf_out, feat_ok = ok_out)
+    import torch
+    dev = torch.device("cuda:0")
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    pf_d = torch.zeros((2, wl.feats, 3), dtype=torch.float64, device=dev)
+    ok_d = torch.zeros((2, wl.feats), dtype=torch.uint8, device=dev)
+    obs_d, mask_d, anc_d = t(obs, torch.float64), t(mask, torch.uint8), t(anchor, torch.int32)
+    g.triangulate(obs_d, mask_d, anc_d, pf_out=pf_d, ok_out=ok_d, **prm)
+    dof = t(mask.sum(-1).astype(np.int32) - 1, torch.int32)
+    g.msckf_update(capi.VIS_ALL_OBS, pf_d, anc_d, obs_d, mask_d, dof, fp.visual_noise, 0, feat_ok=ok_d)
+    g.synchronize()
+    assert np.array_equal(pf_d.cpu().numpy(), pf) and np.array_equal(ok_d.cpu().numpy().astype(bool), ok)
+    for b, f in enumerate(orc):
+        frb = fr.seq(b)
+        frb.obs, frb.obs_mask, frb.pf_w = obs[b], mask[b] * ok[b][:, None], pf[b]
+        frb.obs_total = mask[b].sum(-1).astype(np.int32)
+        ms = f.build_map_server(frb)
+        ids = [k for k in sorted(ms) if ok[b, k]]
+        f.remove_lost.last_gammas = []
+        f.remove_lost.max_valid_ids = 10 ** 6
+        f.remove_lost.update_with_ids(f.state, ms, ids, wl.stereo, keep="cols")
+    assert_state_close(g, orc, wl.sw, what="triangulate -> msckf chain")
