@@ -402,8 +402,15 @@ def main():
     fp64_peak = C.c_double(0.0)
     lib.igv_measure_fp64_peak(local, C.byref(fp64_peak))
     total_prof_ms = sum(v["ms"] for v in fam.values())
+    traffic = None
+    try:  # DRAM bytes per launch of this kernel from the committed ncu capture, if it is the same configuration
+        tj = json.load(open(os.path.join(ROOT, "profiles", "qr_traffic.json")))
+        if tj.get("workload") == wl.name and int(tj.get("batch", -1)) == B:
+            traffic = float(tj["dram_bytes_per_launch"])
+    except Exception:
+        pass
     roofline = {"kernel": "k_qr_compress", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": qr_bytes, "avg_launch_ms": qr_ms,
                 "share_of_step": fam["qr"]["ms"] / total_prof_ms if total_prof_ms else None,
                 "note": "FP64 dense kernel: the binding roof is the DFMA pipe, see roofline_fp64"}
