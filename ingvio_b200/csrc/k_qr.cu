@@ -239,6 +239,262 @@ __global__ void __launch_bounds__(W * 32, MINB) k_qr_compress(QrArgs a) {
   }
 }
 
+// ---- single-warp stream kernel (large batches) -------------------------------------------------
+// Same algorithm, one warp per CTA owning one row range of one sequence, restructured around the
+// per-reflector latency chain (ncu r01c: 43% of the cycles were fixed-latency waits, the FP64 pipe
+// was 43% busy with 2 warps per scheduler):
+//   * every lane keeps the squared norm of its own column of the live slot up to date INSIDE the
+//     rank-1 update loop (extra FMAs interleave with the update, nothing waits on them), so the
+//     norm of the next reflector is one shuffle away when the step starts;
+//   * the next column is published to the other half of vbuf at the end of the step (one
+//     __syncwarp per step, no norm pass on the critical path);
+//   * beta/tau come from branch-free MUFU seeds + Newton steps so the scalar chain sits in the same
+//     basic block as the dot-product loop and is scheduled underneath it.
+__device__ __forceinline__ double rsqrt_nobranch(double x) {   // x normal, > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // ~2^-21 seed
+  const double e = fma(-x, y * y, 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);                    // cubic step -> ~1 ulp
+}
+__device__ __forceinline__ double rcp_nobranch(double x) {     // x normal, > 0
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// as rcp_nobranch without the final rounding-correction step (relative error ~2^-52 .. 2^-51)
+__device__ __forceinline__ double rcp_short(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
+  return fma(y, e, y);
+}
+
+#include "k_qr_mma.cuh"
+
+template <int NSLOT, int ROWS, int MINB, bool BF>
+__global__ void __launch_bounds__(32, MINB) k_qr_stream(QrArgs a) {
+  static_assert(ROWS % 4 == 0 && ROWS <= 32, "ROWS must be a multiple of 4, <= 32");
+  extern __shared__ double sm[];
+  const int b = blockIdx.y, part = blockIdx.x, nparts = gridDim.x;
+  const int lane = threadIdx.x;
+  const int n = a.n, nc1 = n + 1, ldo = a.ldo;
+  const int r0 = nc1 - 32 * (NSLOT - 1);
+  const int npk = n * (n + 3) / 2;
+  double* Rp = sm;
+  double* vbuf = Rp + npk + 2 - (npk & 1);      // [2][ROWS] (+ [ROWS] dump area for the branch-free publish); Rp[npk] is padding
+  double* dump = vbuf + 2 * ROWS;
+  int* rowstart = reinterpret_cast<int*>(vbuf + 3 * ROWS);
+  __shared__ int s_total, s_f0;
+  for (int t = lane; t < npk; t += 32) Rp[t] = 0.0;
+  const double* src_base;
+  if (a.src_mode == 0) {
+    const int f0 = (int)((long)a.F * part / nparts), f1 = (int)((long)a.F * (part + 1) / nparts);
+    if (lane == 0) {
+      const int* fr = a.f_rows + (size_t)b * a.F_alloc;
+      int acc = 0;
+      for (int f = 0; f < f0; ++f) acc += (fr[f] > 0);
+      int rows = 0;
+      for (int f = f0; f < f1; ++f) {
+        rowstart[f - f0] = rows;
+        const bool on = fr[f] > 0 && (a.max_valid <= 0 || acc < a.max_valid);
+        if (fr[f] > 0) ++acc;
+        if (on) rows += fr[f];
+      }
+      rowstart[f1 - f0] = rows;
+      s_total = rows;
+      s_f0 = f0;
+      if (part == nparts - 1 && a.n_acc) a.n_acc[b] = (a.max_valid > 0) ? min(acc, a.max_valid) : acc;
+    }
+    src_base = a.Hs + (size_t)b * a.hs_seq_stride;
+  } else {
+    if (lane == 0) { s_total = a.dense_rows; s_f0 = 0; }
+    src_base = a.dense + (size_t)b * a.dense_stride;
+  }
+  __syncwarp();
+  const int total = s_total;
+  const int nfr = (a.src_mode == 0) ? ((int)((long)a.F * (part + 1) / nparts) - s_f0) : 0;
+  auto off = [&](int j) { return j * nc1 - (j * (j - 1)) / 2; };
+  int mycol[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) {
+    if (s == NSLOT - 1) mycol[s] = (lane < r0) ? lane : -1;
+    else mycol[s] = r0 + 32 * (NSLOT - 2 - s) + lane;
+  }
+  auto resolve = [&](int v) -> long {   // physical offset of virtual row v (-1: none)
+    if (v >= total) return -1;
+    if (a.src_mode != 0) return (long)v * ldo;
+    int lo = 0, hi = nfr;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (rowstart[mid] <= v) lo = mid; else hi = mid;
+    }
+    return ((long)(s_f0 + lo) * a.qmax + (v - rowstart[lo])) * ldo;
+  };
+
+  double tile[ROWS][NSLOT];
+  unsigned cur = 0;
+  for (int base = 0; base < total; base += ROWS) {
+    const long phys = (lane < ROWS) ? resolve(base + lane) : -1;
+    {  // pull the next chunk's rows towards L2 while this one is being eliminated
+      const long nx = (lane < ROWS) ? resolve(base + ROWS + lane) : -1;
+      if (nx >= 0) {
+        const char* p = reinterpret_cast<const char*>(src_base + nx);
+        for (int o = 0; o < nc1 * 8; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long o = __shfl_sync(0xffffffffu, phys, r);
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s)
+        tile[r][s] = (o >= 0 && mycol[s] >= 0) ? __ldg(src_base + o + mycol[s]) : 0.0;
+    }
+#pragma unroll
+    for (int sj = NSLOT - 1; sj >= 0; --sj) {
+      const int nl = (sj == NSLOT - 1) ? r0 : 32;
+      const int jbase = (sj == NSLOT - 1) ? 0 : r0 + 32 * (NSLOT - 2 - sj);
+      if (jbase >= n) continue;
+      // slot prologue: own-column norms of the slot, lane 0 publishes the first reflector
+      double ss;
+      {
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 4) {
+          q0 = fma(tile[r][sj], tile[r][sj], q0);
+          q1 = fma(tile[r + 1][sj], tile[r + 1][sj], q1);
+          q2 = fma(tile[r + 2][sj], tile[r + 2][sj], q2);
+          q3 = fma(tile[r + 3][sj], tile[r + 3][sj], q3);
+        }
+        ss = (q0 + q1) + (q2 + q3);
+        if (lane == 0) {
+          double* vb = vbuf + cur * ROWS;
+#pragma unroll
+          for (int r = 0; r < ROWS; r += 2)
+            *reinterpret_cast<double2*>(vb + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
+        }
+      }
+      for (int lj = 0; lj < nl; ++lj) {
+        const int j = jbase + lj;
+        if (j >= n) break;  // the residual column is never eliminated
+        const double* vb = vbuf + cur * ROWS;
+        double* vnext = vbuf + (cur ^ 1u) * ROWS;
+        cur ^= 1u;
+        const bool pub = (lane == lj + 1) && (lj + 1 < nl);
+        const double sigma = __shfl_sync(0xffffffffu, ss, lj);
+        __syncwarp();
+        if (sigma < 1e-290) {
+          // nothing below the diagonal in this chunk (uniform branch): tile untouched, norms still valid
+          if (pub) {
+#pragma unroll
+            for (int r = 0; r < ROWS; r += 2)
+              *reinterpret_cast<double2*>(vnext + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
+          }
+          continue;
+        }
+        const int oj = off(j);
+        const double alpha = Rp[oj];
+        const double nrm2 = fma(alpha, alpha, sigma);
+        const double absb = nrm2 * rsqrt_nobranch(nrm2);
+        const double beta = -copysign(absb, alpha);
+        const double amb = alpha - beta;
+        const double taup = rcp_nobranch(fma(fabs(alpha), absb, nrm2));
+        bool act[NSLOT];
+        double rjk[NSLOT];
+        constexpr int ACC = 4;
+        double d[NSLOT][ACC];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          act[s] = (s < sj) || (s == sj && lane > lj && mycol[s] >= 0);
+          rjk[s] = (s <= sj && act[s]) ? Rp[oj + (mycol[s] - j)] : 0.0;
+#pragma unroll
+          for (int q = 0; q < ACC; ++q) d[s][q] = 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(vb + r);
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s)
+            if (s <= sj) {
+              d[s][r % ACC] = fma(v.x, tile[r][s], d[s][r % ACC]);
+              d[s][(r + 1) % ACC] = fma(v.y, tile[r + 1][s], d[s][(r + 1) % ACC]);
+            }
+        }
+        double wks[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          wks[s] = 0.0;
+          if (s <= sj && act[s]) {
+            const double acc = (d[s][0] + d[s][1]) + (d[s][2] + d[s][3]);
+            const double wk = taup * fma(amb, rjk[s], acc);
+            Rp[oj + (mycol[s] - j)] = fma(-wk, amb, rjk[s]);
+            wks[s] = wk;
+          }
+        }
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < ROWS; r += 4) {
+          const double2 va = *reinterpret_cast<const double2*>(vb + r);
+          const double2 vc = *reinterpret_cast<const double2*>(vb + r + 2);
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s)
+            if (s <= sj) {
+              tile[r][s] = fma(-wks[s], va.x, tile[r][s]);
+              tile[r + 1][s] = fma(-wks[s], va.y, tile[r + 1][s]);
+              tile[r + 2][s] = fma(-wks[s], vc.x, tile[r + 2][s]);
+              tile[r + 3][s] = fma(-wks[s], vc.y, tile[r + 3][s]);
+            }
+          q0 = fma(tile[r][sj], tile[r][sj], q0);
+          q1 = fma(tile[r + 1][sj], tile[r + 1][sj], q1);
+          q2 = fma(tile[r + 2][sj], tile[r + 2][sj], q2);
+          q3 = fma(tile[r + 3][sj], tile[r + 3][sj], q3);
+        }
+        ss = (q0 + q1) + (q2 + q3);
+        if constexpr (BF) {
+          // every lane stores (non-owners into the dump area): no divergent region at the end of the step
+          double* dst = pub ? vnext : dump;
+#pragma unroll
+          for (int r = 0; r < ROWS; r += 2)
+            *reinterpret_cast<double2*>(dst + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
+          Rp[(lane == lj) ? oj : npk] = beta;
+        } else {
+          if (pub) {
+#pragma unroll
+            for (int r = 0; r < ROWS; r += 2)
+              *reinterpret_cast<double2*>(vnext + r) = make_double2(tile[r][sj], tile[r + 1][sj]);
+          }
+          if (lane == lj) Rp[oj] = beta;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  double* out = a.out + (size_t)b * a.out_stride + (size_t)part * n * nc1;
+  for (int j = 0; j < n; ++j) {
+    const int oj = off(j);
+    for (int k = lane; k < nc1; k += 32) out[(size_t)j * nc1 + k] = (k >= j) ? Rp[oj + (k - j)] : 0.0;
+  }
+}
+
+template <int NSLOT, int ROWS, int MINB, bool BF>
+void launch_stream(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st) {
+  const int n = a.n;
+  const size_t npk = (size_t)n * (n + 3) / 2;
+  size_t smem = sizeof(double) * (npk + 2 + 3 * ROWS) + sizeof(int) * (max_frange + 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_qr_stream<NSLOT, ROWS, MINB, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(split, B);
+  k_qr_stream<NSLOT, ROWS, MINB, BF><<<grid, 32, smem, st>>>(a);
+}
+
 template <int NSLOT, int ROWS, int W, int MINB>
 void launch_one(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st) {
   const int n = a.n;
@@ -255,20 +511,36 @@ void launch_one(const QrArgs& a, int split, int B, int max_frange, cudaStream_t 
 
 void launch_qr(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st) {
   const int nslot = (a.n + 1 + 31) / 32;
-  static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("IGV_QR_CFG"); cfg = e ? atoi(e) : 0; }
+  // IGV_QR_CFG: test/tuning knob. 0 = automatic, 8 = force the single-warp stream kernel,
+  // 9 = force the multi-warp kernel, 1..7 = multi-warp / legacy variants for A/B timing.
+  const char* e = getenv("IGV_QR_CFG");
+  const int cfg = e ? atoi(e) : 0;
+  // one independent single-warp stream per CTA when there are enough CTAs to fill the chip
+  const bool stream = nslot <= 3 && ((cfg >= 8 && cfg != 9) || (cfg == 0 && a.src_mode == 0 && (long)B * split >= 1000));
+  const int nct = (a.n + 1 + 7) / 8;
+  if (cfg == 20 && nct <= 9) {   // DMMA panel kernel
+    if (nct <= 4) launch_mma<4, 12>(a, split, B, max_frange, st);
+    else if (nct <= 6) launch_mma<6, 10>(a, split, B, max_frange, st);
+    else launch_mma<9, 8>(a, split, B, max_frange, st);
+    return;
+  }
+  if (stream) {
+    if (nslot <= 1) launch_stream<1, 32, 12, false>(a, split, B, max_frange, st);
+    else if (nslot <= 2) launch_stream<2, 32, 9, false>(a, split, B, max_frange, st);
+    else if (cfg == 10) launch_stream<3, 24, 10, false>(a, split, B, max_frange, st);
+    else if (cfg == 11) launch_stream<3, 16, 11, false>(a, split, B, max_frange, st);
+    else if (cfg == 12) launch_stream<3, 32, 8, true>(a, split, B, max_frange, st);
+    else if (cfg == 13) launch_stream<3, 24, 10, true>(a, split, B, max_frange, st);
+    else if (cfg == 14) launch_stream<3, 16, 11, true>(a, split, B, max_frange, st);
+    else launch_stream<3, 32, 8, false>(a, split, B, max_frange, st);
+    return;
+  }
   if (nslot <= 1) launch_one<1, 32, 4, 2>(a, split, B, max_frange, st);
   else if (nslot <= 2) launch_one<2, 32, 4, 2>(a, split, B, max_frange, st);
   else if (nslot <= 3) {
-    // one independent single-warp stream per CTA when there are enough CTAs to fill the chip
-    if (cfg == 0 && a.src_mode == 0 && (long)B * split >= 1000) launch_one<3, 32, 1, 8>(a, split, B, max_frange, st);
-    else if (cfg == 5) launch_one<3, 32, 1, 8>(a, split, B, max_frange, st);
-    else if (cfg == 6) launch_one<3, 16, 1, 12>(a, split, B, max_frange, st);
-    else if (cfg == 7) launch_one<3, 24, 1, 10>(a, split, B, max_frange, st);
+    if (cfg == 5) launch_one<3, 32, 1, 8>(a, split, B, max_frange, st);
     else if (cfg == 1) launch_one<3, 16, 4, 3>(a, split, B, max_frange, st);
-    else if (cfg == 2) launch_one<3, 16, 8, 1>(a, split, B, max_frange, st);
     else if (cfg == 3) launch_one<3, 32, 8, 1>(a, split, B, max_frange, st);
-    else if (cfg == 4) launch_one<3, 24, 4, 2>(a, split, B, max_frange, st);
     else launch_one<3, 32, 4, 2>(a, split, B, max_frange, st);
   }
   else if (nslot <= 4) launch_one<4, 24, 4, 2>(a, split, B, max_frange, st);

@@ -1,0 +1,58 @@
+"""The QR compression has three kernels (multi-warp CTA per row range, single-warp DFMA streams, single-warp
+DMMA panel streams) and a row-split + merge path. The dispatcher picks by batch size, so the parity suite's
+small batches would only ever reach one of them: re-run the visual-update parity cases with each kernel
+forced through the IGV_QR_CFG / IGV_QR_SPLIT knobs (k_qr.cu launch_qr)."""
+import pytest
+
+import test_gpu_parity as tp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=[("8", None), ("8", "3"), ("9", "2"), ("20", None), ("20", "3")],
+                ids=["stream", "stream_split3", "cta_split2", "mma", "mma_split3"])
+def qr_variant(request, monkeypatch):
+    cfg, split = request.param
+    monkeypatch.setenv("IGV_QR_CFG", cfg)
+    if split:
+        monkeypatch.setenv("IGV_QR_SPLIT", split)
+    return request.param
+
+
+@pytest.mark.parametrize("wname", ["tiny", "tiny_stereo"])
+def test_all_obs_frames(qr_variant, wname):
+    tp.test_msckf_all_obs_frames(wname)
+
+
+def test_ragged_outliers_and_cap(qr_variant):
+    tp.test_msckf_ragged_outliers_and_cap()
+
+
+@pytest.mark.parametrize("mode,stereo", [("keyframe", False), ("sw_marg", False), ("keyframe", True)])
+def test_selected_modes(qr_variant, mode, stereo):
+    tp.test_msckf_selected_modes(mode, stereo)
+
+
+def test_c2_frames(qr_variant):
+    tp.test_c2_frames_against_oracle()
+
+
+@pytest.mark.parametrize("cfg", ["8", "20"])
+def test_c1_frames(monkeypatch, cfg):
+    """c1 (SW=5: n+1 = 31 columns: one column slot / four column tiles) through the stream and DMMA kernels."""
+    import numpy as np
+    from helpers import assert_state_close, filter_params, gstep, make_gpu, make_oracles
+    from ingvio_b200.synth import WORKLOADS, SyntheticStream
+    monkeypatch.setenv("IGV_QR_CFG", cfg)
+    wl = WORKLOADS["c1"]
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 2)
+    orc = make_oracles(wl, st, fp)
+    g = make_gpu(wl, st, fp)
+    for i in range(9):
+        fr = st.next_frame()
+        gstep(g, fr, fp)
+        for b, f in enumerate(orc):
+            f.step(fr.seq(b))
+        assert_state_close(g, orc, wl.sw, what=f"c1 frame {i}")
+    assert np.all((g.flags() & 3) == 0)
