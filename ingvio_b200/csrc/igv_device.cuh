@@ -357,6 +357,34 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz
   return *s_ok != 0;
 }
 
+// Branch-free reciprocal / reciprocal square root for normal positive arguments: MUFU seed (~2^-21) +
+// Newton steps. Unlike 1.0 / x, rsqrt(x) and __drcp_rn(x) there is no slow-path call, so the compiler can
+// schedule the chain underneath independent work in the same basic block.
+__device__ __forceinline__ double rsqrt_nobranch(double x) {   // x normal, > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // ~2^-21 seed
+  const double e = fma(-x, y * y, 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);                    // cubic step -> ~1 ulp
+}
+__device__ __forceinline__ double rcp_nobranch(double x) {     // x normal, > 0
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// as rcp_nobranch without the final rounding-correction step (relative error ~2^-52 .. 2^-51)
+__device__ __forceinline__ double rcp_short(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
+  return fma(y, e, y);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -54,6 +54,7 @@ __host__ __device__ inline int feat_per_warp(int Mmax, int ldm) {
 
 template <int RHO, bool PS_SMEM>
 __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
+  constexpr int QT = 24;   // largest projected block (rows) whose gate runs in registers, see (5a)
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -381,6 +382,50 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
         sqr[i] = qv;
         if (i >= 3) sS[M * ldm + i] = qv;       // extra row M of S: the right-hand side of L y = r_proj
       }
+      __syncwarp();
+    }
+    bool pd = true;
+    double gamma = nan("");
+    if (q <= QT && q < 32) {
+      // ---- (5a) small blocks: S' stays in REGISTERS, lane = row (lane q holds the right-hand side), and
+      // the gate value comes from a square-root-free LDL^T elimination: with S = L D L^T and L z = r_proj,
+      // gamma = sum_j z_j^2 / d_j. Positive definiteness (all d_j > 0) is the same test the Cholesky makes.
+      // Column j of the trailing update needs a_cj from lane c: one shuffle per (j, c) pair instead of the
+      // shared-memory round trips and barriers of the in-place version below (30% of this kernel's time).
+      const int row = lane;
+      const bool on = row < q;
+      const int ii = on ? 3 + row : 3;
+      const double v0 = sV[ii * 3], v1 = sV[ii * 3 + 1], v2 = sV[ii * 3 + 2];
+      const double e0 = sE[ii * 3], e1 = sE[ii * 3 + 1], e2 = sE[ii * 3 + 2];
+      const double* srow = sS + ii * ldm;
+      double ar[QT];
+#pragma unroll
+      for (int c = 0; c < QT; ++c) {
+        const int j = min(c + 3, M - 1);
+        double val = srow[j] - (v0 * sAm[j * 3] + v1 * sAm[j * 3 + 1] + v2 * sAm[j * 3 + 2] +
+                                e0 * sV[j * 3] + e1 * sV[j * 3 + 1] + e2 * sV[j * 3 + 2]);
+        if (c == row) val += a.noise2;
+        if (row == q) val = sqr[j];
+        ar[c] = (c < q) ? val : 0.0;
+      }
+      double gacc = 0.0;
+#pragma unroll
+      for (int j = 0; j < QT; ++j) {
+        if (j >= q) break;
+        const double d = __shfl_sync(0xffffffffu, ar[j], j);
+        if (!(d > 0.0)) { pd = false; break; }
+        const double inv = rcp_nobranch(d);
+        const double t = ar[j];           // a_{row, j}
+        const double l = t * inv;
+        if (row == q) gacc = fma(t, l, gacc);
+#pragma unroll
+        for (int c = j + 1; c < QT; ++c) {
+          const double tc = __shfl_sync(0xffffffffu, t, c);   // a_{c, j}
+          ar[c] = fma(-l, tc, ar[c]);
+        }
+      }
+      if (pd) gamma = __shfl_sync(0xffffffffu, gacc, q);
+    } else {
       // trailing block, lower triangle: lane = row i, uniform loop over j (broadcast reads of row j data)
       for (int i0 = 3; i0 < M; i0 += 32) {
         const int i = i0 + lane;
@@ -397,36 +442,34 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
         }
       }
       __syncwarp();
-    }
-    // ---- (5) Cholesky of S = sS[3:M,3:M] (lower) with the rhs as row M: L y = r_proj rides along ----
-    bool pd = true;
-    for (int j = 3; j < M; ++j) {
-      const double d = sS[j * ldm + j];
-      if (!(d > 0.0)) { pd = false; break; }
-      const double inv = rsqrt(d);
-      __syncwarp();
-      for (int i = j + 1 + lane; i <= M; i += 32) sS[i * ldm + j] *= inv;   // rows j+1..M (incl. rhs row)
-      if (lane == 0) sS[j * ldm + j] = d * inv;
-      __syncwarp();
-      for (int i0 = j + 1; i0 <= M; i0 += 32) {
-        const int i = i0 + lane;
-        const bool on = i <= M;
-        const int ii = on ? i : j + 1;
-        double* srow = sS + ii * ldm;
-        const double lij = srow[j];
-        const int cmax = min(M - 1, i0 + 31);   // columns j+1..min(i, M-1): rhs row only has columns < M
-        for (int c = j + 1; c <= cmax; ++c) {
-          const double lcj = sS[c * ldm + j];
-          if (on && c <= i) srow[c] = fma(-lij, lcj, srow[c]);
+      // ---- (5b) Cholesky of S = sS[3:M,3:M] (lower) with the rhs as row M: L y = r_proj rides along ----
+      for (int j = 3; j < M; ++j) {
+        const double d = sS[j * ldm + j];
+        if (!(d > 0.0)) { pd = false; break; }
+        const double inv = rsqrt(d);
+        __syncwarp();
+        for (int i = j + 1 + lane; i <= M; i += 32) sS[i * ldm + j] *= inv;   // rows j+1..M (incl. rhs row)
+        if (lane == 0) sS[j * ldm + j] = d * inv;
+        __syncwarp();
+        for (int i0 = j + 1; i0 <= M; i0 += 32) {
+          const int i = i0 + lane;
+          const bool on = i <= M;
+          const int ii = on ? i : j + 1;
+          double* srow = sS + ii * ldm;
+          const double lij = srow[j];
+          const int cmax = min(M - 1, i0 + 31);   // columns j+1..min(i, M-1): rhs row only has columns < M
+          for (int c = j + 1; c <= cmax; ++c) {
+            const double lcj = sS[c * ldm + j];
+            if (on && c <= i) srow[c] = fma(-lij, lcj, srow[c]);
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
-    }
-    double gamma = nan("");
-    if (pd) {
-      double g = 0.0;
-      for (int c = 3 + lane; c < M; c += 32) { const double y = sS[M * ldm + c]; g = fma(y, y, g); }
-      gamma = warp_sum(g);
+      if (pd) {
+        double g = 0.0;
+        for (int c = 3 + lane; c < M; c += 32) { const double y = sS[M * ldm + c]; g = fma(y, y, g); }
+        gamma = warp_sum(g);
+      }
     }
     const int dof = a.dof[bf];
     const bool accept = pd && dof >= 1 && dof <= a.chi2_n && (gamma < a.chi2[dof - 1]);

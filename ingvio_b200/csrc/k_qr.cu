@@ -250,31 +250,6 @@ __global__ void __launch_bounds__(W * 32, MINB) k_qr_compress(QrArgs a) {
 //     __syncwarp per step, no norm pass on the critical path);
 //   * beta/tau come from branch-free MUFU seeds + Newton steps so the scalar chain sits in the same
 //     basic block as the dot-product loop and is scheduled underneath it.
-__device__ __forceinline__ double rsqrt_nobranch(double x) {   // x normal, > 0
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // ~2^-21 seed
-  const double e = fma(-x, y * y, 1.0);
-  return fma(fma(e, 0.375, 0.5), y * e, y);                    // cubic step -> ~1 ulp
-}
-__device__ __forceinline__ double rcp_nobranch(double x) {     // x normal, > 0
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  e = fma(e, e, e);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
-}
-
-// as rcp_nobranch without the final rounding-correction step (relative error ~2^-52 .. 2^-51)
-__device__ __forceinline__ double rcp_short(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  e = fma(e, e, e);
-  return fma(y, e, y);
-}
-
 #include "k_qr_mma.cuh"
 
 template <int NSLOT, int ROWS, int MINB, bool BF>
@@ -510,28 +485,23 @@ void launch_one(const QrArgs& a, int split, int B, int max_frange, cudaStream_t 
 }
 
 void launch_qr(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st) {
-  const int nslot = (a.n + 1 + 31) / 32;
-  // IGV_QR_CFG: test/tuning knob. 0 = automatic, 8 = force the single-warp stream kernel,
-  // 9 = force the multi-warp kernel, 1..7 = multi-warp / legacy variants for A/B timing.
+  const int nslot = (a.n + 1 + 31) / 32;   // 32-column register slots (DFMA kernels)
+  const int nct = (a.n + 1 + 7) / 8;       // 8-column tiles (DMMA kernel)
+  // IGV_QR_CFG: test/tuning knob. 0 = automatic; 20 = force the DMMA panel kernel, 8 = force the single-warp
+  // DFMA stream kernel, 9 = force the multi-warp DFMA kernel (5, 1, 3: legacy variants for A/B timing).
   const char* e = getenv("IGV_QR_CFG");
   const int cfg = e ? atoi(e) : 0;
   // one independent single-warp stream per CTA when there are enough CTAs to fill the chip
-  const bool stream = nslot <= 3 && ((cfg >= 8 && cfg != 9) || (cfg == 0 && a.src_mode == 0 && (long)B * split >= 1000));
-  const int nct = (a.n + 1 + 7) / 8;
-  if (cfg == 20 && nct <= 9) {   // DMMA panel kernel
+  const bool many = a.src_mode == 0 && (long)B * split >= 1000;
+  if (nct <= 9 && (cfg == 20 || (cfg == 0 && many))) {
     if (nct <= 4) launch_mma<4, 12>(a, split, B, max_frange, st);
     else if (nct <= 6) launch_mma<6, 10>(a, split, B, max_frange, st);
     else launch_mma<9, 8>(a, split, B, max_frange, st);
     return;
   }
-  if (stream) {
+  if (nslot <= 3 && (cfg == 8 || (cfg == 0 && many))) {
     if (nslot <= 1) launch_stream<1, 32, 12, false>(a, split, B, max_frange, st);
     else if (nslot <= 2) launch_stream<2, 32, 9, false>(a, split, B, max_frange, st);
-    else if (cfg == 10) launch_stream<3, 24, 10, false>(a, split, B, max_frange, st);
-    else if (cfg == 11) launch_stream<3, 16, 11, false>(a, split, B, max_frange, st);
-    else if (cfg == 12) launch_stream<3, 32, 8, true>(a, split, B, max_frange, st);
-    else if (cfg == 13) launch_stream<3, 24, 10, true>(a, split, B, max_frange, st);
-    else if (cfg == 14) launch_stream<3, 16, 11, true>(a, split, B, max_frange, st);
     else launch_stream<3, 32, 8, false>(a, split, B, max_frange, st);
     return;
   }
