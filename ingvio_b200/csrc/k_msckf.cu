@@ -52,9 +52,8 @@ __host__ __device__ inline int feat_per_warp(int Mmax, int ldm) {
   return Mmax * 15 + 2 * Mmax + (Mmax + 1) * ldm + 2 * Mmax + 8;
 }
 
-template <int RHO, bool PS_SMEM>
+template <int RHO, bool PS_SMEM, int QT>   // QT: largest projected block (rows) whose gate runs in registers, see (5a)
 __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
-  constexpr int QT = 24;   // largest projected block (rows) whose gate runs in registers, see (5a)
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -477,53 +476,61 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
     // ---- (6) write the projected block [H | r] rows 3..M-1, row-major, lanes over columns ----------
     if (accept) {
       double* out = a.Hs + (size_t)b * a.hs_seq_stride + (size_t)f * a.qmax * a.ldo;
-      for (int j = lane; j < n + 1; j += 32) {
-        if (j == n) {
-          for (int i = 3; i < M; ++i) out[(size_t)(i - 3) * a.ldo + j] = sqr[i];
-          continue;
-        }
-        const int c = j / 6, comp = j % 6;
-        const int kown = slot2k[c];
-        const bool anc_rot = (c == anc) && (comp < 3);
-        // the column's own-observation entries (rows kown*RHO + t)
-        double ownv[RHO];
+      // three column groups (j, j + 32, j + 64) per pass so that the broadcast reads of V's row i and the
+      // row loop are shared; per group the lane keeps z = T^T V^T a_j and its column's own entries
+      for (int j0 = 0; j0 < n + 1; j0 += 96) {
+        double z[3][3], ownv[3][RHO];
+        int own_lo[3], acomp[3];   // acomp >= 0: anchor rotation column (component), else -1
+        bool isres[3], live[3];
 #pragma unroll
-        for (int t = 0; t < RHO; ++t) {
-          double v = 0.0;
-          if (kown >= 0) {
-            const int row = kown * RHO + t;
-            if (comp < 3) v = (kown == kanc) ? 0.0 : sB[row * 3 + comp];
-            else v = ((kown == kanc) && drop) ? 0.0 : -sA[row * 3 + comp - 3];
-          }
-          ownv[t] = v;
-        }
-        // y = V^T a_j  (sparse column)
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-        if (kown >= 0) {
+        for (int gq = 0; gq < 3; ++gq) {
+          const int j = j0 + 32 * gq + lane;
+          live[gq] = j < n + 1;
+          isres[gq] = (j == n);
+          const int jc = (j < n) ? j : 0;
+          const int c = jc / 6, comp = jc % 6;
+          const int kown = (j < n) ? slot2k[c] : -1;
+          const bool anc_rot = (j < n) && (c == anc) && (comp < 3);
+          acomp[gq] = anc_rot ? comp : -1;
+          double y0 = 0.0, y1 = 0.0, y2 = 0.0;
 #pragma unroll
           for (int t = 0; t < RHO; ++t) {
-            const int row = kown * RHO + t;
-            y0 = fma(sV[row * 3], ownv[t], y0); y1 = fma(sV[row * 3 + 1], ownv[t], y1); y2 = fma(sV[row * 3 + 2], ownv[t], y2);
+            double v = 0.0;
+            if (kown >= 0) {
+              const int row = kown * RHO + t;
+              if (comp < 3) v = (kown == kanc) ? 0.0 : sB[row * 3 + comp];
+              else v = ((kown == kanc) && drop) ? 0.0 : -sA[row * 3 + comp - 3];
+              y0 = fma(sV[row * 3], v, y0); y1 = fma(sV[row * 3 + 1], v, y1); y2 = fma(sV[row * 3 + 2], v, y2);
+            }
+            ownv[gq][t] = v;
           }
-        }
-        if (anc_rot) {
-          for (int row = 0; row < M; ++row) {
-            if (row / RHO == kanc) continue;
-            const double v = -sB[row * 3 + comp];
-            y0 = fma(sV[row * 3], v, y0); y1 = fma(sV[row * 3 + 1], v, y1); y2 = fma(sV[row * 3 + 2], v, y2);
+          if (anc_rot) {
+            for (int row = 0; row < M; ++row) {
+              if (row / RHO == kanc) continue;
+              const double v = -sB[row * 3 + comp];
+              y0 = fma(sV[row * 3], v, y0); y1 = fma(sV[row * 3 + 1], v, y1); y2 = fma(sV[row * 3 + 2], v, y2);
+            }
           }
+          z[gq][0] = T00 * y0;
+          z[gq][1] = T01 * y0 + T11 * y1;
+          z[gq][2] = T02 * y0 + T12 * y1 + T22 * y2;
+          own_lo[gq] = (kown >= 0) ? kown * RHO : -(1 << 20);
         }
-        const double z0 = T00 * y0, z1 = T01 * y0 + T11 * y1, z2 = T02 * y0 + T12 * y1 + T22 * y2;
-        const int own_lo = (kown >= 0) ? kown * RHO : -1;
         for (int i = 3; i < M; ++i) {
-          double v = -(sV[i * 3] * z0 + sV[i * 3 + 1] * z1 + sV[i * 3 + 2] * z2);
-          const int t = i - own_lo;
-          if (own_lo >= 0 && t >= 0 && t < RHO) {
+          const double s0 = sV[i * 3], s1 = sV[i * 3 + 1], s2 = sV[i * 3 + 2];
+          const double qri = sqr[i];
+          const bool not_anchor_row = (i / RHO != kanc);
+          double* orow = out + (size_t)(i - 3) * a.ldo + j0 + lane;
 #pragma unroll
-            for (int tt = 0; tt < RHO; ++tt) if (tt == t) v += ownv[tt];
+          for (int gq = 0; gq < 3; ++gq) {
+            double v = -(s0 * z[gq][0] + s1 * z[gq][1] + s2 * z[gq][2]);
+            const int t = i - own_lo[gq];
+#pragma unroll
+            for (int tt = 0; tt < RHO; ++tt) if (tt == t) v += ownv[gq][tt];
+            if (acomp[gq] >= 0 && not_anchor_row) v -= sB[i * 3 + acomp[gq]];
+            if (isres[gq]) v = qri;
+            if (live[gq]) orow[32 * gq] = v;
           }
-          if (anc_rot && (i / RHO != kanc)) v -= sB[i * 3 + comp];
-          out[(size_t)(i - 3) * a.ldo + j] = v;
         }
       }
     }
@@ -531,14 +538,24 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
   }
 }
 
-template <int RHO, bool PS>
-void launch_feat(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+template <int RHO, bool PS, int QT>
+void launch_feat_q(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_msckf_features<RHO, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_msckf_features<RHO, PS, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_set = true;
   }
-  k_msckf_features<RHO, PS><<<grid, threads, smem, st>>>(a);
+  k_msckf_features<RHO, PS, QT><<<grid, threads, smem, st>>>(a);
+}
+
+template <int RHO, bool PS>
+void launch_feat(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+  // register-resident gate sized to the largest block this window can produce (rho * clones - 3 rows)
+  const int qmax = a.Mmax - 3;
+  if (qmax <= 9) launch_feat_q<RHO, PS, 9>(a, grid, threads, smem, st);
+  else if (qmax <= 17) launch_feat_q<RHO, PS, 17>(a, grid, threads, smem, st);
+  else if (qmax <= 21) launch_feat_q<RHO, PS, 21>(a, grid, threads, smem, st);
+  else launch_feat_q<RHO, PS, 25>(a, grid, threads, smem, st);
 }
 
 }  // namespace
@@ -566,7 +583,9 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   while (W > 1 && sizeof(double) * (fixed + (size_t)W * a.per_warp) > 200 * 1024) --W;
   const size_t smem = sizeof(double) * (fixed + (size_t)W * a.per_warp);
   // each CTA stages P_s once and its warps loop over tracks: a few CTAs per sequence are enough
-  const int per_cta = (h->B >= 296) ? 4 * W : W;
+  // (staging costs ~10% of the kernel with 5 CTAs per sequence: one CTA per sequence once the batch alone
+  // fills the chip, B = 148 * 8 is exactly four waves of the 2 resident CTAs per SM)
+  const int per_cta = (h->B >= 296) ? max(l.F, 1) : W;
   const int blocks_x = max(1, min((l.F + per_cta - 1) / per_cta, 64));
   dim3 grid(blocks_x, h->B);
   if (h->rho == 2) {
