@@ -56,6 +56,12 @@ enum { IGV_R_ISO = 0,   /* R = sigma^2 I, R points to ONE double per sequence: s
 enum { IGV_VIS_ALL_OBS = 0,   /* RemoveLostUpdate: every observation inside the window          */
        IGV_VIS_SELECTED = 1   /* KeyframeUpdate / SwMargUpdate: observations at selected clones  */ };
 
+/* how igv_msckf_update compresses the stacked Jacobian to [R | Q^T r] (the reference: Eigen::SPQR,
+ * RemoveLostUpdate.cpp:139-155, SwMargUpdate.cpp:161-176, KeyframeUpdate.cpp:557-572) */
+enum { IGV_COMPRESS_AUTO = 0,         /* GRAM where supported (<= 215 columns), else HOUSEHOLDER          */
+       IGV_COMPRESS_HOUSEHOLDER = 1,  /* blocked Householder QR of the stack (k_qr.cu)                    */
+       IGV_COMPRESS_GRAM = 2          /* R from the Cholesky elimination of [H r]^T [H r] (k_gram.cu)     */ };
+
 /* per-sequence status bits (igv_get_flags) */
 enum { IGV_FLAG_NEG_DIAG = 1,      /* negative covariance diagonal after an update (StateManager.cpp:413-421) */
        IGV_FLAG_CHOL_FAIL = 2,     /* innovation covariance not positive definite; update skipped            */
@@ -87,6 +93,7 @@ igv_status igv_destroy(igv_batch* h);
 const char* igv_last_error(const igv_batch* h);
 igv_status igv_set_pointer_mode(igv_batch* h, int mode);
 igv_status igv_synchronize(igv_batch* h);
+igv_status igv_set_compression(igv_batch* h, int kind);   /* IGV_COMPRESS_* (default AUTO) */
 long long igv_launch_count(const igv_batch* h);          /* kernels launched so far on this handle */
 igv_status igv_set_params(igv_batch* h, const igv_params* p);
 /* chi^2 quantile table: table[d-1] = quantile(d), d = 1..max_dof.  Replaces

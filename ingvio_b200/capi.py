@@ -14,6 +14,7 @@ IGV_PTR_HOST, IGV_PTR_DEVICE = 0, 1
 GPS, GLO, GAL, BDS, FS, YOF = range(6)
 R_ISO, R_DIAG, R_FULL = 0, 1, 2
 VIS_ALL_OBS, VIS_SELECTED = 0, 1
+COMPRESS_AUTO, COMPRESS_HOUSEHOLDER, COMPRESS_GRAM = 0, 1, 2
 FLAG_NEG_DIAG, FLAG_CHOL_FAIL, FLAG_GNSS_REJECTED = 1, 2, 4
 
 c_dp = C.POINTER(C.c_double)
@@ -66,6 +67,7 @@ SIGNATURES = {
     "igv_last_error": (C.c_char_p, [_H]),
     "igv_set_pointer_mode": (C.c_int, [_H, C.c_int]),
     "igv_synchronize": (C.c_int, [_H]),
+    "igv_set_compression": (C.c_int, [_H, C.c_int]),
     "igv_launch_count": (C.c_longlong, [_H]),
     "igv_set_params": (C.c_int, [_H, C.POINTER(igv_params)]),
     "igv_set_chi2_table": (C.c_int, [_H, c_dp, C.c_int]),

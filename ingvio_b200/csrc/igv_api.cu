@@ -187,6 +187,8 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
   IGV_ALLOC(h->Hc, B * h->ncols_max * (h->ncols_max + 1));
   h->qr_split_cap = (h->B < 296) ? 16 : 1;
   if (h->qr_split_cap > 1) IGV_ALLOC(h->Rpart, B * h->qr_split_cap * h->ncols_max * (h->ncols_max + 1));
+  h->gram_n1p = igv_gram_n1p(h->ncols_max);
+  IGV_ALLOC(h->Gws, B * h->qr_split_cap * h->gram_n1p * h->gram_n1p);
   IGV_ALLOC(h->Zws, B * h->max_rows * (h->ld + 1));
   IGV_ALLOC(h->Sws, B * h->max_rows * h->max_rows);
   IGV_ALLOC(h->dxws, B * h->ld);
@@ -212,7 +214,7 @@ igv_status igv_destroy(igv_batch* h) {
   if (!h) return IGV_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
-                  h->Hc, h->Rpart, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws, h->arena};
+                  h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws, h->arena};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (char* p : h->retired) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -225,6 +227,12 @@ const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "nu
 igv_status igv_set_pointer_mode(igv_batch* h, int mode) {
   if (!h || (mode != IGV_PTR_HOST && mode != IGV_PTR_DEVICE)) return IGV_ERR_INVALID;
   h->ptr_mode = mode;
+  return IGV_OK;
+}
+
+igv_status igv_set_compression(igv_batch* h, int kind) {
+  if (!h || kind < IGV_COMPRESS_AUTO || kind > IGV_COMPRESS_GRAM) return IGV_ERR_INVALID;
+  h->compress = kind;
   return IGV_OK;
 }
 

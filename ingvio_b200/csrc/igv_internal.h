@@ -69,6 +69,9 @@ struct igv_batch {
   double* Hc = nullptr;                // compressed [R | Q^T r]   B x ncols_max x (ncols_max+1) row-major
   double* Rpart = nullptr;             // partial triangles for split QR
   int qr_split_cap = 0;
+  double* Gws = nullptr;               // partial Gram matrices of the stack  B x qr_split_cap x gram_n1p^2 (k_gram.cu)
+  int gram_n1p = 0;
+  int compress = 0;                    // IGV_COMPRESS_*
   double* Zws = nullptr;               // B x max_rows x (ld+1)
   double* Sws = nullptr;               // B x max_rows x max_rows
   double* dxws = nullptr;              // B x ld
@@ -144,6 +147,9 @@ struct IgvMsckfLaunch {
 };
 void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& a);
 void igv_launch_qr_compress(igv_batch* h, int F, int max_valid);
+int igv_gram_n1p(int ncols_max);
+bool igv_gram_supported(int n);
+void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split);
 void igv_launch_triangulate(igv_batch* h, int F, int obs_slots, const double* obs, const unsigned char* mask,
                             const int* anchor, const igv_tri_params& prm, double* pf_out, unsigned char* ok_out);
 

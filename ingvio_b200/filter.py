@@ -108,6 +108,10 @@ class BatchFilter:
         except Exception:
             pass
 
+    def set_compression(self, kind):
+        """capi.COMPRESS_AUTO | COMPRESS_HOUSEHOLDER | COMPRESS_GRAM: how msckf_update forms [R | Q^T r]."""
+        self._ck(self.lib.igv_set_compression(self.h, int(kind)))
+
     def synchronize(self):
         self._ck(self.lib.igv_synchronize(self.h))
 

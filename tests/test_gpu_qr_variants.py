@@ -1,4 +1,4 @@
-"""The QR compression has three kernels (multi-warp CTA per row range, single-warp DFMA streams, single-warp
+"""The default compression is the Gram / Cholesky path (k_gram.cu, IGV_QR_CFG=30 forces it). The Householder QR compression has three kernels (multi-warp CTA per row range, single-warp DFMA streams, single-warp
 DMMA panel streams) and a row-split + merge path. The dispatcher picks by batch size, so the parity suite's
 small batches would only ever reach one of them: re-run the visual-update parity cases with each kernel
 forced through the IGV_QR_CFG / IGV_QR_SPLIT knobs (k_qr.cu launch_qr)."""
@@ -9,8 +9,8 @@ import test_gpu_parity as tp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[("8", None), ("8", "3"), ("9", "2"), ("20", None), ("20", "3")],
-                ids=["stream", "stream_split3", "cta_split2", "mma", "mma_split3"])
+@pytest.fixture(params=[("8", None), ("8", "3"), ("9", "2"), ("20", None), ("20", "3"), ("30", None), ("30", "3")],
+                ids=["stream", "stream_split3", "cta_split2", "mma", "mma_split3", "gram", "gram_split3"])
 def qr_variant(request, monkeypatch):
     cfg, split = request.param
     monkeypatch.setenv("IGV_QR_CFG", cfg)
@@ -37,7 +37,7 @@ def test_c2_frames(qr_variant):
     tp.test_c2_frames_against_oracle()
 
 
-@pytest.mark.parametrize("cfg", ["8", "20"])
+@pytest.mark.parametrize("cfg", ["8", "20", "30"])
 def test_c1_frames(monkeypatch, cfg):
     """c1 (SW=5: n+1 = 31 columns: one column slot / four column tiles) through the stream and DMMA kernels."""
     import numpy as np
