@@ -197,6 +197,66 @@ __device__ __forceinline__ void cta_gemm(int M, int N, int K, FA a, FB b, FC c) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same contraction on the FP64 tensor pipe: C(i,j) (op)= sum_k A(i,k) * B(k,j) with DMMA.8x8x4
+// (mma.sync.m8n8k4.f64). Every warp owns whole (8 TU) x (8 TV) blocks of C, dealt round-robin; per k-step of
+// 4 it fetches TU + TV operand values per lane through the functors and issues TU * TV DMMAs (256 FMAs each),
+// against TM + TN fetches per TM * TN FMAs of the register-tiled version above.
+// Fragment ownership: lane l supplies A(i0 + l/4, k0 + l%4) and B(k0 + l%4, j0 + l/4) and receives
+// C(i0 + l/4, j0 + 2 (l%4) + {0,1}).  `skip(i0, j0)` drops whole blocks (e.g. above the diagonal).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+template <int TU, int TV, class FA, class FB, class FC, class FS>
+__device__ __forceinline__ void cta_gemm_mma(int M, int N, int K, FA a, FB b, FC c, FS skip) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int fk = lane & 3, fc = lane >> 2;
+  constexpr int BM = 8 * TU, BN = 8 * TV;
+  const int gm = (M + BM - 1) / BM, gn = (N + BN - 1) / BN;
+  for (int t = warp; t < gm * gn; t += nw) {
+    const int i0 = (t % gm) * BM, j0 = (t / gm) * BN;
+    if (skip(i0, j0)) continue;
+    int ia[TU], jb[TV];
+#pragma unroll
+    for (int u = 0; u < TU; ++u) ia[u] = min(i0 + 8 * u + fc, M - 1);
+#pragma unroll
+    for (int v = 0; v < TV; ++v) jb[v] = min(j0 + 8 * v + fc, N - 1);
+    double acc[TU][TV][2];
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+#pragma unroll
+      for (int v = 0; v < TV; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const int k = k0 + fk;
+      const bool vk = k < K;
+      const int kk = vk ? k : K - 1;
+      double fa[TU], fb[TV];
+#pragma unroll
+      for (int u = 0; u < TU; ++u) { const double x = a(ia[u], kk); fa[u] = vk ? x : 0.0; }
+#pragma unroll
+      for (int v = 0; v < TV; ++v) { const double x = b(kk, jb[v]); fb[v] = vk ? x : 0.0; }
+#pragma unroll
+      for (int u = 0; u < TU; ++u)
+#pragma unroll
+        for (int v = 0; v < TV; ++v) mma884(acc[u][v][0], acc[u][v][1], fa[u], fb[v]);
+    }
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+#pragma unroll
+      for (int v = 0; v < TV; ++v) {
+        const int row = i0 + 8 * u + fc, col = j0 + 8 * v + 2 * fk;
+        if (row < M) {
+          if (col < N) c(row, col, acc[u][v][0]);
+          if (col + 1 < N) c(row, col + 1, acc[u][v][1]);
+        }
+      }
+  }
+}
+
 // In-place lower Cholesky of the n x n matrix S (column-major, leading dim lds), CTA-cooperative,
 // right-looking. Returns false (uniformly) if a non-positive pivot appears. `s_ok` is a shared int.
 __device__ inline bool cta_cholesky(double* S, int n, int lds, int* s_ok) {
@@ -237,34 +297,34 @@ __device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int r
 }
 
 // Blocked right-looking Cholesky fused with the forward substitution of the right-hand sides:
-//   S = L L^T (lower, in place; S is r x r column-major, leading dim r) and
+//   S = L L^T (lower, in place; S is r x r column-major, leading dim lds) and
 //   Z[:, c0:c0+nc] <- L^-1 Z[:, c0:c0+nc]   (Z is r x * column-major, leading dim ldz).
 // Per block of NB columns: (a) warp 0 factors the NB x NB diagonal block, (b) one thread per row of the
 // panel / per right-hand side solves against it, (c) the trailing update of [S | Z] is a K = NB
 // register-tiled GEMM over all threads.  3 barriers per block; the right-hand sides ride along, so
 // there is no separate triangular solve.  Returns false (uniformly) on a non-positive pivot.
 template <int NB>
-__device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz, int c0, int nc, int* s_ok) {
+__device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z, int ldz, int c0, int nc, int* s_ok) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ double s_rdiag[NB];   // 1 / L[k][k] of the current diagonal block
   if (tid == 0) *s_ok = 1;
   __syncthreads();
   for (int jb = 0; jb < r; jb += NB) {
     const int nb = min(NB, r - jb);
-    double* D = S + jb + (long)jb * r;   // diagonal block, element (i,k) at D[i + k*r]
+    double* D = S + jb + (long)jb * lds;   // diagonal block, element (i,k) at D[i + k*r]
     // (a) unblocked Cholesky of the diagonal block by warp 0 (lane = row)
     if (warp == 0) {
       for (int k = 0; k < nb; ++k) {
-        const double d = D[k + (long)k * r];
+        const double d = D[k + (long)k * lds];
         if (!(d > 0.0)) { if (lane == 0) *s_ok = 0; break; }
         const double inv = rsqrt(d);
         __syncwarp();
-        if (lane > k && lane < nb) D[lane + (long)k * r] *= inv;
-        if (lane == k) { D[k + (long)k * r] = d * inv; s_rdiag[k] = inv; }
+        if (lane > k && lane < nb) D[lane + (long)k * lds] *= inv;
+        if (lane == k) { D[k + (long)k * lds] = d * inv; s_rdiag[k] = inv; }
         __syncwarp();
         if (lane > k && lane < nb) {
-          const double lik = D[lane + (long)k * r];
-          for (int c = k + 1; c <= lane; ++c) D[lane + (long)c * r] = fma(-lik, D[c + (long)k * r], D[lane + (long)c * r]);
+          const double lik = D[lane + (long)k * lds];
+          for (int c = k + 1; c <= lane; ++c) D[lane + (long)c * lds] = fma(-lik, D[c + (long)k * lds], D[lane + (long)c * lds]);
         }
         __syncwarp();
       }
@@ -276,17 +336,17 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz
     for (int t = tid; t < m + nc; t += blockDim.x) {
       double x[NB];
       if (t < m) {
-        double* row = S + (i0 + t) + (long)jb * r;   // element k at row[k*r]
+        double* row = S + (i0 + t) + (long)jb * lds;   // element k at row[k*r]
 #pragma unroll
         for (int k = 0; k < NB; ++k)
           if (k < nb) {
-            double acc = row[(long)k * r];
+            double acc = row[(long)k * lds];
 #pragma unroll
-            for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-x[p], D[k + (long)p * r], acc);
+            for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-x[p], D[k + (long)p * lds], acc);
             x[k] = acc * s_rdiag[k];
           }
 #pragma unroll
-        for (int k = 0; k < NB; ++k) if (k < nb) row[(long)k * r] = x[k];
+        for (int k = 0; k < NB; ++k) if (k < nb) row[(long)k * lds] = x[k];
       } else {
         double* col = Z + jb + (long)(c0 + t - m) * ldz;   // element k at col[k]
 #pragma unroll
@@ -294,7 +354,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz
           if (k < nb) {
             double acc = col[k];
 #pragma unroll
-            for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-D[k + (long)p * r], x[p], acc);
+            for (int p = 0; p < NB; ++p) if (p < k) acc = fma(-D[k + (long)p * lds], x[p], acc);
             x[k] = acc * s_rdiag[k];
           }
 #pragma unroll
@@ -302,54 +362,23 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, double* Z, int ldz
       }
     }
     __syncthreads();
-    // (c) trailing update, 4x4 register tiles over rows [i0, r) x columns [S: i0..r-1 | Z: c0..c0+nc-1]
+    // (c) trailing update of rows [i0, r) x columns [S: i0..r-1 (lower part) | Z: c0..c0+nc-1], K = nb, on DMMA
     if (m > 0) {
       const int ncol = m + nc;
-      const int gm = (m + 3) / 4, gn = (ncol + 3) / 4;
-      for (int t = tid; t < gm * gn; t += blockDim.x) {
-        const int ti = t % gm, tj = t / gm;
-        int ri[4], cj[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { ri[u] = i0 + min(ti + u * gm, m - 1); cj[u] = min(tj + u * gn, ncol - 1); }
-        const double* bp[4];
-        int bs[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          if (cj[v] < m) { bp[v] = S + (i0 + cj[v]) + (long)jb * r; bs[v] = r; }      // L[c][jb+k]
-          else { bp[v] = Z + jb + (long)(c0 + cj[v] - m) * ldz; bs[v] = 1; }          // Y1[k][cz]
-        }
-        double acc[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-        for (int k = 0; k < nb; ++k) {
-          double av[4], bv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) av[u] = S[ri[u] + (long)(jb + k) * r];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) bv[v] = bp[v][(long)k * bs[v]];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int il = ti + u * gm, cl = tj + v * gn;
-            if (il < m && cl < ncol) {
-              const int i = i0 + il;
-              if (cl < m) {
-                const int c = i0 + cl;
-                if (c <= i) S[i + (long)c * r] -= acc[u][v];
-              } else {
-                Z[i + (long)(c0 + cl - m) * ldz] -= acc[u][v];
-              }
+      cta_gemm_mma<2, 2>(
+          m, ncol, nb, [&](int il, int k) { return S[(i0 + il) + (long)(jb + k) * lds]; },
+          [&](int k, int cl) {
+            return (cl < m) ? S[(i0 + cl) + (long)(jb + k) * lds] : Z[jb + k + (long)(c0 + cl - m) * ldz];
+          },
+          [&](int il, int cl, double v) {
+            const int i = i0 + il;
+            if (cl < m) {
+              if (cl <= il) S[i + (long)(i0 + cl) * lds] -= v;
+            } else {
+              Z[i + (long)(c0 + cl - m) * ldz] -= v;
             }
-          }
-      }
+          },
+          [&](int bi, int bj) { return bj + 16 <= m && bj > bi + 15; });
     }
     __syncthreads();
   }

@@ -26,7 +26,7 @@ struct EkfArgs {
   const double* res; long strideRes; int res_inc;
   const double* R; long strideR; int r_kind; double r_iso_value; const int* only_if;
   double* Zws; long strideZ; double* Sws; long strideS;
-  int z_in_smem, s_in_smem;
+  int z_in_smem, s_in_smem, ld_pad;
   double* dx_out; double* dxws;
   int gamma_only; double* gamma_out;
   const int* gate_rows; const double* chi2; int chi2_n;
@@ -44,14 +44,17 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
   double* Pb = a.P + (size_t)b * ld * ld;
   const double* Hb = a.H + (size_t)b * a.strideH;
   const double* resb = a.res + (size_t)b * a.strideRes;
-  const int ldz = r;                     // Z is r x (N+1) column-major: column i = (H P[:, i]) ; column N = res
+  // Z is r x (N+1) column-major: column i = (H P[:, i]) ; column N = res. In shared memory the leading dimensions
+  // are padded to 4 (mod 8) doubles: the 4 x 8 operand fragments of the DMMA stages then hit distinct banks.
+  const int ldz = a.z_in_smem ? a.ld_pad : r;
+  const int lds = a.s_in_smem ? a.ld_pad : r;
   if (a.only_if && !a.only_if[b]) {
     if (a.dx_out) for (int i = tid; i < N; i += blockDim.x) a.dx_out[(size_t)b * N + i] = 0.0;
     return;
   }
   double* smp = sm;
   double* Z = a.z_in_smem ? smp : a.Zws + (size_t)b * a.strideZ;
-  if (a.z_in_smem) smp += (size_t)r * (N + 1);
+  if (a.z_in_smem) smp += (size_t)ldz * (N + 1);
   double* S = a.s_in_smem ? smp : a.Sws + (size_t)b * a.strideS;
 
   for (int q = tid; q < a.blk.n_blocks; q += blockDim.x) {
@@ -67,31 +70,34 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
   //     the thread-fast index is i so that P reads are contiguous.
   {
     const int Ni = a.gamma_only ? n : N;  // gate only needs the measured rows of P
-    cta_gemm<4, 4>(Ni, r, n,
-                   [&](int i, int k) { const int ii = a.gamma_only ? cols[i] : i; return Pb[ii + (size_t)cols[k] * ld]; },
-                   [&](int k, int j) { return Hat(j, k); },
-                   [&](int i, int j, double v) { Z[j + (size_t)i * ldz] = v; });
+    cta_gemm_mma<2, 2>(Ni, r, n,
+                       [&](int i, int k) { const int ii = a.gamma_only ? cols[i] : i; return Pb[ii + (size_t)cols[k] * ld]; },
+                       [&](int k, int j) { return Hat(j, k); },
+                       [&](int i, int j, double v) { Z[j + (size_t)i * ldz] = v; },
+                       [](int, int) { return false; });
     for (int t = tid; t < r; t += blockDim.x) Z[t + (size_t)N * ldz] = resb[(size_t)t * a.res_inc];
   }
   __syncthreads();
   // (2) S = H * Z[:, cols] + R                          (StateManager.cpp:399-403)
   {
     const double* Rb = a.R ? a.R + (size_t)b * a.strideR : nullptr;
-    cta_gemm<4, 4>(r, r, n, [&](int i, int k) { return Hat(i, k); },
-                   [&](int k, int j) { const int cc = a.gamma_only ? k : cols[k]; return Z[j + (size_t)cc * ldz]; },
-                   [&](int i, int j, double v) {
-                     double rr = 0.0;
-                     if (a.r_kind == IGV_R_ISO) rr = (i == j) ? (Rb ? Rb[0] : a.r_iso_value) : 0.0;
-                     else if (a.r_kind == IGV_R_DIAG) rr = (i == j) ? Rb[i] : 0.0;
-                     else rr = Rb[i + (size_t)j * r];
-                     S[i + (size_t)j * r] = v + rr;
-                   });
+    // only the lower triangle of S is used by the factorisation: blocks above the diagonal are skipped
+    cta_gemm_mma<2, 2>(r, r, n, [&](int i, int k) { return Hat(i, k); },
+                       [&](int k, int j) { const int cc = a.gamma_only ? k : cols[k]; return Z[j + (size_t)cc * ldz]; },
+                       [&](int i, int j, double v) {
+                         double rr = 0.0;
+                         if (a.r_kind == IGV_R_ISO) rr = (i == j) ? (Rb ? Rb[0] : a.r_iso_value) : 0.0;
+                         else if (a.r_kind == IGV_R_DIAG) rr = (i == j) ? Rb[i] : 0.0;
+                         else rr = Rb[i + (size_t)j * r];
+                         S[i + (size_t)j * lds] = v + rr;
+                       },
+                       [](int bi, int bj) { return bj > bi + 15; });
   }
   __syncthreads();
   // (3) S = L L^T
   // (3)+(4)+(5) S = L L^T fused with Y = L^-1 Z (all N columns) and w = L^-1 res (column N)
-  const bool ok = a.gamma_only ? cta_chol_solve_fused<8>(S, r, Z, ldz, N, 1, &s_ok)
-                               : cta_chol_solve_fused<8>(S, r, Z, ldz, 0, N + 1, &s_ok);
+  const bool ok = a.gamma_only ? cta_chol_solve_fused<8>(S, r, lds, Z, ldz, N, 1, &s_ok)
+                               : cta_chol_solve_fused<8>(S, r, lds, Z, ldz, 0, N + 1, &s_ok);
   if (!ok) {
     if (tid == 0) {
       atomicOr(&a.flags[b], IGV_FLAG_CHOL_FAIL);
@@ -133,43 +139,17 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
     dxb[i] = acc;
     if (a.dx_out) a.dx_out[(size_t)b * N + i] = acc;
   }
-  // (7) P -= Y^T Y : lower triangle by 4x4 register tiles, mirrored on store
-  {
-    const int g = (N + 3) / 4;
-    for (int t = tid; t < g * g; t += blockDim.x) {
-      const int ti = t % g, tj = t / g;
-      if (tj > ti) continue;  // tile (ti,tj) covers rows {ti+u*g}, cols {tj+v*g}; keep the half with ti>=tj
-      double acc[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-      int ri[4], cj[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { ri[u] = min(ti + u * g, N - 1); cj[u] = min(tj + u * g, N - 1); }
-      for (int k = 0; k < r; ++k) {
-        double av[4], bv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { av[u] = Z[k + (size_t)ri[u] * ldz]; bv[u] = Z[k + (size_t)cj[u] * ldz]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int i = ti + u * g, j = tj + v * g;
-          if (i < N && j < N) {
-            // interleaved tiles: (i,j) and (j,i) are both produced only when ti==tj; otherwise mirror
-            const double val = Pb[i + (size_t)j * ld] - acc[u][v];
-            Pb[i + (size_t)j * ld] = val;
-            if (ti != tj) Pb[j + (size_t)i * ld] = val;
-          }
-        }
-    }
-  }
+  // (7) P -= Y^T Y : blocks of the lower triangle on DMMA, mirrored on store
+  cta_gemm_mma<2, 2>(N, N, r, [&](int i, int k) { return Z[k + (size_t)i * ldz]; },
+                     [&](int k, int j) { return Z[k + (size_t)j * ldz]; },
+                     [&](int i, int j, double v) {
+                       if (j <= i) {
+                         const double val = Pb[i + (size_t)j * ld] - v;
+                         Pb[i + (size_t)j * ld] = val;
+                         if (i != j) Pb[j + (size_t)i * ld] = val;
+                       }
+                     },
+                     [](int bi, int bj) { return bj > bi + 15; });
   __syncthreads();
   // (8) negative diagonal check (StateManager.cpp:413-421) and box-plus (:425)
   for (int i = tid; i < N; i += blockDim.x)
@@ -196,7 +176,9 @@ void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& l) {
   a.apply_boxplus = l.apply_boxplus; a.flags = h->flags;
   // shared-memory placement: Z first, then S, as long as they fit
   const size_t cap = 200 * 1024;
-  const size_t zb = sizeof(double) * (size_t)l.rows * (h->N + 1), sb = sizeof(double) * (size_t)l.rows * l.rows;
+  const int ld_pad = l.rows + ((4 - l.rows % 8) + 8) % 8;   // smallest >= rows that is 4 (mod 8)
+  a.ld_pad = ld_pad;
+  const size_t zb = sizeof(double) * (size_t)ld_pad * (h->N + 1), sb = sizeof(double) * (size_t)ld_pad * l.rows;
   size_t smem = 0;
   a.z_in_smem = (zb <= cap) ? 1 : 0;
   if (a.z_in_smem) smem += zb;
