@@ -94,6 +94,9 @@ const char* igv_last_error(const igv_batch* h);
 igv_status igv_set_pointer_mode(igv_batch* h, int mode);
 igv_status igv_synchronize(igv_batch* h);
 igv_status igv_set_compression(igv_batch* h, int kind);   /* IGV_COMPRESS_* (default AUTO) */
+/* which kernels the last igv_msckf_update used: 0 Householder QR of the materialised stack, 1 Gram matrix of the
+ * materialised stack, 2 Gram matrix accumulated inside the per-track kernel (no stack in HBM); -1 before any update */
+int igv_last_visual_path(const igv_batch* h);
 long long igv_launch_count(const igv_batch* h);          /* kernels launched so far on this handle */
 igv_status igv_set_params(igv_batch* h, const igv_params* p);
 /* chi^2 quantile table: table[d-1] = quantile(d), d = 1..max_dof.  Replaces

@@ -68,6 +68,7 @@ SIGNATURES = {
     "igv_set_pointer_mode": (C.c_int, [_H, C.c_int]),
     "igv_synchronize": (C.c_int, [_H]),
     "igv_set_compression": (C.c_int, [_H, C.c_int]),
+    "igv_last_visual_path": (C.c_int, [_H]),
     "igv_launch_count": (C.c_longlong, [_H]),
     "igv_set_params": (C.c_int, [_H, C.POINTER(igv_params)]),
     "igv_set_chi2_table": (C.c_int, [_H, c_dp, C.c_int]),

@@ -236,6 +236,8 @@ igv_status igv_set_compression(igv_batch* h, int kind) {
   return IGV_OK;
 }
 
+int igv_last_visual_path(const igv_batch* h) { return h ? h->last_visual_path : -1; }
+
 igv_status igv_synchronize(igv_batch* h) {
   if (!h) return IGV_ERR_INVALID;
   IGV_CUDA(h, cudaStreamSynchronize(h->stream));

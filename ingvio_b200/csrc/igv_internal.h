@@ -72,6 +72,8 @@ struct igv_batch {
   double* Gws = nullptr;               // partial Gram matrices of the stack  B x qr_split_cap x gram_n1p^2 (k_gram.cu)
   int gram_n1p = 0;
   int compress = 0;                    // IGV_COMPRESS_*
+  int last_visual_path = -1;           // igv_last_visual_path
+  bool feat_fused = false;             // the last k_msckf_features launch accumulated the Gram matrix itself
   double* Zws = nullptr;               // B x max_rows x (ld+1)
   double* Sws = nullptr;               // B x max_rows x max_rows
   double* dxws = nullptr;              // B x ld
@@ -150,6 +152,7 @@ void igv_launch_qr_compress(igv_batch* h, int F, int max_valid);
 int igv_gram_n1p(int ncols_max);
 bool igv_gram_supported(int n);
 void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split);
+void igv_launch_gram_factor(igv_batch* h, int nparts);
 void igv_launch_triangulate(igv_batch* h, int F, int obs_slots, const double* obs, const unsigned char* mask,
                             const int* anchor, const igv_tri_params& prm, double* pf_out, unsigned char* ok_out);
 

@@ -417,8 +417,16 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
     case 4: launch_accum<4>(a, split, h->B, warps, smem, h->stream); break;
     default: launch_accum<5>(a, split, h->B, warps, smem, h->stream); break;
   }
+  igv_launch_gram_factor(h, split);
+  h->launches += 1;
+}
+
+void igv_launch_gram_factor(igv_batch* h, int nparts) {
+  IgvLayout L = h->layout();
+  const int n = 6 * L.n_clones;
   FactorArgs f;
-  f.G = h->Gws; f.g_seq_stride = a.g_seq_stride; f.n1p = a.n1p; f.nparts = split;
+  f.G = h->Gws; f.g_seq_stride = (long)h->qr_split_cap * h->gram_n1p * h->gram_n1p;
+  f.n1p = 24 * ((n + 1 + 23) / 24) + 8; f.nparts = nparts;
   f.n = n; f.out = h->Hc; f.out_stride = (long)h->ncols_max * (h->ncols_max + 1);
   f.tol = 1e-13;
   const size_t fsmem = sizeof(double) * ((size_t)n * (n + 3) / 2 + 2 * n);
@@ -428,5 +436,5 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
     fattr = true;
   }
   k_gram_factor<<<h->B, 256, fsmem, h->stream>>>(f);
-  h->launches += 2;
+  h->launches += 1;
 }

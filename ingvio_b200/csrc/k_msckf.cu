@@ -22,6 +22,9 @@
 //
 // Algorithmic bytes per feature: reads 24 + 8*rho*nobs (+ 96*SW poses and 8 n^2 of P_s per CTA),
 // writes 8*(M-3)*(n+1).
+#include <cstdint>
+#include <cstdlib>
+
 #include "igv_device.cuh"
 
 using namespace igv;
@@ -45,15 +48,22 @@ struct FeatArgs {
   int Mmax;                          // rho * n_clones
   int ldm;                           // row stride of the per-warp S matrix (odd)
   int per_warp;                      // doubles of per-warp scratch
+  int ssz;                           // doubles of the per-warp S region (>= (Mmax+1)*ldm; FUSE: also holds Z rows + D blocks)
+  // FUSE: the track's contribution to the Gram matrix of the stack is accumulated in the kernel (see (6'))
+  int nt, ldz;                       // 8-column tiles of the stack's n+1 columns; row stride of the Z rows
+  double* G; long g_seq_stride; int n1p;   // out: upper triangle of [H r]^T [H r], row stride n1p
+  int* n_acc; int max_valid;
 };
 
 // per-warp scratch layout (doubles): A[M][3] B[M][3] V[M][3] Am[M][3] E[M][3] r[M] qr[M] S[(M+1)][ldm] maps
-__host__ __device__ inline int feat_per_warp(int Mmax, int ldm) {
-  return Mmax * 15 + 2 * Mmax + (Mmax + 1) * ldm + 2 * Mmax + 8;
+__host__ __device__ inline int feat_per_warp(int Mmax, int ssz) {
+  return Mmax * 15 + 2 * Mmax + ssz + 2 * Mmax + 8;
 }
 
-template <int RHO, bool PS_SMEM, int QT>   // QT: largest projected block (rows) whose gate runs in registers, see (5a)
-__global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
+// QT: largest projected block (rows) whose gate runs in registers, see (5a). FUSE: one CTA of up to 16 warps per
+// sequence; instead of writing the projected blocks to HBM the kernel accumulates their Gram matrix, see (6').
+template <int RHO, bool PS_SMEM, int QT, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msckf_features(FeatArgs a) {
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
   double* sr = sE + Mmax * 3;      // [M] residual
   double* sqr = sr + Mmax;         // [M] Q^T r
   double* sS = sqr + Mmax;         // [(M+1)][ldm] : H_x P_s H_x^T, then S and its Cholesky factor (+ rhs row)
-  int* k2slot = reinterpret_cast<int*>(sS + (Mmax + 1) * ldm);  // [ncl] obs k -> slot
+  int* k2slot = reinterpret_cast<int*>(sS + a.ssz);             // [ncl] obs k -> slot
   int* slot2k = k2slot + ncl;                                    // [ncl] slot -> obs k or -1
   const double* Xb = a.X + (size_t)b * a.xsize;
   for (int t = threadIdx.x; t < 12 * ncl; t += blockDim.x) sPose[t] = Xb[IGV_X_CORE + t];
@@ -82,15 +92,31 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
       sPs[t] = Pb[(a.L.idx_clone[i / 6] + i % 6) + (size_t)(a.L.idx_clone[j / 6] + j % 6) * a.ld];
     }
   }
+  // FUSE: CTA-level accumulators behind the per-warp regions
+  double* wsbase = sPs + (PS_SMEM ? n * n : 0);                  // per-warp regions start here
+  const int zoff = Mmax * 15 + 2 * Mmax;                         // offset of sS inside a per-warp region
+  const int ntt = a.nt * (a.nt + 1) / 2;
+  double* S_acc = wsbase + (size_t)nwarps * a.per_warp;          // [(ncl+1) anchors][ncl][27]
+  double2* Gt = reinterpret_cast<double2*>(                                                     // [ntt][32], 16-byte aligned
+      (reinterpret_cast<uintptr_t>(S_acc + (size_t)(ncl + 1) * ncl * 27) + 15) & ~static_cast<uintptr_t>(15));
+  int* flag_s = reinterpret_cast<int*>(Gt + (size_t)ntt * 32);   // [nwarps]
+  if (FUSE) {
+    for (int t = threadIdx.x; t < (ncl + 1) * ncl * 27; t += blockDim.x) S_acc[t] = 0.0;
+    for (int t = threadIdx.x; t < ntt * 32; t += blockDim.x) Gt[t] = make_double2(0.0, 0.0);
+  }
   __syncthreads();
   const bool drop = (a.mode == IGV_VIS_SELECTED);
+  int acc_count = 0;   // FUSE: accepted tracks so far (for the max_valid cap), identical in every thread
 
-  for (int f = blockIdx.x * nwarps + warp; f < a.F; f += gridDim.x * nwarps) {
+  for (int fbase = blockIdx.x * nwarps; fbase < a.F; fbase += gridDim.x * nwarps) {
+    const int f = fbase + warp;
+    int flag = 0;      // FUSE: 0 = no contribution, else 1 + anchor slot (ncl + 1: anchor outside the window)
+    if (f < a.F) do {
     const size_t bf = (size_t)b * a.F + f;          // index into the caller's arrays
     const size_t bo = (size_t)b * a.F_alloc + f;    // index into f_rows / f_gamma
     if (a.feat_ok && !a.feat_ok[bf]) {              // track rejected upstream (e.g. triangulation failed)
       if (lane == 0) { a.f_rows[bo] = 0; a.f_gamma[bo] = nan(""); }
-      continue;
+      break;
     }
     const double pf[3] = {a.pf[bf * 3], a.pf[bf * 3 + 1], a.pf[bf * 3 + 2]};
     const int anc = a.anchor[bf];
@@ -164,7 +190,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
     if (q < 1) {
       if (lane == 0) { a.f_rows[bo] = 0; a.f_gamma[bo] = nan(""); }
       __syncwarp();
-      continue;
+      break;
     }
     const int kanc = (anc >= 0 && anc < ncl) ? slot2k[anc] : -1;  // observation taken at the anchor clone
     const int ca = (anc >= 0 && anc < ncl) ? anc : -1;
@@ -473,8 +499,104 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
     const int dof = a.dof[bf];
     const bool accept = pd && dof >= 1 && dof <= a.chi2_n && (gamma < a.chi2[dof - 1]);
     if (lane == 0) { a.f_gamma[bo] = gamma; a.f_rows[bo] = accept ? q : 0; }
+    // ---- (6') FUSE: the track's term of G = [H r]^T [H r] without forming the projected block ---------------
+    // With W = [H_x | r] (M rows) and Q = [Q1 | Q2] the projected block is Q2^T W, so its Gram matrix is
+    //     W^T Q2 Q2^T W = W^T W - Z^T Z,   Z = Q1^T W = rows 0..2 of Q^T W   (3 x (n+1)).
+    // W^T W is block sparse: with U_s = [B | -A] the rows of the observation at clone s (6 columns) and the
+    // anchor a's rotation columns carrying -B,  D_s = U_s^T U_s, d_s = U_s^T r_s:
+    //     G[s,s] += D_s,  G[s,a_rot] -= D_s[:, :3],  G[a_rot,a_rot] += D_s[:3,:3],  g[s] += d_s,  g[a_rot] -= d_s[:3].
+    // The warp leaves Z (3 rows) and the D_s | d_s (27 numbers per clone) in its own S region; after the block
+    // barrier the CTA folds the Z rows of all warps into G with DMMA and the D_s into S_acc[anchor][s] in warp
+    // order, so the sum is independent of the schedule (bitwise reproducible).
+    if (accept && FUSE) {
+      double* zrow = sS;                      // [3][ldz]
+      double* dblk = sS + 3 * a.ldz;          // [ncl][27]
+      const int ncolp = 8 * a.nt;
+      for (int j0 = 0; j0 < ncolp; j0 += 32) {
+        const int j = j0 + lane;
+        if (j >= ncolp) break;
+        double zr[3] = {0.0, 0.0, 0.0};
+        if (j < n) {
+          const int c = j / 6, comp = j % 6;
+          const int kown = slot2k[c];
+          const bool anc_rot = (c == anc) && (comp < 3);
+          double y0 = 0.0, y1 = 0.0, y2 = 0.0, ownv[RHO];
+#pragma unroll
+          for (int t = 0; t < RHO; ++t) {
+            double v = 0.0;
+            if (kown >= 0) {
+              const int row = kown * RHO + t;
+              if (comp < 3) v = (kown == kanc) ? 0.0 : sB[row * 3 + comp];
+              else v = ((kown == kanc) && drop) ? 0.0 : -sA[row * 3 + comp - 3];
+              y0 = fma(sV[row * 3], v, y0); y1 = fma(sV[row * 3 + 1], v, y1); y2 = fma(sV[row * 3 + 2], v, y2);
+            }
+            ownv[t] = v;
+          }
+          if (anc_rot) {
+            for (int row = 0; row < M; ++row) {
+              if (row / RHO == kanc) continue;
+              const double v = -sB[row * 3 + comp];
+              y0 = fma(sV[row * 3], v, y0); y1 = fma(sV[row * 3 + 1], v, y1); y2 = fma(sV[row * 3 + 2], v, y2);
+            }
+          }
+          const double z0 = T00 * y0, z1 = T01 * y0 + T11 * y1, z2 = T02 * y0 + T12 * y1 + T22 * y2;
+          const int own_lo = (kown >= 0) ? kown * RHO : -(1 << 20);
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            double v = -(sV[p * 3] * z0 + sV[p * 3 + 1] * z1 + sV[p * 3 + 2] * z2);
+            const int t = p - own_lo;
+#pragma unroll
+            for (int tt = 0; tt < RHO; ++tt) if (tt == t) v += ownv[tt];
+            if (anc_rot && (p / RHO != kanc)) v -= sB[p * 3 + comp];
+            zr[p] = v;
+          }
+        } else if (j == n) {
+          zr[0] = sqr[0]; zr[1] = sqr[1]; zr[2] = sqr[2];
+        }
+        zrow[j] = zr[0]; zrow[a.ldz + j] = zr[1]; zrow[2 * a.ldz + j] = zr[2];
+      }
+      for (int sl = lane; sl < ncl; sl += 32) {
+        double* dd = dblk + sl * 27;
+        const int k = slot2k[sl];
+        if (k < 0) {
+#pragma unroll
+          for (int e = 0; e < 27; ++e) dd[e] = 0.0;
+        } else {
+          const bool isanc = (k == kanc);
+          double u[RHO][6], rr[RHO];
+#pragma unroll
+          for (int t = 0; t < RHO; ++t) {
+            const int row = k * RHO + t;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              u[t][j] = isanc ? 0.0 : sB[row * 3 + j];
+              u[t][3 + j] = (isanc && drop) ? 0.0 : -sA[row * 3 + j];
+            }
+            rr[t] = sr[row];
+          }
+          int e = 0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j, ++e) {
+              double acc = 0.0;
+#pragma unroll
+              for (int t = 0; t < RHO; ++t) acc = fma(u[t][i], u[t][j], acc);
+              dd[e] = acc;
+            }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < RHO; ++t) acc = fma(u[t][i], rr[t], acc);
+            dd[21 + i] = acc;
+          }
+        }
+      }
+      flag = (ca >= 0) ? ca + 1 : ncl + 1;
+    }
     // ---- (6) write the projected block [H | r] rows 3..M-1, row-major, lanes over columns ----------
-    if (accept) {
+    if (accept && !FUSE) {
       double* out = a.Hs + (size_t)b * a.hs_seq_stride + (size_t)f * a.qmax * a.ldo;
       // three column groups (j, j + 32, j + 64) per pass so that the broadcast reads of V's row i and the
       // row loop are shared; per group the lane keeps z = T^T V^T a_j and its column's own entries
@@ -535,31 +657,134 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k_msckf_features(FeatArgs a) {
       }
     }
     __syncwarp();
+    } while (0);
+    if (FUSE) {
+      const int fk = lane & 3, fc = lane >> 2;
+      if (lane == 0) flag_s[warp] = flag;
+      __syncthreads();
+      unsigned onmask = 0;   // warps whose track enters the update: accepted and inside the max_valid cap
+      for (int w = 0; w < nwarps; ++w)
+        if (flag_s[w]) {
+          if (a.max_valid <= 0 || acc_count < a.max_valid) onmask |= 1u << w;
+          ++acc_count;
+        }
+      if (onmask) {
+        // G -= Z^T Z over the 3 * nwarps staged rows; the upper-triangle tiles are dealt to the warps
+        const int nrows = 3 * nwarps;
+        for (int ti = warp; ti < ntt; ti += nwarps) {
+          int ci = 0, rem = ti;
+          while (rem >= a.nt - ci) { rem -= a.nt - ci; ++ci; }
+          const int cj = ci + rem;
+          double2 g = Gt[ti * 32 + lane];
+          for (int k0 = 0; k0 < nrows; k0 += 4) {
+            const int r = k0 + fk, w = r / 3, p = r - 3 * w;
+            const bool on = (r < nrows) && ((onmask >> w) & 1u);
+            const double* zp = wsbase + (size_t)(on ? w : 0) * a.per_warp + zoff + p * a.ldz + fc;
+            const double za = on ? zp[8 * ci] : 0.0, zb = on ? zp[8 * cj] : 0.0;
+            mma884(g.x, g.y, -za, zb);
+          }
+          Gt[ti * 32 + lane] = g;
+        }
+        for (int idx = threadIdx.x; idx < ncl * 27; idx += blockDim.x)
+          for (int w = 0; w < nwarps; ++w)
+            if ((onmask >> w) & 1u) {
+              const int aw = flag_s[w] - 1;
+              S_acc[(size_t)aw * ncl * 27 + idx] += (wsbase + (size_t)w * a.per_warp + zoff + 3 * a.ldz)[idx];
+            }
+      }
+      __syncthreads();
+    }
+  }
+  if (FUSE) {
+    // ---- assemble the upper triangle of G in shared memory (over the dead per-warp regions) and write it -------
+    const int fk = lane & 3, fc = lane >> 2;
+    const int n1 = n + 1, ldg = n1 | 1;
+    double* Gf = wsbase;
+    for (int ti = warp; ti < ntt; ti += nwarps) {
+      int ci = 0, rem = ti;
+      while (rem >= a.nt - ci) { rem -= a.nt - ci; ++ci; }
+      const int cj = ci + rem;
+      const double2 g = Gt[ti * 32 + lane];
+      const int row = 8 * ci + fc, col = 8 * cj + 2 * fk;
+      if (row < n1) {
+        if (col < n1) Gf[row * ldg + col] = g.x;
+        if (col + 1 < n1) Gf[row * ldg + col + 1] = g.y;
+      }
+    }
+    __syncthreads();
+    auto uidx = [](int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); };   // i <= j < 6
+    // clone-diagonal blocks and the right-hand side: sum over the anchors in a fixed order
+    for (int idx = threadIdx.x; idx < ncl * 27; idx += blockDim.x) {
+      const int sl = idx / 27, e = idx - 27 * sl;
+      double tot = 0.0;
+      for (int an = 0; an <= ncl; ++an) tot += S_acc[(size_t)an * ncl * 27 + idx];
+      if (e < 21) {
+        int i = 0, rem = e;
+        while (rem >= 6 - i) { rem -= 6 - i; ++i; }
+        Gf[(6 * sl + i) * ldg + 6 * sl + i + rem] += tot;
+      } else {
+        Gf[(6 * sl + e - 21) * ldg + n] += tot;
+      }
+    }
+    __syncthreads();
+    // anchor coupling: block (s, a_rot) -= D[:, :3]. Blocks {s, a} and {a, s} share the rot-rot entries of the
+    // upper triangle, so s < a and s > a are two phases; the anchor's own rot-rot block and right-hand side ride
+    // in the first one (disjoint targets).
+    for (int phase = 0; phase < 2; ++phase) {
+      for (int idx = threadIdx.x; idx < ncl * ncl * 18; idx += blockDim.x) {
+        const int an = idx / (ncl * 18), rem = idx - an * ncl * 18, sl = rem / 18, q18 = rem - 18 * sl;
+        const int i = q18 / 3, jp = q18 - 3 * i;
+        if (sl == an || ((sl < an) != (phase == 0))) continue;
+        const double val = S_acc[((size_t)an * ncl + sl) * 27 + uidx(min(i, jp), max(i, jp))];
+        const int r_ = 6 * sl + i, c_ = 6 * an + jp;
+        Gf[min(r_, c_) * ldg + max(r_, c_)] -= val;
+      }
+      if (phase == 0) {
+        for (int idx = threadIdx.x; idx < ncl * 9; idx += blockDim.x) {
+          const int an = idx / 9, e9 = idx - 9 * an;
+          int i = 0, j = 0, src;
+          if (e9 < 6) { int rem = e9; while (rem >= 3 - i) { rem -= 3 - i; ++i; } j = i + rem; src = uidx(i, j); }
+          else { i = e9 - 6; src = 21 + i; }
+          double tot = 0.0;
+          for (int sl = 0; sl < ncl; ++sl)
+            if (sl != an) tot += S_acc[((size_t)an * ncl + sl) * 27 + src];
+          if (e9 < 6) Gf[(6 * an + i) * ldg + 6 * an + j] += tot;
+          else Gf[(6 * an + i) * ldg + n] -= tot;
+        }
+      }
+      __syncthreads();
+    }
+    double* G = a.G + (size_t)b * a.g_seq_stride;
+    for (int row = warp; row < n1; row += nwarps)
+      for (int col = row + lane; col < n1; col += 32) G[(size_t)row * a.n1p + col] = Gf[row * ldg + col];
+    if (threadIdx.x == 0 && a.n_acc) a.n_acc[b] = (a.max_valid > 0) ? min(acc_count, a.max_valid) : acc_count;
   }
 }
 
-template <int RHO, bool PS, int QT>
+template <int RHO, bool PS, int QT, bool FUSE>
 void launch_feat_q(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_msckf_features<RHO, PS, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_msckf_features<RHO, PS, QT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr_set = true;
   }
-  k_msckf_features<RHO, PS, QT><<<grid, threads, smem, st>>>(a);
+  k_msckf_features<RHO, PS, QT, FUSE><<<grid, threads, smem, st>>>(a);
 }
 
-template <int RHO, bool PS>
+template <int RHO, bool PS, bool FUSE>
 void launch_feat(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   // register-resident gate sized to the largest block this window can produce (rho * clones - 3 rows)
   const int qmax = a.Mmax - 3;
-  if (qmax <= 9) launch_feat_q<RHO, PS, 9>(a, grid, threads, smem, st);
-  else if (qmax <= 17) launch_feat_q<RHO, PS, 17>(a, grid, threads, smem, st);
-  else if (qmax <= 21) launch_feat_q<RHO, PS, 21>(a, grid, threads, smem, st);
-  else launch_feat_q<RHO, PS, 25>(a, grid, threads, smem, st);
+  if (qmax <= 9) launch_feat_q<RHO, PS, 9, FUSE>(a, grid, threads, smem, st);
+  else if (qmax <= 17) launch_feat_q<RHO, PS, 17, FUSE>(a, grid, threads, smem, st);
+  else if (qmax <= 21) launch_feat_q<RHO, PS, 21, FUSE>(a, grid, threads, smem, st);
+  else launch_feat_q<RHO, PS, 25, FUSE>(a, grid, threads, smem, st);
 }
 
 }  // namespace
 
+// Sets h->feat_fused when the kernel also accumulated the Gram matrix of the stack (FUSE): igv_launch_qr_compress
+// then only runs the factorisation.
 void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   IgvProfScope prof_scope_(h, IGV_K_FEATURES);
   FeatArgs a;
@@ -575,10 +800,43 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   a.hs_seq_stride = (size_t)h->cfg.max_feats * h->qmax * (h->ncols_max + 1); a.F_alloc = h->cfg.max_feats;
   a.Mmax = h->rho * a.L.n_clones;
   a.ldm = a.Mmax | 1;
-  a.per_warp = feat_per_warp(a.Mmax, a.ldm);
-  const int n = 6 * a.L.n_clones;
+  a.ssz = (a.Mmax + 1) * a.ldm;
+  a.per_warp = feat_per_warp(a.Mmax, a.ssz);
+  const int ncl = a.L.n_clones, n = 6 * ncl;
+  a.nt = (n + 1 + 7) / 8; a.ldz = 8 * a.nt + 4;
+  a.G = h->Gws; a.g_seq_stride = (long)h->qr_split_cap * h->gram_n1p * h->gram_n1p; a.n1p = 24 * ((n + 1 + 23) / 24) + 8;
+  a.n_acc = h->n_acc; a.max_valid = l.max_valid;
   const bool ps = ((size_t)n * n * sizeof(double) <= 72 * 1024);
   const size_t fixed = 12 * IGV_MAX_CLONES + (ps ? (size_t)n * n : 0);
+  // ---- fused Gram accumulation: one CTA of up to 16 warps per sequence -----------------------------------------
+  h->feat_fused = false;
+  {
+    const char* e = getenv("IGV_FUSE");          // test knob: 1 forces the fused kernel, 0 forbids it
+    const int ef = e ? atoi(e) : -1;
+    const char* q = getenv("IGV_QR_CFG");        // a forced compression kernel needs the materialised stack
+    const int qc = q ? atoi(q) : 0;
+    const bool allowed = ps && a.nt <= 9 && ncl <= 32 && l.F >= 1 && h->compress != IGV_COMPRESS_HOUSEHOLDER && qc == 0;
+    if (allowed && (ef == 1 || (ef != 0 && h->B >= 296))) {
+      const int ntt = a.nt * (a.nt + 1) / 2;
+      const int ssz = max(a.ssz, 3 * a.ldz + ncl * 27);
+      const int pw = feat_per_warp(a.Mmax, ssz);
+      const size_t extra = (size_t)(ncl + 1) * ncl * 27 + 2 + (size_t)ntt * 64 + 8;
+      int W = 16;
+      while (W > 1 && sizeof(double) * (fixed + (size_t)W * pw + extra) > 222 * 1024) --W;
+      const bool room = (size_t)W * pw >= (size_t)(n + 1) * ((n + 1) | 1);   // G is assembled over the per-warp regions
+      if (W >= 12 && room) {
+        W = (l.F + (l.F + W - 1) / W - 1) / ((l.F + W - 1) / W);   // fewest warps with the same number of rounds
+        a.ssz = ssz; a.per_warp = pw;
+        const size_t smem = sizeof(double) * (fixed + (size_t)W * pw + extra);
+        dim3 grid(1, h->B);
+        if (h->rho == 2) launch_feat<2, true, true>(a, grid, W * 32, smem, h->stream);
+        else launch_feat<4, true, true>(a, grid, W * 32, smem, h->stream);
+        h->feat_fused = true;
+        h->launches++;
+        return;
+      }
+    }
+  }
   int W = kWarps;
   while (W > 1 && sizeof(double) * (fixed + (size_t)W * a.per_warp) > 200 * 1024) --W;
   const size_t smem = sizeof(double) * (fixed + (size_t)W * a.per_warp);
@@ -589,11 +847,11 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   const int blocks_x = max(1, min((l.F + per_cta - 1) / per_cta, 64));
   dim3 grid(blocks_x, h->B);
   if (h->rho == 2) {
-    if (ps) launch_feat<2, true>(a, grid, W * 32, smem, h->stream);
-    else launch_feat<2, false>(a, grid, W * 32, smem, h->stream);
+    if (ps) launch_feat<2, true, false>(a, grid, W * 32, smem, h->stream);
+    else launch_feat<2, false, false>(a, grid, W * 32, smem, h->stream);
   } else {
-    if (ps) launch_feat<4, true>(a, grid, W * 32, smem, h->stream);
-    else launch_feat<4, false>(a, grid, W * 32, smem, h->stream);
+    if (ps) launch_feat<4, true, false>(a, grid, W * 32, smem, h->stream);
+    else launch_feat<4, false, false>(a, grid, W * 32, smem, h->stream);
   }
   h->launches++;
 }

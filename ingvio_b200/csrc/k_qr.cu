@@ -533,16 +533,24 @@ void igv_launch_qr_compress(igv_batch* h, int F, int max_valid) {
     const int s = atoi(env);
     if (s >= 1) split = min(h->qr_split_cap, min(s, max(1, F)));
   }
+  if (h->feat_fused) {   // k_msckf_features<FUSE> already left the Gram matrix of the accepted stack in Gws
+    h->feat_fused = false;
+    h->last_visual_path = 2;
+    igv_launch_gram_factor(h, 1);
+    return;
+  }
   {
     // IGV_QR_CFG (test knob) >= 1 forces one of the Householder kernels, 30 forces the Gram path
     const char* e = getenv("IGV_QR_CFG");
     const int cfg = e ? atoi(e) : 0;
     const bool forced_hh = (cfg > 0 && cfg != 30) || h->compress == IGV_COMPRESS_HOUSEHOLDER;
     if (!forced_hh && igv_gram_supported(n)) {
+      h->last_visual_path = 1;
       igv_launch_gram_compress(h, F, max_valid, split);
       return;
     }
   }
+  h->last_visual_path = 0;
   QrArgs a;
   a.Hs = h->Hs; a.F = F; a.qmax = h->qmax; a.ldo = n + 1; a.f_rows = h->f_rows; a.max_valid = max_valid;
   a.dense = nullptr; a.dense_stride = 0; a.dense_rows = 0; a.src_mode = 0;

@@ -112,6 +112,10 @@ class BatchFilter:
         """capi.COMPRESS_AUTO | COMPRESS_HOUSEHOLDER | COMPRESS_GRAM: how msckf_update forms [R | Q^T r]."""
         self._ck(self.lib.igv_set_compression(self.h, int(kind)))
 
+    def last_visual_path(self):
+        """0 Householder QR, 1 Gram of the materialised stack, 2 Gram fused into the per-track kernel."""
+        return int(self.lib.igv_last_visual_path(self.h))
+
     def synchronize(self):
         self._ck(self.lib.igv_synchronize(self.h))
 
