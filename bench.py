@@ -308,11 +308,13 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
-        def timed(idx, table, after_step=None):
+        def timed(idx, table, after_step=None, before_stop=None):
             for i in idx[:W]:
                 run_step(g, table[i], frames[i][1])
                 if after_step:
                     after_step()
+            if before_stop:
+                before_stop()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0 = g.launch_count
@@ -321,6 +323,8 @@ def main():
                 run_step(g, table[i], frames[i][1])
                 if after_step:
                     after_step()
+            if before_stop:
+                before_stop()
             e1.record(ts)
             barrier()
             ms = e0.elapsed_time(e1)
@@ -340,15 +344,33 @@ def main():
         clk.start()
         ms_dev, launches = timed(seg(0), dev_frames)
         clocks = clk.stop()
-        # ---- (2) e2e: pinned host inputs through the same API + D2H read of mean and trace(P) ----
-        d2h = {"n": 0}
+        # ---- (2) e2e: pinned host inputs through the same API + D2H read of mean and trace(P) EVERY step ----
+        # The read-back is pipelined by one frame (igv_*_async + fences): the host submits frame k+1 (its bulk
+        # host->device copies travel on the library's copy stream) before it consumes the result of frame k.
+        nx = g.state_size()
+        xbuf = [torch.empty((B, nx), dtype=torch.float64).pin_memory() for _ in range(2)]
+        tbuf = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in range(2)]
+        d2h = {"n": xbuf[0].numel() * 8 + tbuf[0].numel() * 8, "i": 0, "sum": 0.0}
+
+        def consume(slot):
+            g.fence_wait(slot)
+            d2h["sum"] += float(tbuf[slot][0]) + float(xbuf[slot][0, 9])   # the host really reads the result
 
         def read_back():
-            x = g.get_state()
-            tr = g.cov_trace()
-            d2h["n"] = x.nbytes + tr.nbytes
+            i = d2h["i"]
+            g.get_state_async(xbuf[i % 2])
+            g.cov_trace_async(tbuf[i % 2])
+            g.fence_record(i % 2)
+            if i > 0:
+                consume((i - 1) % 2)
+            d2h["i"] = i + 1
 
-        ms_e2e, _ = timed(seg(1), pin_frames, after_step=read_back)
+        def drain():
+            if d2h["i"] > 0:
+                consume((d2h["i"] - 1) % 2)
+            d2h["i"] = 0
+
+        ms_e2e, _ = timed(seg(1), pin_frames, after_step=read_back, before_stop=drain)
         # ---- (3) per-kernel-family device times (CUDA events on the launching stream) ----
         lib = g.lib
         import ctypes as C
@@ -389,37 +411,58 @@ def main():
     value = total_updates / (ms_dev * 1e-3)
     e2e_value = total_updates / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (QR compression) ----
+    # ---- roofline of the dominant kernel ----
+    # SURVEY.md section 8(d) per-sequence figures of the stages a kernel covers, x B sequences per launch.
     n = 6 * wl.sw
     q = wl.rho * wl.sw - 3
     m = wl.feats * q
-    qr_launches = max(1, fam["qr"]["launches"])
-    qr_ms = fam["qr"]["ms"] / qr_launches
-    qr_bytes = B * (8.0 * m * (n + 1) + 8.0 * n * (n + 1))          # SURVEY.md §8d "QR compress" bytes x B
-    qr_flops = B * (2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 4.0 * m * n)  # SURVEY.md §8d FLOPs x B
+    r_keep = min(m, n)
+    feat_bytes = 96.0 * wl.sw + 8.0 * wl.rho * wl.feats * wl.sw + 24.0 * wl.feats + 8.0 * m * (n + 1)
+    feat_flops = wl.feats * sum(4.0 * (wl.rho * wl.sw - k) * (n + 3 - k) for k in range(3)) + wl.feats * wl.sw * (wl.rho / 2) * 198.0
+    qr_bytes1 = 8.0 * m * (n + 1) + 8.0 * r_keep * (n + 1)
+    qr_flops1 = (2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 4.0 * m * n) if m > n else 0.0
+    fused = g.last_visual_path() == 2
+    fam_launch = lambda k: max(1, fam[k]["launches"])
+    if fused:
+        # one kernel does the per-track Jacobian / null space / gate AND the compression's accumulation: it is
+        # charged with both stages' algorithmic work; the n x n factorisation (k_gram_factor) is family "qr"
+        dom, dom_kernel = "features", "k_msckf_features<FUSE> (per-track Jacobian + null space + gate + Gram accumulation, DMMA)"
+        dom_bytes, dom_flops = B * (feat_bytes + qr_bytes1), B * (feat_flops + qr_flops1)
+        compulsory = B * (96.0 * wl.sw + 8.0 * wl.rho * wl.feats * wl.sw + 24.0 * wl.feats + 8.0 * n * n + 8.0 * (n + 1) * (n + 2) / 2)
+    elif fam["qr"]["ms"] / fam_launch("qr") >= fam["features"]["ms"] / fam_launch("features"):
+        dom, dom_kernel = "qr", ("k_gram_stream/k_gram_accum + k_gram_factor" if g.last_visual_path() == 1 else "k_qr_* (Householder)")
+        dom_bytes, dom_flops, compulsory = B * qr_bytes1, B * qr_flops1, B * qr_bytes1
+    else:
+        dom, dom_kernel = "features", "k_msckf_features"
+        dom_bytes, dom_flops, compulsory = B * feat_bytes, B * feat_flops, B * feat_bytes
+    dom_ms = fam[dom]["ms"] / fam_launch(dom)
     hbm_peak, peak_src = peaks()
-    achieved_gbs = qr_bytes / (qr_ms * 1e-3) / 1e9
+    achieved_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
     fp64_peak = C.c_double(0.0)
     lib.igv_measure_fp64_peak(local, C.byref(fp64_peak))
     total_prof_ms = sum(v["ms"] for v in fam.values())
     traffic = None
     try:  # DRAM bytes per launch of this kernel from the committed ncu capture, if it is the same configuration
-        tj = json.load(open(os.path.join(ROOT, "profiles", "qr_traffic.json")))
-        if tj.get("workload") == wl.name and int(tj.get("batch", -1)) == B:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "dominant_traffic.json")))
+        if tj.get("workload") == wl.name and int(tj.get("batch", -1)) == B and tj.get("family") == dom and bool(tj.get("fused")) == fused:
             traffic = float(tj["dram_bytes_per_launch"])
     except Exception:
         pass
-    qr_kernel = "k_qr_mma (DMMA panels)" if (n + 1 <= 72 and B >= 1000) else "k_qr_compress"
-    roofline = {"kernel": qr_kernel, "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"kernel": dom_kernel, "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": qr_bytes, "avg_launch_ms": qr_ms,
-                "share_of_step": fam["qr"]["ms"] / total_prof_ms if total_prof_ms else None,
-                "note": "FP64 dense kernel: the binding roof is the FP64 pipe (DFMA = DMMA peak), see roofline_fp64"}
-    roofline_fp64 = {"kernel": qr_kernel, "bound": "fp64_pipe", "achieved": qr_flops / (qr_ms * 1e-3) / 1e12,
+                "algorithmic_bytes_per_launch": dom_bytes, "compulsory_bytes_per_launch": compulsory,
+                "avg_launch_ms": dom_ms,
+                "share_of_step": fam[dom]["ms"] / total_prof_ms if total_prof_ms else None,
+                "note": "algorithmic bytes = SURVEY 8(d) figures of the stages this kernel covers (they include the projected "
+                        "stack's HBM round trip, which the fused kernel never materialises: traffic << algorithmic); the kernel "
+                        "is FP64 issue/latency bound, see roofline_fp64"}
+    roofline_fp64 = {"kernel": dom_kernel, "bound": "fp64_pipe", "achieved": dom_flops / (dom_ms * 1e-3) / 1e12,
                      "peak": fp64_peak.value, "unit": "TFLOP/s",
-                     "frac": (qr_flops / (qr_ms * 1e-3) / 1e12) / fp64_peak.value if fp64_peak.value else None,
+                     "frac": (dom_flops / (dom_ms * 1e-3) / 1e12) / fp64_peak.value if fp64_peak.value else None,
                      "peak_source": "igv_measure_fp64_peak (DFMA probe on this GPU, this run; DMMA.8x8x4 measures the same 37 TFLOP/s)",
-                     "algorithmic_flops_per_launch": qr_flops}
+                     "algorithmic_flops_per_launch": dom_flops,
+                     "note": "SURVEY 8(d) FLOPs of the covered stages (dense null-space projection + Householder QR); the Gram "
+                             "formulation executes fewer"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

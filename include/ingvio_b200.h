@@ -122,6 +122,14 @@ int igv_gnss_idx(const igv_batch* h, int gtype);   /* Type::idx() of a GNSS scal
 int igv_state_size(const igv_batch* h);
 igv_status igv_state_get(igv_batch* h, double* dst);
 igv_status igv_state_set(igv_batch* h, const double* src);
+/* Pipelined read-back: the *_async calls enqueue the copy and return; igv_fence_record marks a point of the handle's
+ * stream (fence 0..3) and igv_fence_wait blocks the host until the device has reached it. With HOST pointers the
+ * destination must be page-locked for the copy to overlap. A caller that reads the result of frame k after
+ * submitting frame k+1 lets the bulk host->device copies of k+1 overlap the kernels of k. */
+igv_status igv_state_get_async(igv_batch* h, double* dst);
+igv_status igv_cov_trace_async(igv_batch* h, double* trace_out /* B */);
+igv_status igv_fence_record(igv_batch* h, int fence);
+igv_status igv_fence_wait(igv_batch* h, int fence);
 
 /* ---- covariance lifecycle (StateManager.cpp:121-242) ---------------------------------------- */
 igv_status igv_cov_get(igv_batch* h, double* dst, int ld);         /* getFullCov; B x (ld*N)       */

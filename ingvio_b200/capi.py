@@ -67,6 +67,10 @@ SIGNATURES = {
     "igv_last_error": (C.c_char_p, [_H]),
     "igv_set_pointer_mode": (C.c_int, [_H, C.c_int]),
     "igv_synchronize": (C.c_int, [_H]),
+    "igv_state_get_async": (C.c_int, [_H, C.c_void_p]),
+    "igv_cov_trace_async": (C.c_int, [_H, C.c_void_p]),
+    "igv_fence_record": (C.c_int, [_H, C.c_int]),
+    "igv_fence_wait": (C.c_int, [_H, C.c_int]),
     "igv_set_compression": (C.c_int, [_H, C.c_int]),
     "igv_last_visual_path": (C.c_int, [_H]),
     "igv_launch_count": (C.c_longlong, [_H]),

@@ -33,32 +33,44 @@ igv_status check_launch(igv_batch* h) {
   return IGV_OK;
 }
 
-// Reserve `bytes` in the staging arena. On growth the old block is RETIRED, not freed: pointers handed
-// out earlier in the same API call (and kernels already enqueued on them) stay valid; retired blocks are
+// Reserve `bytes` in the current staging slot. On growth the old block is RETIRED, not freed: pointers handed
+// out earlier in the same API call (and copies / kernels already enqueued on them) stay valid; retired blocks are
 // released by arena_reset() at the start of a later call (cudaFree synchronises with the device).
 igv_status arena_reserve(igv_batch* h, size_t bytes, char** out) {
+  igv_batch::Slot& s = h->slots[h->slot];
   bytes = (bytes + 255) & ~size_t(255);
-  if (h->arena_off + bytes > h->arena_cap) {
-    const size_t ncap = std::max(h->arena_cap * 2, bytes + (size_t(4) << 20));
+  if (s.off + bytes > s.cap) {
+    const size_t ncap = std::max(s.cap * 2, bytes + (size_t(4) << 20));
     char* n = nullptr;
     IGV_CUDA(h, cudaMalloc(&n, ncap));
-    if (h->arena) h->retired.push_back(h->arena);
-    h->arena = n;
-    h->arena_cap = ncap;
-    h->arena_off = 0;
+    if (s.mem) h->retired.push_back(s.mem);
+    s.mem = n;
+    s.cap = ncap;
+    s.off = 0;
   }
-  *out = h->arena + h->arena_off;
-  h->arena_off += bytes;
+  *out = s.mem + s.off;
+  s.off += bytes;
+  s.used = true;
   return IGV_OK;
 }
 
+// Start of an API call: every kernel of the previous call has been enqueued, so its slot is marked consumed once
+// they finish; the call gets the next slot of the ring, whose earlier readers the copy stream waits for.
 void arena_reset(igv_batch* h) {
-  h->arena_off = 0;
+  igv_batch::Slot& prev = h->slots[h->slot];
+  if (prev.used && prev.consumed) cudaEventRecord(prev.consumed, h->stream);
+  h->slot = (h->slot + 1) % igv_batch::kSlots;
+  igv_batch::Slot& s = h->slots[h->slot];
+  if (s.used && s.consumed && h->copy_stream) cudaStreamWaitEvent(h->copy_stream, s.consumed, 0);
+  s.off = 0;
+  s.used = false;
   for (char* p : h->retired) cudaFree(p);
   h->retired.clear();
 }
 
-// Device view of a bulk argument: the pointer itself in DEVICE mode, else a copy in the arena.
+// Device view of a bulk argument: the pointer itself in DEVICE mode, else a copy in the staging slot. Large
+// arguments are copied on the copy stream (the compute stream waits for them through an event), small ones on the
+// compute stream itself.
 template <class T>
 igv_status stage(igv_batch* h, const T* src, size_t count, const T** out) {
   if (!src) { *out = nullptr; return IGV_OK; }
@@ -67,7 +79,13 @@ igv_status stage(igv_batch* h, const T* src, size_t count, const T** out) {
   igv_status s = arena_reserve(h, count * sizeof(T), &mem);
   if (s != IGV_OK) return s;
   T* dst = reinterpret_cast<T*>(mem);
-  IGV_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  if (h->copy_stream && count * sizeof(T) >= igv_batch::kCopyStreamMin) {
+    IGV_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
+    IGV_CUDA(h, cudaEventRecord(h->copied, h->copy_stream));
+    IGV_CUDA(h, cudaStreamWaitEvent(h->stream, h->copied, 0));
+  } else {
+    IGV_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  }
   *out = dst;
   return IGV_OK;
 }
@@ -173,6 +191,18 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
     e = cudaMemsetAsync((ptr), 0, sizeof(*(ptr)) * (size_t)(count), h->stream);            \
     if (e != cudaSuccess) return bail(#ptr, e);                                            \
   } while (0)
+  e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return bail("copy stream", e);
+  e = cudaEventCreateWithFlags(&h->copied, cudaEventDisableTiming);
+  if (e != cudaSuccess) return bail("event", e);
+  for (auto& sl : h->slots) {
+    e = cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming);
+    if (e != cudaSuccess) return bail("event", e);
+  }
+  for (auto& f : h->fences) {
+    e = cudaEventCreateWithFlags(&f, cudaEventDisableTiming);
+    if (e != cudaSuccess) return bail("event", e);
+  }
   IGV_ALLOC(h->P[0], B * h->ld * h->ld);
   IGV_ALLOC(h->P[1], B * h->ld * h->ld);
   IGV_ALLOC(h->X[0], B * h->xsize);
@@ -214,8 +244,13 @@ igv_status igv_destroy(igv_batch* h) {
   if (!h) return IGV_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
-                  h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws, h->arena};
+                  h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws};
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& sl : h->slots) { if (sl.mem) cudaFree(sl.mem); if (sl.consumed) cudaEventDestroy(sl.consumed); }
+  for (auto& f : h->fences) if (f) cudaEventDestroy(f);
+  if (h->copied) cudaEventDestroy(h->copied);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (char* p : h->retired) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -315,6 +350,12 @@ igv_status igv_state_get(igv_batch* h, double* dst) {
   const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   IGV_CUDA(h, cudaMemcpyAsync(dst, h->Xc(), sizeof(double) * h->B * h->xsize, k, h->stream));
   IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+igv_status igv_state_get_async(igv_batch* h, double* dst) {
+  if (!h || !dst) return IGV_ERR_INVALID;
+  const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  IGV_CUDA(h, cudaMemcpyAsync(dst, h->Xc(), sizeof(double) * h->B * h->xsize, k, h->stream));
   return IGV_OK;
 }
 igv_status igv_state_set(igv_batch* h, const double* src) {
@@ -560,7 +601,7 @@ igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a) {
   e.blk.n_blocks = L.n_clones; e.blk.n = n;
   for (int s = 0; s < L.n_clones; ++s) { e.blk.idx[s] = L.idx_clone[s]; e.blk.size[s] = 6; }
   e.rows = n;
-  e.H = h->Hc; e.strideH = (long)h->ncols_max * (h->ncols_max + 1); e.h_ld = n + 1; e.h_rowmajor = 1;
+  e.H = h->Hc; e.strideH = (long)h->ncols_max * (h->ncols_max + 1); e.h_ld = n + 1; e.h_rowmajor = 1; e.h_upper = 1;
   e.res = h->Hc + n; e.strideRes = e.strideH; e.res_inc = n + 1;
   e.R = nullptr; e.strideR = 0; e.r_kind = IGV_R_ISO; e.r_iso_value = a->noise * a->noise;
   double* ddx = nullptr;
@@ -745,6 +786,29 @@ igv_status igv_cov_trace(igv_batch* h, double* trace_out) {
   IGV_TRY(check_launch(h));
   IGV_TRY(fetch(h, trace_out, dev, (size_t)h->B));
   if (h->ptr_mode == IGV_PTR_DEVICE) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
+igv_status igv_cov_trace_async(igv_batch* h, double* trace_out) {
+  if (!h || !trace_out) return IGV_ERR_INVALID;
+  arena_reset(h);
+  double* dev;
+  IGV_TRY(out_buf(h, trace_out, (size_t)h->B, &dev));
+  igv_launch_trace(h, dev);
+  IGV_TRY(check_launch(h));
+  if (h->ptr_mode == IGV_PTR_HOST)
+    IGV_CUDA(h, cudaMemcpyAsync(trace_out, dev, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
+  return IGV_OK;
+}
+
+igv_status igv_fence_record(igv_batch* h, int fence) {
+  if (!h || fence < 0 || fence >= 4) return IGV_ERR_INVALID;
+  IGV_CUDA(h, cudaEventRecord(h->fences[fence], h->stream));
+  return IGV_OK;
+}
+igv_status igv_fence_wait(igv_batch* h, int fence) {
+  if (!h || fence < 0 || fence >= 4) return IGV_ERR_INVALID;
+  IGV_CUDA(h, cudaEventSynchronize(h->fences[fence]));
   return IGV_OK;
 }
 

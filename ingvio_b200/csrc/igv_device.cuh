@@ -211,8 +211,11 @@ __device__ __forceinline__ void mma884(double& d0, double& d1, double a, double 
       : "d"(a), "d"(b));
 }
 
-template <int TU, int TV, class FA, class FB, class FC, class FS>
-__device__ __forceinline__ void cta_gemm_mma(int M, int N, int K, FA a, FB b, FC c, FS skip) {
+// `kbegin(i0, j0)` (a multiple of 4) lets a caller with a triangular operand skip the leading zero part of the
+// contraction; `cload(i, j)` is issued BEFORE the k loop and its value handed to `c(i, j, acc, old)`, so a
+// read-modify-write of C in global memory overlaps the contraction instead of trailing it.
+template <int TU, int TV, class FA, class FB, class FC, class FS, class FK, class FL>
+__device__ __forceinline__ void cta_gemm_mma_ex(int M, int N, int K, FA a, FB b, FC c, FS skip, FK kbegin, FL cload) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int fk = lane & 3, fc = lane >> 2;
   constexpr int BM = 8 * TU, BN = 8 * TV;
@@ -225,12 +228,18 @@ __device__ __forceinline__ void cta_gemm_mma(int M, int N, int K, FA a, FB b, FC
     for (int u = 0; u < TU; ++u) ia[u] = min(i0 + 8 * u + fc, M - 1);
 #pragma unroll
     for (int v = 0; v < TV; ++v) jb[v] = min(j0 + 8 * v + fc, N - 1);
-    double acc[TU][TV][2];
+    double acc[TU][TV][2], old[TU][TV][2];
 #pragma unroll
     for (int u = 0; u < TU; ++u)
 #pragma unroll
-      for (int v = 0; v < TV; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
-    for (int k0 = 0; k0 < K; k0 += 4) {
+      for (int v = 0; v < TV; ++v) {
+        acc[u][v][0] = acc[u][v][1] = 0.0;
+        const int row = min(i0 + 8 * u + fc, M - 1), col = j0 + 8 * v + 2 * fk;
+        old[u][v][0] = cload(row, min(col, N - 1));
+        old[u][v][1] = cload(row, min(col + 1, N - 1));
+      }
+#pragma unroll 4
+    for (int k0 = kbegin(i0, j0); k0 < K; k0 += 4) {
       const int k = k0 + fk;
       const bool vk = k < K;
       const int kk = vk ? k : K - 1;
@@ -250,11 +259,17 @@ __device__ __forceinline__ void cta_gemm_mma(int M, int N, int K, FA a, FB b, FC
       for (int v = 0; v < TV; ++v) {
         const int row = i0 + 8 * u + fc, col = j0 + 8 * v + 2 * fk;
         if (row < M) {
-          if (col < N) c(row, col, acc[u][v][0]);
-          if (col + 1 < N) c(row, col + 1, acc[u][v][1]);
+          if (col < N) c(row, col, acc[u][v][0], old[u][v][0]);
+          if (col + 1 < N) c(row, col + 1, acc[u][v][1], old[u][v][1]);
         }
       }
   }
+}
+
+template <int TU, int TV, class FA, class FB, class FC, class FS>
+__device__ __forceinline__ void cta_gemm_mma(int M, int N, int K, FA a, FB b, FC c, FS skip) {
+  cta_gemm_mma_ex<TU, TV>(M, N, K, a, b, [&](int i, int j, double v, double) { c(i, j, v); }, skip,
+                          [](int, int) { return 0; }, [](int, int) { return 0.0; });
 }
 
 // In-place lower Cholesky of the n x n matrix S (column-major, leading dim lds), CTA-cooperative,

@@ -92,9 +92,17 @@ struct igv_batch {
   std::vector<ProfEv> prof_events;
   double prof_ms[IGV_K_COUNT] = {0};
   long long prof_cnt[IGV_K_COUNT] = {0};
-  // host->device staging arena
-  char* arena = nullptr;
-  size_t arena_cap = 0, arena_off = 0;
+  // host->device staging (HOST pointer mode): a ring of arenas, one per API call. Bulk arguments travel on a copy
+  // stream, so the copies of the NEXT calls overlap the kernels of the current ones; a slot is reused only after
+  // the kernels that read it have finished (event `consumed`).
+  static constexpr int kSlots = 8;
+  static constexpr size_t kCopyStreamMin = size_t(128) << 10;   // smaller arguments ride the compute stream
+  struct Slot { char* mem = nullptr; size_t cap = 0, off = 0; cudaEvent_t consumed = nullptr; bool used = false; };
+  Slot slots[kSlots];
+  int slot = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied = nullptr;
+  cudaEvent_t fences[4] = {nullptr, nullptr, nullptr, nullptr};   // igv_fence_record / igv_fence_wait
   std::vector<char*> retired;
 
   IgvLayout layout() const;
@@ -130,6 +138,7 @@ struct IgvEkfLaunch {
   IgvBlocks blk;
   int rows;
   const double* H; long strideH; int h_ld; int h_rowmajor;
+  int h_upper;               // H is upper triangular (zero left of the diagonal): set for the compressed visual rows
   const double* res; long strideRes; int res_inc;
   const double* R; long strideR; int r_kind;
   double r_iso_value;        // used when r_kind == IGV_R_ISO and R == nullptr

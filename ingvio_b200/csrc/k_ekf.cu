@@ -27,6 +27,7 @@ struct EkfArgs {
   const double* R; long strideR; int r_kind; double r_iso_value; const int* only_if;
   double* Zws; long strideZ; double* Sws; long strideS;
   int z_in_smem, s_in_smem, ld_pad;
+  int h_upper;               // H is upper triangular (rows = compressed [R | y]): leading zeros are skipped
   double* dx_out; double* dxws;
   int gamma_only; double* gamma_out;
   const int* gate_rows; const double* chi2; int chi2_n;
@@ -34,7 +35,9 @@ struct EkfArgs {
   int* flags;
 };
 
-__global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
+constexpr int kEkfThreads = 384;   // 12 warps: two CTAs per SM at 80 registers, 24 warps to hide the operand latency
+
+__global__ void __launch_bounds__(kEkfThreads, 2) k_ekf_update(EkfArgs a) {
   extern __shared__ double sm[];
   __shared__ int cols[6 * IGV_MAX_BLOCKS];
   __shared__ int s_ok;
@@ -70,11 +73,14 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
   //     the thread-fast index is i so that P reads are contiguous.
   {
     const int Ni = a.gamma_only ? n : N;  // gate only needs the measured rows of P
-    cta_gemm_mma<2, 2>(Ni, r, n,
-                       [&](int i, int k) { const int ii = a.gamma_only ? cols[i] : i; return Pb[ii + (size_t)cols[k] * ld]; },
-                       [&](int k, int j) { return Hat(j, k); },
-                       [&](int i, int j, double v) { Z[j + (size_t)i * ldz] = v; },
-                       [](int, int) { return false; });
+    // H upper triangular (the compressed [R | y]): row j of H is zero left of column j, so the contraction of
+    // the output block of rows j0.. starts at k = j0
+    cta_gemm_mma_ex<2, 2>(Ni, r, n,
+                          [&](int i, int k) { const int ii = a.gamma_only ? cols[i] : i; return Pb[ii + (size_t)cols[k] * ld]; },
+                          [&](int k, int j) { return Hat(j, k); },
+                          [&](int i, int j, double v, double) { Z[j + (size_t)i * ldz] = v; },
+                          [](int, int) { return false; },
+                          [&](int, int j0) { return a.h_upper ? (j0 & ~3) : 0; }, [](int, int) { return 0.0; });
     for (int t = tid; t < r; t += blockDim.x) Z[t + (size_t)N * ldz] = resb[(size_t)t * a.res_inc];
   }
   __syncthreads();
@@ -82,16 +88,17 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
   {
     const double* Rb = a.R ? a.R + (size_t)b * a.strideR : nullptr;
     // only the lower triangle of S is used by the factorisation: blocks above the diagonal are skipped
-    cta_gemm_mma<2, 2>(r, r, n, [&](int i, int k) { return Hat(i, k); },
+    cta_gemm_mma_ex<2, 2>(r, r, n, [&](int i, int k) { return Hat(i, k); },
                        [&](int k, int j) { const int cc = a.gamma_only ? k : cols[k]; return Z[j + (size_t)cc * ldz]; },
-                       [&](int i, int j, double v) {
+                       [&](int i, int j, double v, double) {
                          double rr = 0.0;
                          if (a.r_kind == IGV_R_ISO) rr = (i == j) ? (Rb ? Rb[0] : a.r_iso_value) : 0.0;
                          else if (a.r_kind == IGV_R_DIAG) rr = (i == j) ? Rb[i] : 0.0;
                          else rr = Rb[i + (size_t)j * r];
                          S[i + (size_t)j * lds] = v + rr;
                        },
-                       [](int bi, int bj) { return bj > bi + 15; });
+                       [](int bi, int bj) { return bj > bi + 15; },
+                       [&](int i0, int) { return a.h_upper ? (i0 & ~3) : 0; }, [](int, int) { return 0.0; });
   }
   __syncthreads();
   // (3) S = L L^T
@@ -140,16 +147,17 @@ __global__ void __launch_bounds__(256) k_ekf_update(EkfArgs a) {
     if (a.dx_out) a.dx_out[(size_t)b * N + i] = acc;
   }
   // (7) P -= Y^T Y : blocks of the lower triangle on DMMA, mirrored on store
-  cta_gemm_mma<2, 2>(N, N, r, [&](int i, int k) { return Z[k + (size_t)i * ldz]; },
-                     [&](int k, int j) { return Z[k + (size_t)j * ldz]; },
-                     [&](int i, int j, double v) {
-                       if (j <= i) {
-                         const double val = Pb[i + (size_t)j * ld] - v;
-                         Pb[i + (size_t)j * ld] = val;
-                         if (i != j) Pb[j + (size_t)i * ld] = val;
-                       }
-                     },
-                     [](int bi, int bj) { return bj > bi + 15; });
+  cta_gemm_mma_ex<2, 2>(N, N, r, [&](int i, int k) { return Z[k + (size_t)i * ldz]; },
+                        [&](int k, int j) { return Z[k + (size_t)j * ldz]; },
+                        [&](int i, int j, double v, double old) {
+                          if (j <= i) {
+                            const double val = old - v;
+                            Pb[i + (size_t)j * ld] = val;
+                            if (i != j) Pb[j + (size_t)i * ld] = val;
+                          }
+                        },
+                        [](int bi, int bj) { return bj > bi + 15; }, [](int, int) { return 0; },
+                        [&](int i, int j) { return Pb[i + (size_t)j * ld]; });
   __syncthreads();
   // (8) negative diagonal check (StateManager.cpp:413-421) and box-plus (:425)
   for (int i = tid; i < N; i += blockDim.x)
@@ -174,6 +182,7 @@ void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& l) {
   a.gamma_only = l.gamma_only; a.gamma_out = l.gamma_out;
   a.gate_rows = l.gate_rows; a.chi2 = h->chi2; a.chi2_n = h->chi2_n;
   a.apply_boxplus = l.apply_boxplus; a.flags = h->flags;
+  a.h_upper = l.h_upper;
   // shared-memory placement: Z first, then S, as long as they fit
   const size_t cap = 200 * 1024;
   const int ld_pad = l.rows + ((4 - l.rows % 8) + 8) % 8;   // smallest >= rows that is 4 (mod 8)
@@ -189,6 +198,6 @@ void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& l) {
     cudaFuncSetAttribute(k_ekf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_set = true;
   }
-  k_ekf_update<<<h->B, 256, smem, h->stream>>>(a);
+  k_ekf_update<<<h->B, kEkfThreads, smem, h->stream>>>(a);
   h->launches++;
 }

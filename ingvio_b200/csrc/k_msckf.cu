@@ -99,10 +99,16 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
   double* S_acc = wsbase + (size_t)nwarps * a.per_warp;          // [(ncl+1) anchors][ncl][27]
   double2* Gt = reinterpret_cast<double2*>(                                                     // [ntt][32], 16-byte aligned
       (reinterpret_cast<uintptr_t>(S_acc + (size_t)(ncl + 1) * ncl * 27) + 15) & ~static_cast<uintptr_t>(15));
-  int* flag_s = reinterpret_cast<int*>(Gt + (size_t)ntt * 32);   // [nwarps]
+  int* flag_s = reinterpret_cast<int*>(Gt + (size_t)ntt * 32);   // [16]
+  int* tile_cc = flag_s + 16;                                    // [ntt] tile -> (column tile i) | (column tile j) << 8
   if (FUSE) {
     for (int t = threadIdx.x; t < (ncl + 1) * ncl * 27; t += blockDim.x) S_acc[t] = 0.0;
     for (int t = threadIdx.x; t < ntt * 32; t += blockDim.x) Gt[t] = make_double2(0.0, 0.0);
+    for (int t = threadIdx.x; t < ntt; t += blockDim.x) {
+      int ci = 0, rem = t;
+      while (rem >= a.nt - ci) { rem -= a.nt - ci; ++ci; }
+      tile_cc[t] = ci | ((ci + rem) << 8);
+    }
   }
   __syncthreads();
   const bool drop = (a.mode == IGV_VIS_SELECTED);
@@ -236,7 +242,52 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
     const double T02 = -tau[2] * (T00 * g02 + T01 * g12);
     const double T12 = -tau[2] * (T11 * g12);
     // Q^T x = x - V T^T (V^T x):  z = T^T y, z0 = T00 y0, z1 = T01 y0 + T11 y1, z2 = T02 y0 + T12 y1 + T22 y2
-    // ---- (3) M0 = H_x P_s H_x^T into sS (full storage), one lane per observation pair -------------
+    // ---- (3) M0 = H_x P_s H_x^T into sS (full storage) ------------------------------------------------
+    // Row block of observation k: U_k (rho x 6) on its clone c_k and W_k = -B_k (rho x 3) on the anchor's
+    // rotation columns, so  M0[k1,k2] = U1 P[c1,c2] U2^T + (U1 P[c1,a] + W1 P[a,a]) W2^T + W1 (P[a,c2] U2^T).
+    // The two anchor factors depend on ONE observation each: (3a) computes ga_k = U_k P[c_k,a] + W_k P[a,a]
+    // (rho x 3, into sAm) and pa_k = P[a,c_k] U_k^T (3 x rho, into sE) with one lane per observation, (3b) then
+    // needs a single 6 x 6 block of P_s per observation pair.
+    const int rs = PS_SMEM ? n : 1;               // strides of the P blocks: the SMEM copy is [n][n]; the global
+    const long cs = PS_SMEM ? 1 : a.ld;           // matrix is column-major (symmetric)
+    auto pblk = [&](int cr, int cc) -> const double* {   // block (clone cr, clone cc), element (i,j) at [i*rs + j*cs]
+      return PS_SMEM ? sPs + (6 * cr) * n + 6 * cc : Pb + a.L.idx_clone[cr] + (long)a.L.idx_clone[cc] * a.ld;
+    };
+    for (int k = lane; k < nobs; k += 32) {
+      const int c = k2slot[k];
+      const bool ak = (k == kanc);
+#pragma unroll
+      for (int t = 0; t < RHO; ++t) {
+        const int row = k * RHO + t;
+        double ga[3] = {0.0, 0.0, 0.0}, pa[3] = {0.0, 0.0, 0.0};
+        if (ca >= 0) {
+          double u[6], w[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double bb = sB[row * 3 + j], aa = sA[row * 3 + j];
+            u[j] = ak ? 0.0 : bb;
+            u[3 + j] = (ak && drop) ? 0.0 : -aa;
+            w[j] = ak ? 0.0 : -bb;
+          }
+          const double* p1a = pblk(c, ca);
+          const double* pa2 = pblk(ca, c);
+          const double* paa = pblk(ca, ca);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              ga[j] = fma(u[i], p1a[i * rs + j * cs], ga[j]);
+              pa[j] = fma(pa2[j * rs + i * cs], u[i], pa[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ga[j] = fma(w[i], paa[i * rs + j * cs], ga[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { sAm[row * 3 + j] = ga[j]; sE[row * 3 + j] = pa[j]; }
+      }
+    }
+    __syncwarp();
     {
       const int npair = nobs * (nobs + 1) / 2;
       for (int pr = lane; pr < npair; pr += 32) {
@@ -244,23 +295,26 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
         while (k1 * (k1 + 1) / 2 > pr) --k1;
         while ((k1 + 1) * (k1 + 2) / 2 <= pr) ++k1;
         const int k2 = pr - k1 * (k1 + 1) / 2;  // k1 >= k2
-        const int c1 = k2slot[k1], c2 = k2slot[k2];
-        // strides of the P blocks: SMEM copy is [n][n]; the global matrix is column-major (symmetric)
-        const int rs = PS_SMEM ? n : 1;
-        const long cs = PS_SMEM ? 1 : a.ld;
-        const double* p12 = PS_SMEM ? sPs + (6 * c1) * n + 6 * c2 : Pb + a.L.idx_clone[c1] + (long)a.L.idx_clone[c2] * a.ld;
-        const double* pa2 = nullptr; const double* p1a = nullptr; const double* paa = nullptr;
-        if (ca >= 0) {
-          pa2 = PS_SMEM ? sPs + (6 * ca) * n + 6 * c2 : Pb + a.L.idx_clone[ca] + (long)a.L.idx_clone[c2] * a.ld;
-          p1a = PS_SMEM ? sPs + (6 * c1) * n + 6 * ca : Pb + a.L.idx_clone[c1] + (long)a.L.idx_clone[ca] * a.ld;
-          paa = PS_SMEM ? sPs + (6 * ca) * n + 6 * ca : Pb + a.L.idx_clone[ca] + (long)a.L.idx_clone[ca] * a.ld;
-        }
+        const double* p12 = pblk(k2slot[k1], k2slot[k2]);
         const bool a1 = (k1 == kanc), a2 = (k2 == kanc);
+        // rows of observation k2: u2 (6, own clone), w2 (3, anchor rotation), pa2 (3: column of P[a,c2] U2^T)
+        double u2[RHO][6], w2[RHO][3], pa2[RHO][3];
+#pragma unroll
+        for (int t2 = 0; t2 < RHO; ++t2) {
+          const int r2 = k2 * RHO + t2;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double bb = sB[r2 * 3 + j], aa = sA[r2 * 3 + j];
+            u2[t2][j] = a2 ? 0.0 : bb;
+            u2[t2][3 + j] = (a2 && drop) ? 0.0 : -aa;
+            w2[t2][j] = (a2 || ca < 0) ? 0.0 : -bb;
+            pa2[t2][j] = sE[r2 * 3 + j];
+          }
+        }
 #pragma unroll
         for (int t1 = 0; t1 < RHO; t1 += 2) {
           const int r1 = k1 * RHO + t1;
-          // rows r1, r1+1 of H_x: u (6 on clone c1), w (3 on the anchor's rotation columns)
-          double u[2][6], w[2][3];
+          double u[2][6], w[2][3], ga[2][3];
 #pragma unroll
           for (int t = 0; t < 2; ++t)
 #pragma unroll
@@ -269,16 +323,11 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
               u[t][j] = a1 ? 0.0 : bb;
               u[t][3 + j] = (a1 && drop) ? 0.0 : -aa;
               w[t][j] = (a1 || ca < 0) ? 0.0 : -bb;
+              ga[t][j] = sAm[(r1 + t) * 3 + j];
             }
-          // g = row * P[:, clone c2 block] (6),  ga = row * P[:, anchor rot] (3)
-          double g[2][6], ga[2][3];
+          double g[2][6];   // rows r1, r1+1 of U1 P[c1,c2]
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) g[t][j] = 0.0;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) ga[t][j] = 0.0;
-          }
+          for (int j = 0; j < 6; ++j) g[0][j] = g[1][j] = 0.0;
 #pragma unroll
           for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -287,48 +336,16 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
               g[0][j] = fma(u[0][i], p, g[0][j]);
               g[1][j] = fma(u[1][i], p, g[1][j]);
             }
-          if (ca >= 0 && !a1) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j = 0; j < 6; ++j) {
-                const double p = pa2[i * rs + j * cs];
-                g[0][j] = fma(w[0][i], p, g[0][j]);
-                g[1][j] = fma(w[1][i], p, g[1][j]);
-              }
-          }
-          if (ca >= 0 && !a2) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                const double p = p1a[i * rs + j * cs];
-                ga[0][j] = fma(u[0][i], p, ga[0][j]);
-                ga[1][j] = fma(u[1][i], p, ga[1][j]);
-              }
-            if (!a1) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                  const double p = paa[i * rs + j * cs];
-                  ga[0][j] = fma(w[0][i], p, ga[0][j]);
-                  ga[1][j] = fma(w[1][i], p, ga[1][j]);
-                }
-            }
-          }
 #pragma unroll
           for (int t2 = 0; t2 < RHO; ++t2) {
             const int r2 = k2 * RHO + t2;
             double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
+            for (int j = 0; j < 6; ++j) { acc0 = fma(g[0][j], u2[t2][j], acc0); acc1 = fma(g[1][j], u2[t2][j], acc1); }
+#pragma unroll
             for (int j = 0; j < 3; ++j) {
-              const double bb = sB[r2 * 3 + j], aa = sA[r2 * 3 + j];
-              const double u2r = a2 ? 0.0 : bb;
-              const double u2t = (a2 && drop) ? 0.0 : -aa;
-              const double w2 = (a2 || ca < 0) ? 0.0 : -bb;
-              acc0 = fma(g[0][j], u2r, acc0); acc0 = fma(g[0][3 + j], u2t, acc0); acc0 = fma(ga[0][j], w2, acc0);
-              acc1 = fma(g[1][j], u2r, acc1); acc1 = fma(g[1][3 + j], u2t, acc1); acc1 = fma(ga[1][j], w2, acc1);
+              acc0 = fma(w[0][j], pa2[t2][j], acc0); acc0 = fma(ga[0][j], w2[t2][j], acc0);
+              acc1 = fma(w[1][j], pa2[t2][j], acc1); acc1 = fma(ga[1][j], w2[t2][j], acc1);
             }
             if (r2 <= r1) { sS[r1 * ldm + r2] = acc0; sS[r2 * ldm + r1] = acc0; }
             if (r2 <= r1 + 1) { sS[(r1 + 1) * ldm + r2] = acc1; sS[r2 * ldm + r1 + 1] = acc1; }
@@ -662,35 +679,34 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
       const int fk = lane & 3, fc = lane >> 2;
       if (lane == 0) flag_s[warp] = flag;
       __syncthreads();
-      unsigned onmask = 0;   // warps whose track enters the update: accepted and inside the max_valid cap
-      for (int w = 0; w < nwarps; ++w)
-        if (flag_s[w]) {
-          if (a.max_valid <= 0 || acc_count < a.max_valid) onmask |= 1u << w;
-          ++acc_count;
-        }
+      // warps whose track enters the update: accepted by the gate and inside the max_valid cap (in track order)
+      const unsigned accm = __ballot_sync(0xffffffffu, lane < nwarps && flag_s[lane < nwarps ? lane : 0] != 0);
+      unsigned onmask = accm;
+      if (a.max_valid > 0) {
+        onmask = 0;
+        unsigned mm = accm;
+        for (int left = a.max_valid - acc_count; mm && left > 0; --left) { onmask |= mm & (0u - mm); mm &= mm - 1; }
+      }
+      acc_count += __popc(accm);
       if (onmask) {
-        // G -= Z^T Z over the 3 * nwarps staged rows; the upper-triangle tiles are dealt to the warps
-        const int nrows = 3 * nwarps;
+        // G -= Z^T Z: one k-step per contributing warp (its 3 rows of Z + a zero row); the upper-triangle tiles
+        // are dealt to the warps
         for (int ti = warp; ti < ntt; ti += nwarps) {
-          int ci = 0, rem = ti;
-          while (rem >= a.nt - ci) { rem -= a.nt - ci; ++ci; }
-          const int cj = ci + rem;
+          const int cc = tile_cc[ti], ci8 = 8 * (cc & 0xff), cj8 = 8 * (cc >> 8);
           double2 g = Gt[ti * 32 + lane];
-          for (int k0 = 0; k0 < nrows; k0 += 4) {
-            const int r = k0 + fk, w = r / 3, p = r - 3 * w;
-            const bool on = (r < nrows) && ((onmask >> w) & 1u);
-            const double* zp = wsbase + (size_t)(on ? w : 0) * a.per_warp + zoff + p * a.ldz + fc;
-            const double za = on ? zp[8 * ci] : 0.0, zb = on ? zp[8 * cj] : 0.0;
-            mma884(g.x, g.y, -za, zb);
+          for (unsigned mm = onmask; mm; mm &= mm - 1) {
+            const int w = __ffs(mm) - 1;
+            const double* zp = wsbase + (size_t)w * a.per_warp + zoff + (fk < 3 ? fk : 0) * a.ldz + fc;
+            const double za = zp[ci8], zb = zp[cj8];
+            mma884(g.x, g.y, fk < 3 ? -za : 0.0, fk < 3 ? zb : 0.0);
           }
           Gt[ti * 32 + lane] = g;
         }
         for (int idx = threadIdx.x; idx < ncl * 27; idx += blockDim.x)
-          for (int w = 0; w < nwarps; ++w)
-            if ((onmask >> w) & 1u) {
-              const int aw = flag_s[w] - 1;
-              S_acc[(size_t)aw * ncl * 27 + idx] += (wsbase + (size_t)w * a.per_warp + zoff + 3 * a.ldz)[idx];
-            }
+          for (unsigned mm = onmask; mm; mm &= mm - 1) {
+            const int w = __ffs(mm) - 1;
+            S_acc[(size_t)(flag_s[w] - 1) * ncl * 27 + idx] += (wsbase + (size_t)w * a.per_warp + zoff + 3 * a.ldz)[idx];
+          }
       }
       __syncthreads();
     }
@@ -701,9 +717,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
     const int n1 = n + 1, ldg = n1 | 1;
     double* Gf = wsbase;
     for (int ti = warp; ti < ntt; ti += nwarps) {
-      int ci = 0, rem = ti;
-      while (rem >= a.nt - ci) { rem -= a.nt - ci; ++ci; }
-      const int cj = ci + rem;
+      const int ci = tile_cc[ti] & 0xff, cj = tile_cc[ti] >> 8;
       const double2 g = Gt[ti * 32 + lane];
       const int row = 8 * ci + fc, col = 8 * cj + 2 * fk;
       if (row < n1) {
@@ -820,7 +834,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
       const int ntt = a.nt * (a.nt + 1) / 2;
       const int ssz = max(a.ssz, 3 * a.ldz + ncl * 27);
       const int pw = feat_per_warp(a.Mmax, ssz);
-      const size_t extra = (size_t)(ncl + 1) * ncl * 27 + 2 + (size_t)ntt * 64 + 8;
+      const size_t extra = (size_t)(ncl + 1) * ncl * 27 + 2 + (size_t)ntt * 64 + 8 + (ntt + 1) / 2;
       int W = 16;
       while (W > 1 && sizeof(double) * (fixed + (size_t)W * pw + extra) > 222 * 1024) --W;
       const bool room = (size_t)W * pw >= (size_t)(n + 1) * ((n + 1) | 1);   // G is assembled over the per-warp regions

@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
   double* Pb = a.P + (size_t)b * ld * ld;
   __shared__ int cidx[S];
   __shared__ int s_nC, s_nS, s_has_fs;
-  __shared__ __align__(16) double sPhi[225], sG[180], sT[S * S], sQ[S * S], sM[15 * 12], sBlk[S * S];
+  __shared__ __align__(16) double sPhi[225], sG[180], sT[S * S], sQ[S * S], sM[15 * 12];
+  __shared__ __align__(16) double sBk[S * S], sX[S * S], sY[S * S], sTt[S * S], sTn[S * S];
   __shared__ double s_dt;
   if (tid == 0) {
     int n = 0;
@@ -135,6 +136,16 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
   for (int r = 0; r < S; ++r)
     for (int j = tid; j < N; j += blockDim.x)
       W[r * N + j] = (r < nS) ? Pb[j + (size_t)cidx[r] * ld] : 0.0;  // P symmetric: row == column (coalesced)
+  __syncthreads();
+  // Per IMU sample the reference updates P11 <- sym(T P11 T^T + Q) and P21 <- P21 T^T (StateManager.cpp:51-118).
+  // The strip x strip block Bk = P11 follows that recursion step by step (including the per-step symmetrisation);
+  // the other columns of the strip only ever see the left factor, w <- T_k w, so the product T_K ... T_1 is
+  // accumulated (S x S) and applied to them ONCE after the last sample: per-step cost O(S^3), not O(S^2 N).
+  for (int t = tid; t < S * S; t += blockDim.x) {
+    const int r = t / S, c = t % S;
+    sBk[t] = (r < nS && c < nS) ? W[r * N + cidx[c]] : 0.0;
+    sTt[t] = (r == c) ? 1.0 : 0.0;
+  }
   __syncthreads();
   for (int step = 0; step < a.n_steps; ++step) {
     // load this step's Phi (15x15) and G*diag(sigma) (15x12), row-major, all threads
@@ -162,24 +173,27 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
       else if (r >= 15 && r < nC && c == nS - 1 && has_fs) val = dt;
       sT[t] = val;
     }
+    __syncthreads();
+    // the S x S products run on DMMA (cta_gemm_mma, 8 x 8 tiles dealt to the 4 warps): the scalar version spent
+    // two shared-memory loads per FMA and was bound by shared-memory bandwidth
+    auto none = [](int, int) { return false; };
     // M = Phi * Gs (15 x 12)
-    for (int t = tid; t < 180; t += blockDim.x) {
-      const int r = t / 12, c = t % 12;
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < 15; ++k) acc = fma(sPhi[r * 15 + k], sG[k * 12 + c], acc);
-      sM[t] = acc;
-    }
+    cta_gemm_mma<1, 1>(15, 12, 15, [&](int i, int k) { return sPhi[i * 15 + k]; }, [&](int k, int j) { return sG[k * 12 + j]; },
+                       [&](int i, int j, double v) { sM[i * 12 + j] = v; }, none);
+    // X = Bk T^T and the accumulated transition Tn = T Tt
+    cta_gemm_mma<1, 1>(S, S, S, [&](int i, int k) { return sBk[i * S + k]; }, [&](int k, int j) { return sT[j * S + k]; },
+                       [&](int i, int j, double v) { sX[i * S + j] = v; }, none);
+    cta_gemm_mma<1, 1>(S, S, S, [&](int i, int k) { return sT[i * S + k]; }, [&](int k, int j) { return sTt[k * S + j]; },
+                       [&](int i, int j, double v) { sTn[i * S + j] = v; }, none);
     __syncthreads();
     // Q block: dt * M M^T on the IMU part (StateManager.cpp:97) + clock terms (:99-116)
+    cta_gemm_mma<1, 1>(15, 15, 12, [&](int i, int k) { return sM[i * 12 + k]; }, [&](int k, int j) { return sM[j * 12 + k]; },
+                       [&](int i, int j, double v) { sQ[i * S + j] = v * dt; }, none);
     for (int t = tid; t < S * S; t += blockDim.x) {
       const int r = t / S, c = t % S;
+      if (r < 15 && c < 15) continue;
       double q = 0.0;
-      if (r < 15 && c < 15) {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) q = fma(sM[r * 12 + k], sM[c * 12 + k], q);
-        q *= dt;
-      } else if (a.enable_gnss && r >= 15 && c >= 15 && r < nS && c < nS) {
+      if (a.enable_gnss && r >= 15 && c >= 15 && r < nS && c < nS) {
         const bool rf = has_fs && (r == nS - 1), cf = has_fs && (c == nS - 1);
         const double rw2 = a.prm.noise_cb_rw * a.prm.noise_cb_rw;
         if (!rf && !cf) q = dt * a.prm.noise_cb * a.prm.noise_cb + dt * dt * dt * rw2;
@@ -188,54 +202,43 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
       }
       sQ[t] = q;
     }
-    // (1) column update on the strip: W1[r, cidx[c]] = sum_k W[r, cidx[k]] T[c,k]
-    for (int t = tid; t < S * S; t += blockDim.x) {
-      const int r = t / S, c = t % S;
-      double acc = 0.0;
-      if (r < nS && c < nS) {
-        for (int k = 0; k < nS; ++k) acc = fma(W[r * N + cidx[k]], sT[c * S + k], acc);
-      }
-      sBlk[t] = acc;
-    }
+    // Y = T X
+    cta_gemm_mma<1, 1>(S, S, S, [&](int i, int k) { return sT[i * S + k]; }, [&](int k, int j) { return sX[k * S + j]; },
+                       [&](int i, int j, double v) { sY[i * S + j] = v; }, none);
+    for (int t = tid; t < S * S; t += blockDim.x) sTt[t] = sTn[t];
     __syncthreads();
-    for (int t = tid; t < S * S; t += blockDim.x) {
+    for (int t = tid; t < S * S; t += blockDim.x) {   // + Q, symmetrise (StateManager.cpp:118)
       const int r = t / S, c = t % S;
-      if (r < nS && c < nS) W[r * N + cidx[c]] = sBlk[t];
-    }
-    __syncthreads();
-    // (2) row update: W2[c, j] = sum_k T[c,k] W1[k, j], one thread per column j; the column lives in
-    //     registers and T is zero padded, so both loops are fully unrolled (no predicates, no local memory)
-    for (int j = tid; j < N; j += blockDim.x) {
-      double col[S];
-#pragma unroll
-      for (int k = 0; k < S; ++k) col[k] = W[k * N + j];
-#pragma unroll 4
-      for (int c = 0; c < S; ++c) {
-        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < S; k += 2) {
-          const double2 tv = *reinterpret_cast<const double2*>(&sT[c * S + k]);
-          acc0 = fma(tv.x, col[k], acc0);
-          acc1 = fma(tv.y, col[k + 1], acc1);
-        }
-        if (c < nS) W[c * N + j] = acc0 + acc1;
-      }
-    }
-    __syncthreads();
-    // (3) + Q and (4) symmetrise the strip x strip block (StateManager.cpp:118)
-    for (int t = tid; t < S * S; t += blockDim.x) {
-      const int r = t / S, c = t % S;
-      double v = 0.0;
-      if (r < nS && c < nS) v = 0.5 * ((W[r * N + cidx[c]] + sQ[r * S + c]) + (W[c * N + cidx[r]] + sQ[c * S + r]));
-      sBlk[t] = v;
-    }
-    __syncthreads();
-    for (int t = tid; t < S * S; t += blockDim.x) {
-      const int r = t / S, c = t % S;
-      if (r < nS && c < nS) W[r * N + cidx[c]] = sBlk[t];
+      sBk[t] = (r < nS && c < nS) ? 0.5 * ((sY[r * S + c] + sQ[r * S + c]) + (sY[c * S + r] + sQ[c * S + r])) : 0.0;
     }
     __syncthreads();
   }
+  // apply the accumulated transition to the columns outside the strip (one thread per column, the column in
+  // registers), then drop the strip x strip block in
+  for (int j = tid; j < N; j += blockDim.x) {
+    bool in_strip = false;
+    for (int c = 0; c < nS; ++c) in_strip |= (cidx[c] == j);
+    if (in_strip) continue;
+    double col[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) col[k] = W[k * N + j];
+#pragma unroll 4
+    for (int c = 0; c < S; ++c) {
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < S; k += 2) {
+        const double2 tv = *reinterpret_cast<const double2*>(&sTt[c * S + k]);
+        acc0 = fma(tv.x, col[k], acc0);
+        acc1 = fma(tv.y, col[k + 1], acc1);
+      }
+      if (c < nS) W[c * N + j] = acc0 + acc1;
+    }
+  }
+  for (int t = tid; t < S * S; t += blockDim.x) {
+    const int r = t / S, c = t % S;
+    if (r < nS && c < nS) W[r * N + cidx[c]] = sBk[t];
+  }
+  __syncthreads();
   // write back rows and mirrored columns
   for (int r = 0; r < nS; ++r)
     for (int j = tid; j < N; j += blockDim.x) {

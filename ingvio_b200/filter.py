@@ -154,6 +154,27 @@ class BatchFilter:
         self._ck(self.lib.igv_state_get(self.h, C.c_void_p(out.ctypes.data)))
         return out
 
+    def get_state_async(self, out):
+        """Enqueue the read-back of the packed mean into `out` (B x state_size; page-locked host tensor/array or a
+        device tensor) and return; pair with fence_record / fence_wait."""
+        a = _Arg(out, np.float64)
+        self._set_mode([a])
+        self._ck(self.lib.igv_state_get_async(self.h, a.ptr))
+
+    def cov_trace_async(self, out):
+        a = _Arg(out, np.float64)
+        self._set_mode([a])
+        self._ck(self.lib.igv_cov_trace_async(self.h, a.ptr))
+
+    def fence_record(self, fence):
+        self._ck(self.lib.igv_fence_record(self.h, int(fence)))
+
+    def fence_wait(self, fence):
+        self._ck(self.lib.igv_fence_wait(self.h, int(fence)))
+
+    def state_size(self):
+        return int(self.lib.igv_state_size(self.h))
+
     def set_state(self, x):
         a = _Arg(x, np.float64)
         self._set_mode([a])
