@@ -26,20 +26,44 @@ struct PropArgs {
   int idx_cb[4]; int idx_fs; int enable_gnss;
 };
 
-// thread 0: mean propagation and Phi (15x15, row-major in sPhi), Gs = G*diag(sigma) (15x12 row-major)
-__device__ void imu_step_mean(double* X, const double* wraw, const double* araw, double dt, const IgvDevParams& prm,
-                              const int* idx_cb, int idx_fs, double* sPhi, double* sG, bool zero_fill = true) {
+// One IMU sample in three pieces (ImuPropagator::stateAndCovTransition, ImuPropagator.cpp:98-162, analytic branch):
+//   imu_gammas : Gamma_0,1,2(w dt) -- depends on the sample only                       (any lane, any order)
+//   imu_mean   : R,p,v <- ... (:126-137) and the clock biases (:139-148)               (sequential over samples)
+//   imu_phi_g  : Phi (15x15, :150-161) and G diag(sigma) (15x12, :112-117, StateManager.cpp:92-96) from the state
+//                BEFORE the sample, the sample and its Gammas                          (any lane, any order)
+// Phi / G go to a zero-initialised workspace whose sparsity pattern never changes, so only non-zeros are written.
+__device__ __forceinline__ void imu_gammas(const double* wraw, const double* bg, double dt, double* G012) {
+  const double wd[3] = {(wraw[0] - bg[0]) * dt, (wraw[1] - bg[1]) * dt, (wraw[2] - bg[2]) * dt};
+  gamma_func(wd, 0, G012); gamma_func(wd, 1, G012 + 9); gamma_func(wd, 2, G012 + 18);
+}
+
+__device__ __forceinline__ void imu_mean(double* X, const double* araw, double dt, const IgvDevParams& prm,
+                                         const int* idx_cb, int idx_fs, const double* G012) {
   double* R = X; double* p = X + 9; double* v = X + 12;
-  const double* bg = X + 15; const double* ba = X + 18;
-  if (zero_fill) {  // the (b, step) workspace is zeroed once at allocation: the sparsity pattern never changes
-    for (int i = 0; i < 225; ++i) sPhi[i] = 0.0;
-    for (int i = 0; i < 180; ++i) sG[i] = 0.0;
+  const double* ba = X + 18;
+  const double a[3] = {araw[0] - ba[0], araw[1] - ba[1], araw[2] - ba[2]};
+  double Rn[9], RG1[9], RG2[9], t1[3], t2[3];
+  mat3_mul(R, G012, Rn); mat3_mul(R, G012 + 9, RG1); mat3_mul(R, G012 + 18, RG2);
+  mat3_vec(RG1, a, t1);
+  mat3_vec(RG2, a, t2);
+  const double* g = prm.g;
+  for (int i = 0; i < 3; ++i) {
+    const double vh = v[i];
+    v[i] = vh + g[i] * dt + t1[i] * dt;
+    p[i] = p[i] + vh * dt + 0.5 * g[i] * dt * dt + t2[i] * dt * dt;
   }
+  for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  if (idx_fs >= 0)  // ImuPropagator.cpp:139-148
+    for (int i = 0; i < 4; ++i) if (idx_cb[i] >= 0) X[33 + i] += dt * X[33 + 4];
+}
+
+// pre: R (9), p (3), v (3) before the sample; post: p, v after it (X + 9 of the next state)
+__device__ void imu_phi_g(const double* pre, const double* pn, const double* vn, const double* bg, const double* ba,
+                          const double* wraw, const double* araw, double dt, const IgvDevParams& prm,
+                          const double* G012, double* sPhi, double* sG) {
+  const double* Rh = pre; const double* ph = pre + 9; const double* vh = pre + 12;
   for (int i = 0; i < 15; ++i) sPhi[16 * i] = 1.0;
-  double Rh[9], ph[3], vh[3], S[9], T[9];
-  for (int i = 0; i < 9; ++i) Rh[i] = R[i];
-  for (int i = 0; i < 3; ++i) { ph[i] = p[i]; vh[i] = v[i]; }
-  // G (ImuPropagator.cpp:112-117), scaled by the noise sigmas (StateManager.cpp:92-96)
+  double S[9], T[9];
   skew3(ph, S); mat3_mul(S, Rh, T);
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
     sG[r * 12 + c] = Rh[3 * r + c] * prm.noise_g;
@@ -53,20 +77,9 @@ __device__ void imu_step_mean(double* X, const double* wraw, const double* araw,
   for (int r = 0; r < 3; ++r) { sG[(9 + r) * 12 + 6 + r] = prm.noise_bg; sG[(12 + r) * 12 + 9 + r] = prm.noise_ba; }
   const double w[3] = {wraw[0] - bg[0], wraw[1] - bg[1], wraw[2] - bg[2]};
   const double a[3] = {araw[0] - ba[0], araw[1] - ba[1], araw[2] - ba[2]};
-  const double wd[3] = {w[0] * dt, w[1] * dt, w[2] * dt};
-  double G0[9], G1[9], G2[9], RG1[9], RG2[9], Rn[9], t[3];
-  gamma_func(wd, 0, G0); gamma_func(wd, 1, G1); gamma_func(wd, 2, G2);
-  mat3_mul(Rh, G0, Rn); mat3_mul(Rh, G1, RG1); mat3_mul(Rh, G2, RG2);
+  double RG1[9], RG2[9];
+  mat3_mul(Rh, G012 + 9, RG1); mat3_mul(Rh, G012 + 18, RG2);
   const double* g = prm.g;
-  double vn[3], pn[3];
-  mat3_vec(RG1, a, t);
-  for (int i = 0; i < 3; ++i) vn[i] = vh[i] + g[i] * dt + t[i] * dt;
-  mat3_vec(RG2, a, t);
-  for (int i = 0; i < 3; ++i) pn[i] = ph[i] + vh[i] * dt + 0.5 * g[i] * dt * dt + t[i] * dt * dt;
-  for (int i = 0; i < 9; ++i) R[i] = Rn[i];
-  for (int i = 0; i < 3; ++i) { p[i] = pn[i]; v[i] = vn[i]; }
-  if (idx_fs >= 0)  // ImuPropagator.cpp:139-148
-    for (int i = 0; i < 4; ++i) if (idx_cb[i] >= 0) X[33 + i] += dt * X[33 + 4];
   // Phi blocks (ImuPropagator.cpp:150-161)
   double Sg[9];
   skew3(g, Sg);
@@ -86,26 +99,49 @@ __device__ void imu_step_mean(double* X, const double* wraw, const double* araw,
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) sPhi[(3 + r) * 15 + 9 + c] = -A1[3 * r + c] * dt + A2[3 * r + c];
 }
 
-// One THREAD per sequence: the K mean-propagation steps are sequential within a sequence but independent
-// across sequences; Phi_k and G_k*sigma go to a workspace that the strip kernel consumes.
-__global__ void __launch_bounds__(64) k_imu_mean(double* X, int xsize, int B, int n_steps, const double* gyro,
-                                                   const double* accel, const double* dt, IgvDevParams prm,
-                                                   int idx_cb0, int idx_cb1, int idx_cb2, int idx_cb3, int idx_fs,
-                                                   double* pre) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per sequence. The K samples of a frame are sequential only through the mean: lanes first evaluate the
+// Gamma functions of their sample, lane 0 then runs the short mean recursion (keeping every intermediate state),
+// and the lanes finally build Phi_k and G_k sigma of their sample for the strip kernel.
+constexpr int kImuWarps = 2, kImuChunk = 32;
+__global__ void __launch_bounds__(kImuWarps * 32) k_imu_mean(double* X, int xsize, int B, int n_steps, const double* gyro,
+                                                             const double* accel, const double* dt, IgvDevParams prm,
+                                                             int idx_cb0, int idx_cb1, int idx_cb2, int idx_cb3, int idx_fs,
+                                                             double* pre) {
+  __shared__ double s_gam[kImuWarps][kImuChunk][27];
+  __shared__ double s_st[kImuWarps][kImuChunk + 1][15];   // R, p, v before sample k (entry kImuChunk: after the last)
+  __shared__ double s_x[kImuWarps][IGV_X_CORE];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kImuWarps + wib;
   if (b >= B) return;
   const int idx_cb[4] = {idx_cb0, idx_cb1, idx_cb2, idx_cb3};
   double* Xb = X + (size_t)b * xsize;
-  double Xl[IGV_X_CORE];  // R, p, v, bg, ba, (extrinsics untouched), GNSS scalars: keep on chip across the K steps
-  for (int i = 0; i < IGV_X_CORE; ++i) Xl[i] = Xb[i];
-  for (int step = 0; step < n_steps; ++step) {
-    const size_t o = (size_t)b * n_steps + step;
-    const double d = dt[o];
-    if (d >= 1e-6)  // ImuPropagator.cpp:262
-      imu_step_mean(Xl, gyro + o * 3, accel + o * 3, d, prm, idx_cb, idx_fs, pre + o * 405, pre + o * 405 + 225, false);
+  double* Xl = s_x[wib];
+  for (int i = lane; i < IGV_X_CORE; i += 32) Xl[i] = Xb[i];
+  __syncwarp();
+  for (int base = 0; base < n_steps; base += kImuChunk) {
+    const int cnt = min(kImuChunk, n_steps - base);
+    const size_t o = (size_t)b * n_steps + base + lane;
+    const double d = (lane < cnt) ? dt[o] : 0.0;
+    const bool live = d >= 1e-6;   // ImuPropagator.cpp:262
+    if (live) imu_gammas(gyro + o * 3, Xl + 15, d, s_gam[wib][lane]);
+    __syncwarp();
+    if (lane == 0) {
+      for (int k = 0; k < cnt; ++k) {
+        for (int i = 0; i < 15; ++i) s_st[wib][k][i] = Xl[i];
+        const size_t ok = (size_t)b * n_steps + base + k;
+        const double dk = dt[ok];
+        if (dk >= 1e-6) imu_mean(Xl, accel + ok * 3, dk, prm, idx_cb, idx_fs, s_gam[wib][k]);
+      }
+      for (int i = 0; i < 15; ++i) s_st[wib][cnt][i] = Xl[i];
+    }
+    __syncwarp();
+    if (live)
+      imu_phi_g(s_st[wib][lane], s_st[wib][lane + 1] + 9, s_st[wib][lane + 1] + 12, Xl + 15, Xl + 18, gyro + o * 3, accel + o * 3,
+                d, prm, s_gam[wib][lane], pre + o * 405, pre + o * 405 + 225);
+    __syncwarp();
   }
-  for (int i = 0; i < 15; ++i) Xb[i] = Xl[i];          // R, p, v
-  for (int i = 33; i < 37; ++i) Xb[i] = Xl[i];         // clock biases (ImuPropagator.cpp:139-148)
+  for (int i = lane; i < 15; i += 32) Xb[i] = Xl[i];                  // R, p, v
+  if (lane < 4) Xb[33 + lane] = Xl[33 + lane];                       // clock biases (ImuPropagator.cpp:139-148)
 }
 
 __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
@@ -272,7 +308,7 @@ void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const d
       h->pre_cap = need;
     }
     a.pre = h->pre_ws;
-    k_imu_mean<<<(h->B + 63) / 64, 64, 0, h->stream>>>(h->Xc(), h->xsize, h->B, n_steps, gyro, accel, dt, h->params,
+    k_imu_mean<<<(h->B + kImuWarps - 1) / kImuWarps, kImuWarps * 32, 0, h->stream>>>(h->Xc(), h->xsize, h->B, n_steps, gyro, accel, dt, h->params,
                                                       a.idx_cb[0], a.idx_cb[1], a.idx_cb[2], a.idx_cb[3], a.idx_fs,
                                                       h->pre_ws);
     h->launches++;
