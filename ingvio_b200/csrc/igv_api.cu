@@ -34,16 +34,18 @@ igv_status check_launch(igv_batch* h) {
 }
 
 // Reserve `bytes` in the current staging slot. On growth the old block is RETIRED, not freed: pointers handed
-// out earlier in the same API call (and copies / kernels already enqueued on them) stay valid; retired blocks are
-// released by arena_reset() at the start of a later call (cudaFree synchronises with the device).
+// out earlier in the same API call (and copies / kernels already enqueued on them) stay valid.
 igv_status arena_reserve(igv_batch* h, size_t bytes, char** out) {
   igv_batch::Slot& s = h->slots[h->slot];
   bytes = (bytes + 255) & ~size_t(255);
   if (s.off + bytes > s.cap) {
-    const size_t ncap = std::max(s.cap * 2, bytes + (size_t(4) << 20));
+    // every slot converges to the same capacity (the largest call seen so far), so a steady-state frame loop stops
+    // allocating after one trip around the ring
+    const size_t ncap = std::max(std::max(s.cap * 2, bytes + (size_t(4) << 20)), h->slot_cap);
+    h->slot_cap = ncap;
     char* n = nullptr;
     IGV_CUDA(h, cudaMalloc(&n, ncap));
-    if (s.mem) h->retired.push_back(s.mem);
+    if (s.mem) h->retired.push_back(s.mem);   // kept until igv_destroy: cudaFree would synchronise the device
     s.mem = n;
     s.cap = ncap;
     s.off = 0;
@@ -57,6 +59,7 @@ igv_status arena_reserve(igv_batch* h, size_t bytes, char** out) {
 // Start of an API call: every kernel of the previous call has been enqueued, so its slot is marked consumed once
 // they finish; the call gets the next slot of the ring, whose earlier readers the copy stream waits for.
 void arena_reset(igv_batch* h) {
+  igv_commit_copies(h);
   igv_batch::Slot& prev = h->slots[h->slot];
   if (prev.used && prev.consumed) cudaEventRecord(prev.consumed, h->stream);
   h->slot = (h->slot + 1) % igv_batch::kSlots;
@@ -64,13 +67,20 @@ void arena_reset(igv_batch* h) {
   if (s.used && s.consumed && h->copy_stream) cudaStreamWaitEvent(h->copy_stream, s.consumed, 0);
   s.off = 0;
   s.used = false;
-  for (char* p : h->retired) cudaFree(p);
-  h->retired.clear();
+  if (s.cap < h->slot_cap) {   // converge to the common capacity right away (the old block is retired, never freed here)
+    char* n = nullptr;
+    if (cudaMalloc(&n, h->slot_cap) == cudaSuccess) {
+      if (s.mem) h->retired.push_back(s.mem);
+      s.mem = n;
+      s.cap = h->slot_cap;
+    } else {
+      cudaGetLastError();
+    }
+  }
 }
 
-// Device view of a bulk argument: the pointer itself in DEVICE mode, else a copy in the staging slot. Large
-// arguments are copied on the copy stream (the compute stream waits for them through an event), small ones on the
-// compute stream itself.
+// Device view of a bulk argument: the pointer itself in DEVICE mode, else a copy in the staging slot, made on the
+// copy stream (the compute stream is ordered after all of a call's copies by ONE event, igv_commit_copies).
 template <class T>
 igv_status stage(igv_batch* h, const T* src, size_t count, const T** out) {
   if (!src) { *out = nullptr; return IGV_OK; }
@@ -79,10 +89,9 @@ igv_status stage(igv_batch* h, const T* src, size_t count, const T** out) {
   igv_status s = arena_reserve(h, count * sizeof(T), &mem);
   if (s != IGV_OK) return s;
   T* dst = reinterpret_cast<T*>(mem);
-  if (h->copy_stream && count * sizeof(T) >= igv_batch::kCopyStreamMin) {
+  if (h->copy_stream) {
     IGV_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
-    IGV_CUDA(h, cudaEventRecord(h->copied, h->copy_stream));
-    IGV_CUDA(h, cudaStreamWaitEvent(h->stream, h->copied, 0));
+    h->copies_pending = true;   // igv_commit_copies orders the compute stream after it before the first kernel
   } else {
     IGV_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   }

@@ -95,13 +95,14 @@ struct igv_batch {
   // host->device staging (HOST pointer mode): a ring of arenas, one per API call. Bulk arguments travel on a copy
   // stream, so the copies of the NEXT calls overlap the kernels of the current ones; a slot is reused only after
   // the kernels that read it have finished (event `consumed`).
-  static constexpr int kSlots = 8;
-  static constexpr size_t kCopyStreamMin = size_t(128) << 10;   // smaller arguments ride the compute stream
+  static constexpr int kSlots = 12;
   struct Slot { char* mem = nullptr; size_t cap = 0, off = 0; cudaEvent_t consumed = nullptr; bool used = false; };
   Slot slots[kSlots];
+  size_t slot_cap = 0;                  // common target capacity of the slots
   int slot = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copied = nullptr;
+  bool copies_pending = false;          // staged copies the compute stream has not been ordered after yet
   cudaEvent_t fences[4] = {nullptr, nullptr, nullptr, nullptr};   // igv_fence_record / igv_fence_wait
   std::vector<char*> retired;
 
@@ -110,9 +111,19 @@ struct igv_batch {
   double* Xc() const { return X[xcur]; }
 };
 
+// Order the compute stream after every host->device copy staged so far (called before the first kernel that may
+// read a staged argument: every launcher does it, through IgvProfScope or directly).
+inline void igv_commit_copies(igv_batch* h) {
+  if (!h->copies_pending) return;
+  cudaEventRecord(h->copied, h->copy_stream);
+  cudaStreamWaitEvent(h->stream, h->copied, 0);
+  h->copies_pending = false;
+}
+
 struct IgvProfScope {
   igv_batch* h; int kind; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
   IgvProfScope(igv_batch* h_, int kind_) : h(h_), kind(kind_), on(h_->prof_on) {
+    igv_commit_copies(h);
     if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
   }
   ~IgvProfScope() {

@@ -385,6 +385,7 @@ int igv_gram_n1p(int ncols_max) { return 24 * ((ncols_max + 1 + 23) / 24) + 8; }
 bool igv_gram_supported(int n) { return (n + 1 + 23) / 24 <= 9; }   // up to 216 columns (SW <= 35)
 
 void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
+  igv_commit_copies(h);
   IgvLayout L = h->layout();
   const int n = 6 * L.n_clones;
   GramArgs a;
@@ -422,6 +423,7 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
 }
 
 void igv_launch_gram_factor(igv_batch* h, int nparts) {
+  igv_commit_copies(h);
   IgvLayout L = h->layout();
   const int n = 6 * L.n_clones;
   FactorArgs f;

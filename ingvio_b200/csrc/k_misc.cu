@@ -139,6 +139,7 @@ __global__ void k_replace_var_linear(double* P, int ld, int N, int t0, int ts, I
 void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
                              const double* res, double noise_iso, double chi2_mult, int do_chi2, double prior_cov,
                              int* accepted_dev) {
+  igv_commit_copies(h);
   // workspace: Hw (rows x n) | rw (rows) | rho   -- carved from Dws (B x (128*18+2) doubles, n <= 16)
   double* Hw = h->Dws;
   double* rw = Hw + (size_t)h->B * rows * blk.n;
@@ -164,6 +165,7 @@ void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const
 }
 
 void igv_launch_replace_var_linear(igv_batch* h, int tidx, int tsize, const IgvBlocks& blk, const double* H) {
+  igv_commit_copies(h);
   const size_t smem = sizeof(double) * ((size_t)h->N * tsize + tsize * tsize);
   k_replace_var_linear<<<h->B, 128, smem, h->stream>>>(h->Pc(), h->ld, h->N, tidx, tsize, blk, H);
   h->launches++;

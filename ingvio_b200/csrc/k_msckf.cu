@@ -253,39 +253,36 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
     auto pblk = [&](int cr, int cc) -> const double* {   // block (clone cr, clone cc), element (i,j) at [i*rs + j*cs]
       return PS_SMEM ? sPs + (6 * cr) * n + 6 * cc : Pb + a.L.idx_clone[cr] + (long)a.L.idx_clone[cc] * a.ld;
     };
-    for (int k = lane; k < nobs; k += 32) {
+    for (int row = lane; row < M; row += 32) {   // one lane per ROW of the stack (observation row / RHO)
+      const int k = row / RHO;
       const int c = k2slot[k];
       const bool ak = (k == kanc);
+      double ga[3] = {0.0, 0.0, 0.0}, pa[3] = {0.0, 0.0, 0.0};
+      if (ca >= 0) {
+        double u[6], w[3];
 #pragma unroll
-      for (int t = 0; t < RHO; ++t) {
-        const int row = k * RHO + t;
-        double ga[3] = {0.0, 0.0, 0.0}, pa[3] = {0.0, 0.0, 0.0};
-        if (ca >= 0) {
-          double u[6], w[3];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const double bb = sB[row * 3 + j], aa = sA[row * 3 + j];
-            u[j] = ak ? 0.0 : bb;
-            u[3 + j] = (ak && drop) ? 0.0 : -aa;
-            w[j] = ak ? 0.0 : -bb;
-          }
-          const double* p1a = pblk(c, ca);
-          const double* pa2 = pblk(ca, c);
-          const double* paa = pblk(ca, ca);
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              ga[j] = fma(u[i], p1a[i * rs + j * cs], ga[j]);
-              pa[j] = fma(pa2[j * rs + i * cs], u[i], pa[j]);
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) ga[j] = fma(w[i], paa[i * rs + j * cs], ga[j]);
-          }
+        for (int j = 0; j < 3; ++j) {
+          const double bb = sB[row * 3 + j], aa = sA[row * 3 + j];
+          u[j] = ak ? 0.0 : bb;
+          u[3 + j] = (ak && drop) ? 0.0 : -aa;
+          w[j] = ak ? 0.0 : -bb;
         }
+        const double* p1a = pblk(c, ca);
+        const double* pa2 = pblk(ca, c);
+        const double* paa = pblk(ca, ca);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { sAm[row * 3 + j] = ga[j]; sE[row * 3 + j] = pa[j]; }
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            ga[j] = fma(u[i], p1a[i * rs + j * cs], ga[j]);
+            pa[j] = fma(pa2[j * rs + i * cs], u[i], pa[j]);
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ga[j] = fma(w[i], paa[i * rs + j * cs], ga[j]);
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { sAm[row * 3 + j] = ga[j]; sE[row * 3 + j] = pa[j]; }
     }
     __syncwarp();
     {
@@ -529,12 +526,22 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
       double* zrow = sS;                      // [3][ldz]
       double* dblk = sS + 3 * a.ldz;          // [ncl][27]
       const int ncolp = 8 * a.nt;
+      // V^T (rows of the anchor's rotation columns): lanes 0..8 hold entry (q = lane / 3, comp = lane % 3) of
+      // -sum_{rows not at the anchor} V[row][q] B[row][comp]
+      double yanc = 0.0;
+      if (ca >= 0 && lane < 9) {
+        const int q_ = lane / 3, cp = lane - 3 * q_;
+        for (int row = 0; row < M; ++row)
+          if (row / RHO != kanc) yanc = fma(sV[row * 3 + q_], -sB[row * 3 + cp], yanc);
+      }
       for (int j0 = 0; j0 < ncolp; j0 += 32) {
         const int j = j0 + lane;
-        if (j >= ncolp) break;
+        const int c = (j < n) ? j / 6 : 0, comp = (j < n) ? j - 6 * c : 0;
+        const int cq = (comp < 3) ? comp : 0;
+        const double ya0 = __shfl_sync(0xffffffffu, yanc, cq), ya1 = __shfl_sync(0xffffffffu, yanc, 3 + cq),
+                     ya2 = __shfl_sync(0xffffffffu, yanc, 6 + cq);
         double zr[3] = {0.0, 0.0, 0.0};
         if (j < n) {
-          const int c = j / 6, comp = j % 6;
           const int kown = slot2k[c];
           const bool anc_rot = (c == anc) && (comp < 3);
           double y0 = 0.0, y1 = 0.0, y2 = 0.0, ownv[RHO];
@@ -549,13 +556,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
             }
             ownv[t] = v;
           }
-          if (anc_rot) {
-            for (int row = 0; row < M; ++row) {
-              if (row / RHO == kanc) continue;
-              const double v = -sB[row * 3 + comp];
-              y0 = fma(sV[row * 3], v, y0); y1 = fma(sV[row * 3 + 1], v, y1); y2 = fma(sV[row * 3 + 2], v, y2);
-            }
-          }
+          if (anc_rot) { y0 += ya0; y1 += ya1; y2 += ya2; }
           const double z0 = T00 * y0, z1 = T01 * y0 + T11 * y1, z2 = T02 * y0 + T12 * y1 + T22 * y2;
           const int own_lo = (kown >= 0) ? kown * RHO : -(1 << 20);
 #pragma unroll
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
         } else if (j == n) {
           zr[0] = sqr[0]; zr[1] = sqr[1]; zr[2] = sqr[2];
         }
-        zrow[j] = zr[0]; zrow[a.ldz + j] = zr[1]; zrow[2 * a.ldz + j] = zr[2];
+        if (j < ncolp) { zrow[j] = zr[0]; zrow[a.ldz + j] = zr[1]; zrow[2 * a.ldz + j] = zr[2]; }
       }
       for (int sl = lane; sl < ncl; sl += 32) {
         double* dd = dblk + sl * 27;
@@ -689,19 +690,36 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
       }
       acc_count += __popc(accm);
       if (onmask) {
-        // G -= Z^T Z: one k-step per contributing warp (its 3 rows of Z + a zero row); the upper-triangle tiles
-        // are dealt to the warps
-        for (int ti = warp; ti < ntt; ti += nwarps) {
-          const int cc = tile_cc[ti], ci8 = 8 * (cc & 0xff), cj8 = 8 * (cc >> 8);
-          double2 g = Gt[ti * 32 + lane];
-          for (unsigned mm = onmask; mm; mm &= mm - 1) {
-            const int w = __ffs(mm) - 1;
-            const double* zp = wsbase + (size_t)w * a.per_warp + zoff + (fk < 3 ? fk : 0) * a.ldz + fc;
-            const double za = zp[ci8], zb = zp[cj8];
-            mma884(g.x, g.y, fk < 3 ? -za : 0.0, fk < 3 ? zb : 0.0);
+        // Gt += Z^T Z over the 3 * nwarps staged rows (four per DMMA k-step; rows of warps that do not contribute
+        // are masked to zero), subtracted from G at the end. The upper-triangle tiles are dealt to the warps, at
+        // most four each (nwarps >= 12, <= 45 tiles), and stay in registers across the k-steps.
+        double2 g[4];
+        int ci8[4], cj8[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ti = warp + u * nwarps;
+          if (ti < ntt) {
+            const int cc = tile_cc[ti];
+            ci8[u] = 8 * (cc & 0xff) + fc; cj8[u] = 8 * (cc >> 8) + fc;
+            g[u] = Gt[ti * 32 + lane];
           }
-          Gt[ti * 32 + lane] = g;
         }
+        const int nrows = 3 * nwarps;
+        for (int k0 = 0; k0 < nrows; k0 += 4) {
+          const int r = k0 + fk, w = (r * 43) >> 7, p = r - 3 * w;   // w = r / 3 for r < 64
+          const bool on = r < nrows && ((onmask >> w) & 1u);
+          if (!__any_sync(0xffffffffu, on)) continue;
+          const double* zp = wsbase + (size_t)(on ? w : 0) * a.per_warp + zoff + p * a.ldz;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (warp + u * nwarps < ntt) {
+              const double za = zp[ci8[u]], zb = zp[cj8[u]];
+              mma884(g[u].x, g[u].y, on ? za : 0.0, on ? zb : 0.0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (warp + u * nwarps < ntt) Gt[(warp + u * nwarps) * 32 + lane] = g[u];
         for (int idx = threadIdx.x; idx < ncl * 27; idx += blockDim.x)
           for (unsigned mm = onmask; mm; mm &= mm - 1) {
             const int w = __ffs(mm) - 1;
@@ -720,9 +738,9 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
       const int ci = tile_cc[ti] & 0xff, cj = tile_cc[ti] >> 8;
       const double2 g = Gt[ti * 32 + lane];
       const int row = 8 * ci + fc, col = 8 * cj + 2 * fk;
-      if (row < n1) {
-        if (col < n1) Gf[row * ldg + col] = g.x;
-        if (col + 1 < n1) Gf[row * ldg + col + 1] = g.y;
+      if (row < n1) {   // Gt holds + sum Z^T Z
+        if (col < n1) Gf[row * ldg + col] = -g.x;
+        if (col + 1 < n1) Gf[row * ldg + col + 1] = -g.y;
       }
     }
     __syncthreads();
