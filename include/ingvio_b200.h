@@ -244,6 +244,37 @@ typedef struct {
 } igv_gnss_args;
 igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a);
 
+/* ---- GNSS residual generator ("next" row) ------------------------------------------
+ * gnss_comm::psr_res (gnss_comm/src/gnss_spp.cpp:99-146) and gnss_comm::dopp_res (:256-282) with sat_azel,
+ * ecef2geo, calculate_trop_delay (Saastamoinen + Niell) and calculate_ion_delay (Klobuchar) of
+ * gnss_comm/src/gnss_utility.cpp:347-387, :762-901, evaluated at the receiver state GnssUpdate::updateTrackedSys
+ * assembles from the filter mean (GnssUpdate.cpp:101-111), plus the measurement sigmas of GnssUpdate.cpp:177-186 and
+ * :246-255. Inputs are the outputs of gnss_comm::sat_states (gnss_spp.cpp:50-97) and the raw L1 observations; the
+ * outputs are the inputs of igv_gnss_update (in DEVICE pointer mode the two calls chain without a host round trip). */
+typedef struct {
+  int n_sats;                /* S <= max_sats                                                                  */
+  const double* sat_pos;     /* B x S x 3  SatState::pos, ECEF at the transmit time [m]                         */
+  const double* sat_vel;     /* B x S x 3  SatState::vel [m/s]                                                  */
+  const double* sat_clk;     /* B x S x 3  SatState::dt [s], ddt [s/s], tgd [s]                                 */
+  const double* obs;         /* B x S x 3  L1 pseudo-range [m], Doppler [Hz], carrier frequency [Hz] (<= 0: the
+                                satellite has no L1 observation and its outputs stay zero, gnss_spp.cpp:117-119) */
+  const double* obs_std;     /* B x S x 3  ephemeris ura, Obs::psr_std, Obs::dopp_std of the L1 observation     */
+  const double* ttx;         /* B x S x 2  transmit time as day of year (time2doy) and GPS seconds of week
+                                (time2gpst), the only uses gnss_comm makes of it here                           */
+  const int* sys;            /* B x S      IGV_GNSS_GPS..BDS (= gnss_comm::sys2idx)                              */
+  const double* T_enu2ecef;  /* B x 12     GvioAligner::getTenu2ecef: rotation (9, row-major) + translation (3) */
+  const double* iono;        /* B x 8      Klobuchar parameters, or NULL (no ionospheric delay)                 */
+  double psr_noise_amp, dopp_noise_amp;   /* _psr_noise_amp, _dopp_noise_amp (GnssUpdate.h)                      */
+  double* unit;              /* out B x S x 3  receiver->satellite unit vectors (= -J[:, 0:3])                   */
+  double* res_pos;           /* out B x S                                                                       */
+  double* res_vel;           /* out B x S                                                                       */
+  double* sigma_psr;         /* out B x S                                                                       */
+  double* sigma_dopp;        /* out B x S                                                                       */
+  double* azel;              /* out B x S x 2, optional                                                         */
+  double* atmos;             /* out B x S x 2 (ionosphere, troposphere delay [m]), optional                     */
+} igv_gnss_res_args;
+igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a);
+
 /* ---- delayed initialisation / linear replacement ------------------------------------------------
  * StateManager::addVariableDelayed (StateManager.cpp:547-630, with :462-541): new 1-dim variable.
  * H_old: B x (rows x n_old) col-major (ld = rows), H_new: B x rows, res: B x rows.

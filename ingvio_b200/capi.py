@@ -58,6 +58,14 @@ class igv_gnss_args(C.Structure):
                 ("strong_reject", C.c_int), ("dx_out", C.c_void_p)]
 
 
+class igv_gnss_res_args(C.Structure):
+    _fields_ = [("n_sats", C.c_int), ("sat_pos", C.c_void_p), ("sat_vel", C.c_void_p), ("sat_clk", C.c_void_p),
+                ("obs", C.c_void_p), ("obs_std", C.c_void_p), ("ttx", C.c_void_p), ("sys", C.c_void_p),
+                ("T_enu2ecef", C.c_void_p), ("iono", C.c_void_p), ("psr_noise_amp", C.c_double),
+                ("dopp_noise_amp", C.c_double), ("unit", C.c_void_p), ("res_pos", C.c_void_p), ("res_vel", C.c_void_p),
+                ("sigma_psr", C.c_void_p), ("sigma_dopp", C.c_void_p), ("azel", C.c_void_p), ("atmos", C.c_void_p)]
+
+
 # every symbol include/ingvio_b200.h declares: (restype, argtypes)
 _H = C.c_void_p
 _VP = C.c_void_p
@@ -102,6 +110,7 @@ SIGNATURES = {
     "igv_box_plus": (C.c_int, [_H, _VP]),
     "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
     "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
+    "igv_gnss_residuals": (C.c_int, [_H, C.POINTER(igv_gnss_res_args)]),
     "igv_triangulate": (C.c_int, [_H, C.POINTER(igv_tri_args)]),
     "igv_add_variable_delayed": (C.c_int, [_H, C.c_int, _VP, C.c_int, c_ip, c_ip, C.c_int, _VP, _VP, _VP,
                                            C.c_double, C.c_double, C.c_int, C.c_double, _VP, _VP]),

@@ -658,6 +658,48 @@ igv_status igv_triangulate(igv_batch* h, const igv_tri_args* a) {
   return IGV_OK;
 }
 
+// ---- GNSS residual generator (gnss_comm::psr_res / dopp_res) ------------------------------------------------
+igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a) {
+  if (!h || !a) return IGV_ERR_INVALID;
+  if (a->n_sats < 0 || a->n_sats > h->cfg.max_sats) return fail(h, IGV_ERR_CAPACITY, "n_sats exceeds max_sats");
+  if (a->n_sats == 0) return IGV_OK;
+  if (!a->sat_pos || !a->sat_vel || !a->sat_clk || !a->obs || !a->obs_std || !a->ttx || !a->sys || !a->T_enu2ecef ||
+      !a->unit || !a->res_pos || !a->res_vel || !a->sigma_psr || !a->sigma_dopp)
+    return IGV_ERR_INVALID;
+  arena_reset(h);
+  const size_t B = h->B, S = a->n_sats;
+  IgvGnssResLaunch g{};
+  g.S = a->n_sats; g.psr_amp = a->psr_noise_amp; g.dopp_amp = a->dopp_noise_amp;
+  IGV_TRY(stage(h, a->sat_pos, B * S * 3, &g.sat_pos));
+  IGV_TRY(stage(h, a->sat_vel, B * S * 3, &g.sat_vel));
+  IGV_TRY(stage(h, a->sat_clk, B * S * 3, &g.sat_clk));
+  IGV_TRY(stage(h, a->obs, B * S * 3, &g.obs));
+  IGV_TRY(stage(h, a->obs_std, B * S * 3, &g.obs_std));
+  IGV_TRY(stage(h, a->ttx, B * S * 2, &g.ttx));
+  IGV_TRY(stage(h, a->sys, B * S, &g.sys));
+  IGV_TRY(stage(h, a->T_enu2ecef, B * 12, &g.T));
+  IGV_TRY(stage(h, a->iono, B * 8, &g.iono));
+  IGV_TRY(out_buf(h, a->unit, B * S * 3, &g.unit));
+  IGV_TRY(out_buf(h, a->res_pos, B * S, &g.res_pos));
+  IGV_TRY(out_buf(h, a->res_vel, B * S, &g.res_vel));
+  IGV_TRY(out_buf(h, a->sigma_psr, B * S, &g.sig_psr));
+  IGV_TRY(out_buf(h, a->sigma_dopp, B * S, &g.sig_dopp));
+  IGV_TRY(out_buf(h, a->azel, B * S * 2, &g.azel));
+  IGV_TRY(out_buf(h, a->atmos, B * S * 2, &g.atmos));
+  igv_launch_gnss_residuals(h, g);
+  IGV_TRY(check_launch(h));
+  if (h->ptr_mode == IGV_PTR_HOST) {
+    auto back = [&](double* user, const double* dev, size_t n) {
+      if (user) cudaMemcpyAsync(user, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    };
+    back(a->unit, g.unit, B * S * 3); back(a->res_pos, g.res_pos, B * S); back(a->res_vel, g.res_vel, B * S);
+    back(a->sigma_psr, g.sig_psr, B * S); back(a->sigma_dopp, g.sig_dopp, B * S);
+    back(a->azel, g.azel, B * S * 2); back(a->atmos, g.atmos, B * S * 2);
+    IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return IGV_OK;
+}
+
 // ---- fused GNSS update --------------------------------------------------------------------------------
 igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
   if (!h || !a) return IGV_ERR_INVALID;

@@ -184,6 +184,15 @@ struct IgvGnssLaunch {
 };
 void igv_launch_gnss_rows(igv_batch* h, const IgvGnssLaunch& a);
 
+struct IgvGnssResLaunch {
+  int S;
+  const double* sat_pos; const double* sat_vel; const double* sat_clk; const double* obs; const double* obs_std;
+  const double* ttx; const int* sys; const double* T; const double* iono;
+  double psr_amp, dopp_amp;
+  double* unit; double* res_pos; double* res_vel; double* sig_psr; double* sig_dopp; double* azel; double* atmos;
+};
+void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l);
+
 void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
                              const double* res, double noise_iso, double chi2_mult, int do_chi2,
                              double prior_cov, int* accepted_dev);

@@ -221,3 +221,63 @@ class SyntheticStream:
         return FramePacket(t=t1, gyro=gyro, accel=accel, dt=dt, pf_w=pf_w, anchor_slot=anchor, obs=obs,
                            obs_mask=mask, obs_total=mask.sum(-1).astype(np.int32), visual_mode=mode,
                            selected_slots=[], marg_slots=marg, max_valid=F, gnss=gn)
+
+
+# ------------------------------------------------------------------------------------------------
+# Raw GNSS epochs (the inputs of igv_gnss_residuals = the outputs of gnss_comm::sat_states + raw L1 observations)
+# ------------------------------------------------------------------------------------------------
+KLOBUCHAR = np.array([0.1118e-7, -0.7451e-8, -0.5961e-7, 0.1192e-6, 0.1167e6, -0.2294e6, -0.1311e6, 0.1049e7])
+L1_FREQ = {0: 1575.42e6, 1: 1602.0e6, 2: 1575.42e6, 3: 1561.098e6}   # GPS, GLO (channel 0), GAL, BDS
+
+
+def geo2ecef(lat_deg, lon_deg, h):
+    a, e2 = 6378137.0, 6.69437999014e-3
+    la, lo = np.deg2rad(lat_deg), np.deg2rad(lon_deg)
+    N = a / np.sqrt(1 - e2 * np.sin(la) ** 2)
+    return np.array([(N + h) * np.cos(la) * np.cos(lo), (N + h) * np.cos(la) * np.sin(lo), (N * (1 - e2) + h) * np.sin(la)])
+
+
+def enu2ecef_rotation(lat_deg, lon_deg):
+    la, lo = np.deg2rad(lat_deg), np.deg2rad(lon_deg)
+    sl, cl, so, co = np.sin(la), np.cos(la), np.sin(lo), np.cos(lo)
+    return np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0.0, cl, sl]])
+
+
+def raw_gnss_epoch(rng, rcv_ecef, rcv_vel_ecef, clock_bias4, clock_drift, S, lat_deg, lon_deg, el_range=(10.0, 85.0),
+                   no_l1=(), below_horizon=()):
+    """One synthetic raw epoch for B receivers (rcv_ecef (B,3), rcv_vel_ecef (B,3), clock_bias4 (B,4), clock_drift (B,)):
+    satellites on a 26 560 km shell at random azimuth / elevation, orbital speed 3.9 km/s, small clock terms, and
+    pseudo-ranges / Dopplers consistent with the receiver up to ~10 m of unmodelled delay + noise. `no_l1` lists
+    satellite indices without an L1 observation (freq = -1), `below_horizon` indices placed under the horizon."""
+    c = 2.99792458e8
+    B = rcv_ecef.shape[0]
+    Re = enu2ecef_rotation(lat_deg, lon_deg)
+    az = rng.uniform(0, 2 * np.pi, (B, S))
+    el = np.deg2rad(rng.uniform(el_range[0], el_range[1], (B, S)))
+    for i in below_horizon:
+        el[:, i] = np.deg2rad(-5.0)
+    enu = np.stack([np.cos(el) * np.sin(az), np.cos(el) * np.cos(az), np.sin(el)], -1)
+    u = np.einsum("ij,bsj->bsi", Re, enu)
+    r0 = np.linalg.norm(rcv_ecef, axis=-1)[:, None]
+    ru = np.einsum("bi,bsi->bs", rcv_ecef, u)
+    rho = -ru + np.sqrt(ru * ru + 26.56e6 ** 2 - r0 * r0)
+    pos = rcv_ecef[:, None, :] + rho[..., None] * u
+    t = rng.standard_normal((B, S, 3))
+    t -= np.einsum("bsi,bsi->bs", t, pos)[..., None] * pos / np.einsum("bsi,bsi->bs", pos, pos)[..., None]
+    vel = 3.9e3 * t / np.linalg.norm(t, axis=-1, keepdims=True)
+    sys = np.tile((np.arange(S) % 4).astype(np.int32), (B, 1))
+    freq = np.vectorize(L1_FREQ.get)(sys).astype(np.float64)
+    sdt = rng.normal(0, 1e-4, (B, S))
+    sddt = rng.normal(0, 1e-11, (B, S))
+    tgd = rng.normal(0, 1e-8, (B, S))
+    cb = np.take_along_axis(clock_bias4, sys.astype(np.int64), axis=1)
+    psr = rho + cb - sdt * c + tgd * c + rng.uniform(4.0, 12.0, (B, S)) + rng.normal(0, 1.0, (B, S))
+    rate = np.einsum("bsi,bsi->bs", vel - rcv_vel_ecef[:, None, :], u) + clock_drift[:, None] - sddt * c
+    dopp = -(rate + rng.normal(0, 0.1, (B, S))) * freq / c
+    for i in no_l1:
+        freq[:, i] = -1.0
+    obs = np.stack([psr, dopp, freq], -1)
+    obs_std = np.stack([np.full((B, S), 2.0), np.full((B, S), 1.0), np.full((B, S), 1.0)], -1)
+    ttx = np.stack([rng.uniform(1.0, 366.0, (B, S)), rng.uniform(0.0, 604800.0, (B, S))], -1)
+    return dict(sat_pos=pos, sat_vel=vel, sat_clk=np.stack([sdt, sddt, tgd], -1), obs=obs, obs_std=obs_std, ttx=ttx,
+                sys=sys, iono=np.tile(KLOBUCHAR, (B, 1)))

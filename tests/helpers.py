@@ -49,11 +49,11 @@ def cov_diag21(fp):
                     [sp.init_cov_ba] * 3 + [sp.init_cov_ext_rot] * 3 + [sp.init_cov_ext_pos] * 3) ** 2.0
 
 
-def make_gpu(wl, stream, fp, with_gnss=True, max_feats=None, max_clones=None):
+def make_gpu(wl, stream, fp, with_gnss=True, max_feats=None, max_clones=None, max_sats=None):
     from ingvio_b200.filter import BatchFilter
     sp = o.StateParams(fp)
     B = stream.B
-    g = BatchFilter(B, max_clones or wl.sw, max_feats or max(wl.feats, 1), max(wl.sats, 1), stereo=wl.stereo,
+    g = BatchFilter(B, max_clones or wl.sw, max_feats or max(wl.feats, 1), max_sats or max(wl.sats, 1), stereo=wl.stereo,
                     noise=dict(noise_g=sp.noise_g, noise_a=sp.noise_a, noise_bg=sp.noise_bg, noise_ba=sp.noise_ba,
                                noise_clockbias=sp.noise_clockbias, noise_cb_rw=sp.noise_cb_rw),
                     gravity=(0.0, 0.0, -fp.gravity_norm), T_cl2cr=(fp.T_cl2cr_R, fp.T_cl2cr_p),
