@@ -269,6 +269,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the CUDA path is the product; no CPU fallback)"
     torch.cuda.set_device(local)

@@ -49,6 +49,17 @@ igv_status arena_reserve(igv_batch* h, size_t bytes, char** out) {
     s.mem = n;
     s.cap = ncap;
     s.off = 0;
+    // bring every other slot to the new capacity NOW (their old blocks are retired, so work in flight on them
+    // stays valid): all allocation happens inside the first large call instead of trickling into later frames
+    for (auto& o : h->slots) {
+      if (&o == &s || o.cap >= ncap) continue;
+      char* m = nullptr;
+      if (cudaMalloc(&m, ncap) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (o.mem) h->retired.push_back(o.mem);
+      o.mem = m;
+      o.cap = ncap;
+      // `off` is untouched: a slot is only ever bumped by the call that owns it, after arena_reset zeroed it
+    }
   }
   *out = s.mem + s.off;
   s.off += bytes;

@@ -99,11 +99,13 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
   double* S_acc = wsbase + (size_t)nwarps * a.per_warp;          // [(ncl+1) anchors][ncl][27]
   double2* Gt = reinterpret_cast<double2*>(                                                     // [ntt][32], 16-byte aligned
       (reinterpret_cast<uintptr_t>(S_acc + (size_t)(ncl + 1) * ncl * 27) + 15) & ~static_cast<uintptr_t>(15));
-  int* flag_s = reinterpret_cast<int*>(Gt + (size_t)ntt * 32);   // [16]
+  double* zero_row = reinterpret_cast<double*>(Gt + (size_t)ntt * 32);   // [ldz] zeros (masked rows of the Z fold)
+  int* flag_s = reinterpret_cast<int*>(zero_row + a.ldz);        // [16]
   int* tile_cc = flag_s + 16;                                    // [ntt] tile -> (column tile i) | (column tile j) << 8
   if (FUSE) {
     for (int t = threadIdx.x; t < (ncl + 1) * ncl * 27; t += blockDim.x) S_acc[t] = 0.0;
     for (int t = threadIdx.x; t < ntt * 32; t += blockDim.x) Gt[t] = make_double2(0.0, 0.0);
+    for (int t = threadIdx.x; t < a.ldz; t += blockDim.x) zero_row[t] = 0.0;
     for (int t = threadIdx.x; t < ntt; t += blockDim.x) {
       int ci = 0, rem = t;
       while (rem >= a.nt - ci) { rem -= a.nt - ci; ++ci; }
@@ -683,7 +685,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
       // warps whose track enters the update: accepted by the gate and inside the max_valid cap (in track order)
       const unsigned accm = __ballot_sync(0xffffffffu, lane < nwarps && flag_s[lane < nwarps ? lane : 0] != 0);
       unsigned onmask = accm;
-      if (a.max_valid > 0) {
+      if (a.max_valid > 0 && a.max_valid - acc_count < __popc(accm)) {   // the cap cuts into this round
         onmask = 0;
         unsigned mm = accm;
         for (int left = a.max_valid - acc_count; mm && left > 0; --left) { onmask |= mm & (0u - mm); mm &= mm - 1; }
@@ -709,13 +711,11 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
           const int r = k0 + fk, w = (r * 43) >> 7, p = r - 3 * w;   // w = r / 3 for r < 64
           const bool on = r < nrows && ((onmask >> w) & 1u);
           if (!__any_sync(0xffffffffu, on)) continue;
-          const double* zp = wsbase + (size_t)(on ? w : 0) * a.per_warp + zoff + p * a.ldz;
+          // masked rows read a row of zeros instead of being selected away after the load
+          const double* zp = on ? wsbase + (size_t)w * a.per_warp + zoff + p * a.ldz : zero_row;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (warp + u * nwarps < ntt) {
-              const double za = zp[ci8[u]], zb = zp[cj8[u]];
-              mma884(g[u].x, g[u].y, on ? za : 0.0, on ? zb : 0.0);
-            }
+            if (warp + u * nwarps < ntt) mma884(g[u].x, g[u].y, zp[ci8[u]], zp[cj8[u]]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -852,7 +852,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
       const int ntt = a.nt * (a.nt + 1) / 2;
       const int ssz = max(a.ssz, 3 * a.ldz + ncl * 27);
       const int pw = feat_per_warp(a.Mmax, ssz);
-      const size_t extra = (size_t)(ncl + 1) * ncl * 27 + 2 + (size_t)ntt * 64 + 8 + (ntt + 1) / 2;
+      const size_t extra = (size_t)(ncl + 1) * ncl * 27 + 2 + (size_t)ntt * 64 + a.ldz + 8 + (ntt + 1) / 2;
       int W = 16;
       while (W > 1 && sizeof(double) * (fixed + (size_t)W * pw + extra) > 222 * 1024) --W;
       const bool room = (size_t)W * pw >= (size_t)(n + 1) * ((n + 1) | 1);   // G is assembled over the per-warp regions

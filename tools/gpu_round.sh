@@ -28,7 +28,7 @@ NCU="ncu --clock-control none"
 BARGS="bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency"
 timeout 600 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/${TAG}_launches.csv python $BARGS > $OUT/${TAG}_ncu_launch.log 2>&1
 if [ "$FULL" = "full" ]; then
-  for K in k_msckf_features k_ekf_update k_gram_factor k_propagate k_imu_mean; do
+  for K in k_msckf_features k_ekf_update; do
     timeout 400 $NCU --set full --import-source on -k regex:$K -s 14 -c 2 -f -o $OUT/${TAG}_$K python $BARGS > $OUT/${TAG}_ncu_$K.log 2>&1
     ncu -i $OUT/${TAG}_$K.ncu-rep --page raw --csv > $OUT/${TAG}_${K}_raw.csv 2>/dev/null
   done
