@@ -275,6 +275,31 @@ typedef struct {
 } igv_gnss_res_args;
 igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a);
 
+/* ---- ephemeris -> satellite state -------------------------------------------------------------------------------
+ * gnss_comm::sat_states (gnss_comm/src/gnss_spp.cpp:50-97): signal transmit time from the pseudo-range, satellite
+ * clock (eph2svdt / geph2svdt), position and velocity (eph2pos, eph2vel: Kepler orbit with harmonic corrections, BDS
+ * GEO rotation; geph2pos / geph2vel: RK4 of the GLONASS force model), gnss_comm/src/gnss_utility.cpp:390-733.
+ * Times are seconds relative to the ephemeris epoch toe (time_diff(t, toe)); calendar types stay on the host.
+ * One ephemeris record of IGV_EPH_STRIDE doubles per satellite:
+ *   Kepler (GPS, GAL, BDS): A, e, i0, OMG0, omg, M0, delta_n, OMG_dot, i_dot, cuc, cus, crc, crs, cic, cis, af0, af1,
+ *     af2, toe_tow (BDS: time2bdt(toe - 14 s)), tgd[0], time_diff(toe, toc), prn, 0, 0
+ *   GLONASS: pos[3], vel[3], acc[3], tau_n, gamma, 0...
+ * Outputs have the layout igv_gnss_residuals consumes (sat_pos, sat_vel, sat_clk = dt, ddt, tgd); ttx_rel (optional,
+ * B x S) is time_diff(transmit time, toe), from which the caller derives day-of-year / seconds-of-week. */
+#define IGV_EPH_STRIDE 24
+typedef struct {
+  int n_sats;
+  const double* eph;         /* B x S x IGV_EPH_STRIDE                                                           */
+  const double* t_obs_rel;   /* B x S  time_diff(obs->time, toe)                                                 */
+  const double* psr;         /* B x S  L1 pseudo-range [m]; <= 0: no L1 observation, the state stays zero        */
+  const int* sys;            /* B x S  IGV_GNSS_GPS..BDS                                                         */
+  double* sat_pos;           /* out B x S x 3 */
+  double* sat_vel;           /* out B x S x 3 */
+  double* sat_clk;           /* out B x S x 3 */
+  double* ttx_rel;           /* out B x S, optional */
+} igv_sat_state_args;
+igv_status igv_sat_states(igv_batch* h, const igv_sat_state_args* a);
+
 /* ---- delayed initialisation / linear replacement ------------------------------------------------
  * StateManager::addVariableDelayed (StateManager.cpp:547-630, with :462-541): new 1-dim variable.
  * H_old: B x (rows x n_old) col-major (ld = rows), H_new: B x rows, res: B x rows.

@@ -66,6 +66,14 @@ class igv_gnss_res_args(C.Structure):
                 ("sigma_psr", C.c_void_p), ("sigma_dopp", C.c_void_p), ("azel", C.c_void_p), ("atmos", C.c_void_p)]
 
 
+class igv_sat_state_args(C.Structure):
+    _fields_ = [("n_sats", C.c_int), ("eph", C.c_void_p), ("t_obs_rel", C.c_void_p), ("psr", C.c_void_p),
+                ("sys", C.c_void_p), ("sat_pos", C.c_void_p), ("sat_vel", C.c_void_p), ("sat_clk", C.c_void_p),
+                ("ttx_rel", C.c_void_p)]
+
+
+EPH_STRIDE = 24
+
 # every symbol include/ingvio_b200.h declares: (restype, argtypes)
 _H = C.c_void_p
 _VP = C.c_void_p
@@ -111,6 +119,7 @@ SIGNATURES = {
     "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
     "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
     "igv_gnss_residuals": (C.c_int, [_H, C.POINTER(igv_gnss_res_args)]),
+    "igv_sat_states": (C.c_int, [_H, C.POINTER(igv_sat_state_args)]),
     "igv_triangulate": (C.c_int, [_H, C.POINTER(igv_tri_args)]),
     "igv_add_variable_delayed": (C.c_int, [_H, C.c_int, _VP, C.c_int, c_ip, c_ip, C.c_int, _VP, _VP, _VP,
                                            C.c_double, C.c_double, C.c_int, C.c_double, _VP, _VP]),

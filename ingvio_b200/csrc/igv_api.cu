@@ -711,6 +711,38 @@ igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a) {
   return IGV_OK;
 }
 
+// ---- ephemeris -> satellite states (gnss_comm::sat_states) ------------------------------------------------------
+igv_status igv_sat_states(igv_batch* h, const igv_sat_state_args* a) {
+  if (!h || !a) return IGV_ERR_INVALID;
+  if (a->n_sats < 0 || a->n_sats > h->cfg.max_sats) return fail(h, IGV_ERR_CAPACITY, "n_sats exceeds max_sats");
+  if (a->n_sats == 0) return IGV_OK;
+  if (!a->eph || !a->t_obs_rel || !a->psr || !a->sys || !a->sat_pos || !a->sat_vel || !a->sat_clk) return IGV_ERR_INVALID;
+  arena_reset(h);
+  const size_t B = h->B, S = a->n_sats;
+  const double *eph, *tob, *psr;
+  const int* sys;
+  IGV_TRY(stage(h, a->eph, B * S * IGV_EPH_STRIDE, &eph));
+  IGV_TRY(stage(h, a->t_obs_rel, B * S, &tob));
+  IGV_TRY(stage(h, a->psr, B * S, &psr));
+  IGV_TRY(stage(h, a->sys, B * S, &sys));
+  double *pos, *vel, *clk, *ttx;
+  IGV_TRY(out_buf(h, a->sat_pos, B * S * 3, &pos));
+  IGV_TRY(out_buf(h, a->sat_vel, B * S * 3, &vel));
+  IGV_TRY(out_buf(h, a->sat_clk, B * S * 3, &clk));
+  IGV_TRY(out_buf(h, a->ttx_rel, B * S, &ttx));
+  igv_launch_sat_states(h, a->n_sats, eph, tob, psr, sys, pos, vel, clk, ttx);
+  IGV_TRY(check_launch(h));
+  if (h->ptr_mode == IGV_PTR_HOST) {
+    auto back = [&](double* user, const double* dev, size_t n) {
+      if (user) cudaMemcpyAsync(user, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    };
+    back(a->sat_pos, pos, B * S * 3); back(a->sat_vel, vel, B * S * 3); back(a->sat_clk, clk, B * S * 3);
+    back(a->ttx_rel, ttx, B * S);
+    IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return IGV_OK;
+}
+
 // ---- fused GNSS update --------------------------------------------------------------------------------
 igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
   if (!h || !a) return IGV_ERR_INVALID;

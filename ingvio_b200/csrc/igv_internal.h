@@ -192,6 +192,8 @@ struct IgvGnssResLaunch {
   double* unit; double* res_pos; double* res_vel; double* sig_psr; double* sig_dopp; double* azel; double* atmos;
 };
 void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l);
+void igv_launch_sat_states(igv_batch* h, int S, const double* eph, const double* t_obs, const double* psr, const int* sys,
+                           double* pos, double* vel, double* clk, double* ttx);
 
 void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
                              const double* res, double noise_iso, double chi2_mult, int do_chi2,

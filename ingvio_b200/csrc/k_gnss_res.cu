@@ -184,6 +184,152 @@ __global__ void __launch_bounds__(128) k_gnss_residuals(ResArgs a) {
   if (a.atmos) { a.atmos[gid * 2] = ion_d; a.atmos[gid * 2 + 1] = tro_d; }
 }
 
+// ---- ephemeris -> satellite state: gnss_comm::sat_states (gnss_spp.cpp:50-97) ---------------------------------
+// One thread per satellite. Broadcast ephemerides: Kepler (GPS / GAL / BDS, eph2svdt :437-446, eph2pos :448-531,
+// eph2vel :533-634, Kepler :390-405 -- which returns the previous iterate) or GLONASS (geph2svdt :684-696, RK4
+// integration glo_orbit / deq :636-682 with TSTEP = 60 s, geph2pos / geph2vel :698-733). Times are seconds relative
+// to the ephemeris epoch toe (the caller's time_diff(obs->time, toe)); field order = IGV_EPH_* of the header.
+constexpr double kMuGps = 3.9860050000e14, kMu = 3.9860044180e14;          // gnss_constant.hpp:210-211
+constexpr double kOmgGlo = 7.2921150000e-5, kOmgBds = 7.2921150000e-5;     // gnss_constant.hpp:207,209
+constexpr double kJ2Glo = 1.0826257E-3, kAGlo = 6378136.0, kTstep = 60.0;  // gnss_constant.hpp:213,206,212
+constexpr double kSinN5 = -0.0871557427476582, kCosN5 = 0.9961946980917456;
+constexpr double kWeek = 604800.0;
+
+struct SatArgs {
+  int B, S;
+  const double* eph; const double* t_obs; const double* psr; const int* sys;
+  double* pos; double* vel; double* clk; double* ttx;
+};
+
+__device__ double kepler(double mk, double es) {
+  double e = mk, ek = 1e6;
+  for (int it = 0; it < 30 && fabs(e - ek) > 1e-14; ++it) {
+    ek = e;
+    e -= (e - es * sin(e) - mk) / (1.0 - es * cos(e));
+  }
+  return ek;   // sic (gnss_utility.cpp:404)
+}
+__device__ double wrap_week(double t) { return t > kWeek / 2 ? t - kWeek : (t < -kWeek / 2 ? t + kWeek : t); }
+
+__device__ void glo_deq(const double* p, const double* v, const double* acc, double* pd, double* vd) {
+  const double r2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+  if (r2 <= 0.0) { for (int i = 0; i < 3; ++i) pd[i] = vd[i] = 0.0; return; }
+  const double r3 = r2 * sqrt(r2), omg2 = kOmgGlo * kOmgGlo;
+  const double a = 1.5 * kJ2Glo * kMu * kAGlo * kAGlo / r2 / r3;
+  const double b = 5.0 * p[2] * p[2] / r2;
+  const double c = -kMu / r3 - a * (1.0 - b);
+  pd[0] = v[0]; pd[1] = v[1]; pd[2] = v[2];
+  vd[0] = (c + omg2) * p[0] + 2.0 * kOmgGlo * v[1] + acc[0];
+  vd[1] = (c + omg2) * p[1] - 2.0 * kOmgGlo * v[0] + acc[1];
+  vd[2] = (c - 2.0 * a) * p[2] + acc[2];
+}
+__device__ void glo_orbit(double dt, double* p, double* v, const double* acc) {
+  double p1[3], p2[3], p3[3], p4[3], v1[3], v2[3], v3[3], v4[3], np_[3], nv[3];
+  glo_deq(p, v, acc, p1, v1);
+  for (int i = 0; i < 3; ++i) { np_[i] = p[i] + 0.5 * p1[i] * dt; nv[i] = v[i] + 0.5 * v1[i] * dt; }
+  glo_deq(np_, nv, acc, p2, v2);
+  for (int i = 0; i < 3; ++i) { np_[i] = p[i] + 0.5 * p2[i] * dt; nv[i] = v[i] + 0.5 * v2[i] * dt; }
+  glo_deq(np_, nv, acc, p3, v3);
+  for (int i = 0; i < 3; ++i) { np_[i] = p[i] + p3[i] * dt; nv[i] = v[i] + v3[i] * dt; }
+  glo_deq(np_, nv, acc, p4, v4);
+  for (int i = 0; i < 3; ++i) {
+    p[i] += (p1[i] + 2.0 * p2[i] + 2.0 * p3[i] + p4[i]) * dt / 6.0;
+    v[i] += (v1[i] + 2.0 * v2[i] + 2.0 * v3[i] + v4[i]) * dt / 6.0;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sat_states(SatArgs a) {
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long)a.B * a.S) return;
+  const double* E = a.eph + gid * IGV_EPH_STRIDE;
+  const int sys = a.sys[gid];
+  const double psr = a.psr[gid];
+  double pos[3] = {0, 0, 0}, vel[3] = {0, 0, 0}, dts = 0.0, ddts = 0.0, tgd = 0.0, tx = 0.0;
+  if (psr > 0.0 && sys >= 0 && sys < 4) {     // no L1 observation: the SatState stays all zero (gnss_spp.cpp:64-66)
+    tx = a.t_obs[gid] - psr / kC;
+    if (sys == IGV_GNSS_GLO) {
+      const double tau_n = E[9], gamma = E[10];
+      double dt = wrap_week(tx);
+      for (int i = 0; i < 2; ++i) dt -= -tau_n + gamma * dt;
+      tx -= -tau_n + gamma * dt;
+      double acc[3] = {E[6], E[7], E[8]};
+      for (int i = 0; i < 3; ++i) { pos[i] = E[i]; vel[i] = E[3 + i]; }
+      dt = tx;
+      dts = -tau_n + gamma * dt;
+      ddts = gamma;
+      for (double tt = dt < 0.0 ? -kTstep : kTstep; fabs(dt) > 1e-9; dt -= tt) {
+        if (fabs(dt) < kTstep) tt = dt;
+        glo_orbit(tt, pos, vel, acc);
+      }
+    } else {
+      const double A = E[0], e = E[1], i0 = E[2], OMG0 = E[3], omg = E[4], M0 = E[5], delta_n = E[6], OMG_dot = E[7],
+                   i_dot = E[8], cuc = E[9], cus = E[10], crc = E[11], crs = E[12], cic = E[13], cis = E[14], af0 = E[15],
+                   af1 = E[16], af2 = E[17], toe_tow = E[18], toe_toc = E[20];
+      const int prn = (int)E[21];
+      tgd = E[19];
+      double dt = tx + toe_toc;
+      for (int i = 0; i < 2; ++i) dt -= af0 + af1 * dt + af2 * dt * dt;
+      tx -= af0 + af1 * dt + af2 * dt * dt;
+      const double tk = wrap_week(tx);
+      const double mu = (sys == IGV_GNSS_GPS) ? kMuGps : kMu;
+      const double omg_e = (sys == IGV_GNSS_BDS) ? kOmgBds : kOmg;
+      const double n = sqrt(mu / (A * A * A)) + delta_n;
+      const double Ek = kepler(M0 + n * tk, e);
+      double sE, cE;
+      sincos(Ek, &sE, &cE);
+      const double Ed = n / (1 - e * cE);
+      const double vd = sqrt(1 - e * e) * Ed / (1 - e * cE);
+      const double vk = atan2(sqrt(1 - e * e) * sE, cE - e);
+      const double phi = vk + omg;
+      double s2, c2;
+      sincos(2 * phi, &s2, &c2);
+      const double dud = 2 * vd * (cus * c2 - cuc * s2), drd = 2 * vd * (crs * c2 - crc * s2),
+                   did = 2 * vd * (cis * c2 - cic * s2);
+      const double ukd = vd + dud, rkd = A * e * Ed * sE + drd, ikd = i_dot + did;
+      const double uk = phi + cus * s2 + cuc * c2;
+      const double rk = A * (1 - e * cE) + crs * s2 + crc * c2;
+      const double ik = i0 + i_dot * tk + cis * s2 + cic * c2;
+      double si, ci, su, cu;
+      sincos(ik, &si, &ci);
+      sincos(uk, &su, &cu);
+      const double xp = rk * cu, yp = rk * su;
+      const double xpd = rkd * cu - rk * ukd * su, ypd = rkd * su + rk * ukd * cu;
+      if (sys == IGV_GNSS_BDS && prn <= 5) {   // BDS GEO
+        const double O = OMG0 + OMG_dot * tk - omg_e * toe_tow;
+        double sO, cO, so, co;
+        sincos(O, &sO, &cO);
+        sincos(omg_e * tk, &so, &co);
+        const double Od = OMG_dot;
+        const double t1 = xpd - yp * Od * ci, t2 = xp * Od + ypd * ci - yp * ikd * si;
+        const double xg = xp * cO - yp * ci * sO, yg = xp * sO + yp * ci * cO, zg = yp * si;
+        const double xgd = t1 * cO - t2 * sO, ygd = t1 * sO + t2 * cO, zgd = ypd * si + ypd * ikd * ci;
+        const double sod = omg_e * co, cod = -omg_e * so;
+        pos[0] = xg * co + yg * so * kCosN5 + zg * so * kSinN5;
+        pos[1] = -xg * so + yg * co * kCosN5 + zg * co * kSinN5;
+        pos[2] = -yg * kSinN5 + zg * kCosN5;
+        vel[0] = xgd * co + xg * cod + ygd * so * kCosN5 + yg * sod * kCosN5 + zgd * so * kSinN5 + zg * sod * kSinN5;
+        vel[1] = -xgd * so - xg * sod + ygd * co * kCosN5 + yg * cod * kCosN5 + zgd * co * kSinN5 + zg * cod * kSinN5;
+        vel[2] = -ygd * kSinN5 + zgd * kCosN5;
+      } else {
+        const double O = OMG0 + (OMG_dot - omg_e) * tk - omg_e * toe_tow;
+        double sO, cO;
+        sincos(O, &sO, &cO);
+        const double Od = OMG_dot - omg_e;
+        const double t1 = xpd - yp * Od * ci, t2 = xp * Od + ypd * ci - yp * ikd * si;
+        pos[0] = xp * cO - yp * ci * sO; pos[1] = xp * sO + yp * ci * cO; pos[2] = yp * si;
+        vel[0] = t1 * cO - t2 * sO; vel[1] = t1 * sO + t2 * cO;
+        vel[2] = ypd * si + ypd * ikd * ci;   // as the reference writes it (gnss_utility.cpp:624)
+      }
+      const double dtc = tx + toe_toc;
+      dts = af0 + af1 * dtc + af2 * dtc * dtc - 2.0 * sqrt(mu * A) * e * sE / kC / kC;
+      ddts = af1 + 2.0 * af2 * dtc - 2.0 * sqrt(mu * A) * e * cE * Ed / kC / kC;
+    }
+  }
+  for (int i = 0; i < 3; ++i) { a.pos[gid * 3 + i] = pos[i]; a.vel[gid * 3 + i] = vel[i]; }
+  a.clk[gid * 3] = dts; a.clk[gid * 3 + 1] = ddts; a.clk[gid * 3 + 2] = tgd;
+  if (a.ttx) a.ttx[gid] = tx;
+}
+
 }  // namespace
 
 void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l) {
@@ -198,5 +344,16 @@ void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l) {
   a.azel = l.azel; a.atmos = l.atmos;
   const long n = (long)h->B * l.S;
   k_gnss_residuals<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
+  h->launches++;
+}
+
+void igv_launch_sat_states(igv_batch* h, int S, const double* eph, const double* t_obs, const double* psr, const int* sys,
+                           double* pos, double* vel, double* clk, double* ttx) {
+  IgvProfScope prof_scope_(h, IGV_K_GNSS_ROWS);
+  SatArgs a;
+  a.B = h->B; a.S = S; a.eph = eph; a.t_obs = t_obs; a.psr = psr; a.sys = sys;
+  a.pos = pos; a.vel = vel; a.clk = clk; a.ttx = ttx;
+  const long n = (long)h->B * S;
+  k_sat_states<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
   h->launches++;
 }

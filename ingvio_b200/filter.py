@@ -402,6 +402,26 @@ class BatchFilter:
         self._ck(self.lib.igv_gnss_update(self.h, C.byref(args)))
         return dx
 
+    def sat_states(self, eph, t_obs_rel, psr, sys, out=None):
+        """gnss_comm::sat_states: ephemeris records (B,S,24) + observation time relative to toe + L1 pseudo-range ->
+        dict(sat_pos, sat_vel, sat_clk, ttx_rel). Host arrays in, numpy out; device tensors need `out`."""
+        a = [_Arg(eph, np.float64), _Arg(t_obs_rel, np.float64), _Arg(psr, np.float64), _Arg(sys, np.int32)]
+        mode = self._set_mode(a)
+        S = int(a[3].keep.shape[1])
+        shapes = dict(sat_pos=(self.B, S, 3), sat_vel=(self.B, S, 3), sat_clk=(self.B, S, 3), ttx_rel=(self.B, S))
+        if mode == capi.IGV_PTR_HOST:
+            out = {k: np.zeros(v) for k, v in shapes.items()}
+        else:
+            assert out is not None and all(k in out for k in shapes), "device mode needs preallocated outputs"
+        o = {k: _Arg(out[k], np.float64) for k in shapes}
+        args = capi.igv_sat_state_args()
+        args.n_sats = S
+        args.eph, args.t_obs_rel, args.psr, args.sys = [x.ptr for x in a]
+        for k in shapes:
+            setattr(args, k, o[k].ptr)
+        self._ck(self.lib.igv_sat_states(self.h, C.byref(args)))
+        return out
+
     def gnss_residuals(self, sat_pos, sat_vel, sat_clk, obs, obs_std, ttx, sys, T_enu2ecef, iono=None, psr_amp=1.0,
                        dopp_amp=1.0, out=None):
         """gnss_comm::psr_res / dopp_res (+ az/el, delays, sigmas) at the filter's receiver state; returns a dict

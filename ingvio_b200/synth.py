@@ -281,3 +281,37 @@ def raw_gnss_epoch(rng, rcv_ecef, rcv_vel_ecef, clock_bias4, clock_drift, S, lat
     ttx = np.stack([rng.uniform(1.0, 366.0, (B, S)), rng.uniform(0.0, 604800.0, (B, S))], -1)
     return dict(sat_pos=pos, sat_vel=vel, sat_clk=np.stack([sdt, sddt, tgd], -1), obs=obs, obs_std=obs_std, ttx=ttx,
                 sys=sys, iono=np.tile(KLOBUCHAR, (B, 1)))
+
+
+def random_ephemerides(rng, B, S, geo=()):
+    """Plausible broadcast ephemerides in the IGV_EPH_* record layout (B,S,24) for constellations sys = i % 4
+    (GPS, GLO, GAL, BDS); indices in `geo` become BDS GEO satellites (prn <= 5). GLONASS records carry a state on a
+    25 500 km orbit. Returns (eph, sys, t_obs_rel, psr)."""
+    eph = np.zeros((B, S, 24))
+    sys = np.tile((np.arange(S) % 4).astype(np.int32), (B, 1))
+    for i in geo:
+        sys[:, i] = 3
+    for b in range(B):
+        for i in range(S):
+            k = sys[b, i]
+            if k == 1:
+                r = 25.5e6
+                u = rng.standard_normal(3); u /= np.linalg.norm(u)
+                t = np.cross(u, rng.standard_normal(3)); t /= np.linalg.norm(t)
+                eph[b, i, 0:3] = r * u
+                eph[b, i, 3:6] = 3.95e3 * t - 7.292115e-5 * np.cross([0, 0, 1.0], r * u)   # ECEF (rotating frame) velocity
+                eph[b, i, 6:9] = rng.normal(0, 1e-6, 3)
+                eph[b, i, 9] = rng.normal(0, 1e-4)      # tau_n
+                eph[b, i, 10] = rng.normal(0, 1e-11)    # gamma
+            else:
+                is_geo = i in geo
+                A = 42.164e6 if is_geo else rng.uniform(26.4e6, 29.7e6)
+                eph[b, i, :22] = [A, rng.uniform(1e-4, 0.02), 0.09 if is_geo else rng.uniform(0.93, 0.99),
+                                  rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-3, 3), rng.normal(0, 4e-9),
+                                  rng.normal(-8e-9, 1e-9), rng.normal(0, 3e-10), rng.normal(0, 2e-6), rng.normal(0, 5e-6),
+                                  rng.normal(200, 80), rng.normal(0, 60), rng.normal(0, 1e-7), rng.normal(0, 1e-7),
+                                  rng.normal(0, 2e-4), rng.normal(0, 1e-11), 0.0, rng.uniform(0, 604800.0),
+                                  rng.normal(0, 8e-9), rng.choice([0.0, 16.0, -7200.0]), 3 if is_geo else rng.integers(6, 30)]
+    t_obs = rng.uniform(-3600.0, 3600.0, (B, S))
+    psr = rng.uniform(2.0e7, 2.6e7, (B, S))
+    return eph, sys, t_obs, psr

@@ -8,8 +8,9 @@ TEST INFRASTRUCTURE (oracle). CPU restatement of the vendored HKUST library
 receiver state assembly of /root/reference/ingvio_estimator/src/GnssUpdate.cpp:101-111 and the noise model
 of :177-186, :246-255.
 
-Boundary. Inputs enter AFTER gnss_comm::sat_states (ephemeris -> satellite position / velocity / clock,
-gnss_spp.cpp:50-97) and after the calendar bookkeeping of gtime_t: per satellite the caller supplies the signal
+Boundary. psr_res / dopp_res take the outputs of gnss_comm::sat_states (ephemeris -> satellite position / velocity /
+clock, gnss_spp.cpp:50-97, restated at the end of this module with eph2pos / eph2vel / geph2pos of
+gnss_utility.cpp:390-733) and sit after the calendar bookkeeping of gtime_t: per satellite the caller supplies the signal
 transmit time as day-of-year (time2doy, gnss_utility.cpp:299-306) and GPS seconds of week (time2gpst, :165-173).
 The L1 selection (L1_freq, :933-962) is the caller's too: `freq` <= 0 marks "no L1 observation", which leaves the
 satellite's rows zero exactly as the `continue` statements of the reference do.
@@ -48,7 +49,7 @@ def ecef2geo(xyz):
     b2 = a2 * (1 - e2)
     b = math.sqrt(b2)
     ep2 = (a2 - b2) / b2
-    p = math.hypot(x, y) if False else math.sqrt(x * x + y * y)
+    p = math.sqrt(x * x + y * y)
     s1, s2 = z * a, p * b
     h = math.sqrt(s1 * s1 + s2 * s2)
     sin_theta, cos_theta = s1 / h, s2 / h
@@ -245,3 +246,213 @@ def epoch_residuals(p_w, v_w, yof, clock_bias4, fs, R_enu2ecef, t_enu2ecef, sat,
     sig_dopp = dopp_amp * np.sqrt(sat["ura"] * ndp / (sin_el * sin_el))
     return dict(unit_psr=-Jp[:, :3], unit_dopp=-Jv[:, :3], res_pos=res_pos, res_vel=res_vel, sigma_psr=sig_psr,
                 sigma_dopp=sig_dopp, azel=azel, atmos=atmos)
+
+
+# ---- ephemeris -> satellite state (gnss_comm::sat_states, gnss_spp.cpp:50-97) ---------------------------------
+# Times are carried as seconds RELATIVE TO THE EPHEMERIS REFERENCE EPOCH toe (time_diff(t, toe), exact in double for
+# the few hours an ephemeris is valid); gtime_t calendar arithmetic stays with the caller.
+MU_GPS = 3.9860050000e14            # gnss_constant.hpp:210
+MU = 3.9860044180e14                # gnss_constant.hpp:211
+EARTH_OMG_GLO = 7.2921150000e-5     # gnss_constant.hpp:207
+EARTH_OMG_BDS = 7.2921150000e-5     # gnss_constant.hpp:209
+TSTEP = 60.0                        # gnss_constant.hpp:212
+J2_GLO = 1.0826257E-3               # gnss_constant.hpp:213
+EARTH_SEMI_MAJOR_GLO = 6378136.0    # gnss_constant.hpp:206
+WEEK_SECONDS = 604800               # gnss_constant.hpp:217
+SIN_N5, COS_N5 = -0.0871557427476582, 0.9961946980917456   # gnss_constant.hpp:226-227
+SYS_GPS, SYS_GLO, SYS_GAL, SYS_BDS = 0, 1, 2, 3             # sys2idx numbering (gnss_constant.hpp:264-270)
+KEPLER_FIELDS = ("A", "e", "i0", "OMG0", "omg", "M0", "delta_n", "OMG_dot", "i_dot", "cuc", "cus", "crc", "crs", "cic",
+                 "cis", "af0", "af1", "af2", "toe_tow", "tgd", "toe_minus_toc", "prn")
+GLO_FIELDS = ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "tau_n", "gamma")
+
+
+def kepler(mk, es):
+    """gnss_utility.cpp:390-405 -- note that the reference returns the PREVIOUS iterate `ek`."""
+    e, ek, it = mk, 1e6, 0
+    while it < 30 and abs(e - ek) > 1e-14:
+        ek = e
+        e -= (e - es * math.sin(e) - mk) / (1.0 - es * math.cos(e))
+        it += 1
+    return ek
+
+
+def _wrap_week(t):
+    if t > WEEK_SECONDS / 2:
+        return t - WEEK_SECONDS
+    if t < -WEEK_SECONDS / 2:
+        return t + WEEK_SECONDS
+    return t
+
+
+def _mu_omg(sys):
+    if sys == SYS_GPS:
+        return MU_GPS, EARTH_OMG_GPS
+    if sys == SYS_GLO:
+        return MU, EARTH_OMG_GLO
+    if sys == SYS_BDS:
+        return MU, EARTH_OMG_BDS
+    return MU, EARTH_OMG_GPS
+
+
+def eph2svdt(t_rel, eph):
+    """gnss_utility.cpp:437-446; t_rel = time_diff(t, toe)."""
+    dt = t_rel + eph["toe_minus_toc"]
+    for _ in range(2):
+        dt -= eph["af0"] + eph["af1"] * dt + eph["af2"] * dt * dt
+    return eph["af0"] + eph["af1"] * dt + eph["af2"] * dt * dt
+
+
+def _kepler_plane(t_rel, eph, sys):
+    tk = _wrap_week(t_rel)
+    mu, omg_e = _mu_omg(sys)
+    n = math.sqrt(mu / eph["A"] ** 3) + eph["delta_n"]
+    Ek = kepler(eph["M0"] + n * tk, eph["e"])
+    return tk, mu, omg_e, n, Ek
+
+
+def eph2pos(t_rel, eph, sys):
+    """gnss_utility.cpp:448-531 -> (position ECEF, svdt)."""
+    tk, mu, omg_e, n, Ek = _kepler_plane(t_rel, eph, sys)
+    sE, cE = math.sin(Ek), math.cos(Ek)
+    e = eph["e"]
+    vk = math.atan2(math.sqrt(1 - e * e) * sE, cE - e)
+    phi = vk + eph["omg"]
+    c2, s2 = math.cos(2 * phi), math.sin(2 * phi)
+    uk = phi + eph["cus"] * s2 + eph["cuc"] * c2
+    rk = eph["A"] * (1 - e * cE) + eph["crs"] * s2 + eph["crc"] * c2
+    ik = eph["i0"] + eph["i_dot"] * tk + eph["cis"] * s2 + eph["cic"] * c2
+    si, ci = math.sin(ik), math.cos(ik)
+    xp, yp = rk * math.cos(uk), rk * math.sin(uk)
+    if sys == SYS_BDS and eph["prn"] <= 5:      # BDS GEO
+        O = eph["OMG0"] + eph["OMG_dot"] * tk - omg_e * eph["toe_tow"]
+        sO, cO = math.sin(O), math.cos(O)
+        xg, yg, zg = xp * cO - yp * ci * sO, xp * sO + yp * ci * cO, yp * si
+        so, co = math.sin(omg_e * tk), math.cos(omg_e * tk)
+        pos = np.array([xg * co + yg * so * COS_N5 + zg * so * SIN_N5, -xg * so + yg * co * COS_N5 + zg * co * SIN_N5,
+                        -yg * SIN_N5 + zg * COS_N5])
+    else:
+        O = eph["OMG0"] + (eph["OMG_dot"] - omg_e) * tk - omg_e * eph["toe_tow"]
+        sO, cO = math.sin(O), math.cos(O)
+        pos = np.array([xp * cO - yp * ci * sO, xp * sO + yp * ci * cO, yp * si])
+    dt = t_rel + eph["toe_minus_toc"]
+    dts = eph["af0"] + eph["af1"] * dt + eph["af2"] * dt * dt
+    dts -= 2.0 * math.sqrt(mu * eph["A"]) * e * sE / LIGHT_SPEED / LIGHT_SPEED
+    return pos, dts
+
+
+def eph2vel(t_rel, eph, sys):
+    """gnss_utility.cpp:533-634 -> (velocity ECEF, svddt)."""
+    tk, mu, omg_e, n, Ek = _kepler_plane(t_rel, eph, sys)
+    sE, cE = math.sin(Ek), math.cos(Ek)
+    e = eph["e"]
+    Ed = n / (1 - e * cE)
+    vd = math.sqrt(1 - e * e) * Ed / (1 - e * cE)
+    vk = math.atan2(math.sqrt(1 - e * e) * sE, cE - e)
+    phi = vk + eph["omg"]
+    c2, s2 = math.cos(2 * phi), math.sin(2 * phi)
+    dud = 2 * vd * (eph["cus"] * c2 - eph["cuc"] * s2)
+    drd = 2 * vd * (eph["crs"] * c2 - eph["crc"] * s2)
+    did = 2 * vd * (eph["cis"] * c2 - eph["cic"] * s2)
+    ukd, rkd, ikd = vd + dud, eph["A"] * e * Ed * sE + drd, eph["i_dot"] + did
+    uk = phi + eph["cus"] * s2 + eph["cuc"] * c2
+    rk = eph["A"] * (1 - e * cE) + eph["crs"] * s2 + eph["crc"] * c2
+    ik = eph["i0"] + eph["i_dot"] * tk + eph["cis"] * s2 + eph["cic"] * c2
+    si, ci = math.sin(ik), math.cos(ik)
+    su, cu = math.sin(uk), math.cos(uk)
+    xp, yp = rk * cu, rk * su
+    xpd, ypd = rkd * cu - rk * ukd * su, rkd * su + rk * ukd * cu
+    if sys == SYS_BDS and eph["prn"] <= 5:
+        O = eph["OMG0"] + eph["OMG_dot"] * tk - omg_e * eph["toe_tow"]
+        sO, cO = math.sin(O), math.cos(O)
+        Od = eph["OMG_dot"]
+        t1 = xpd - yp * Od * ci
+        t2 = xp * Od + ypd * ci - yp * ikd * si
+        xg, yg, zg = xp * cO - yp * ci * sO, xp * sO + yp * ci * cO, yp * si
+        xgd, ygd = t1 * cO - t2 * sO, t1 * sO + t2 * cO
+        zgd = ypd * si + ypd * ikd * ci          # as the reference writes it (:606)
+        so, co = math.sin(omg_e * tk), math.cos(omg_e * tk)
+        sod, cod = omg_e * co, -omg_e * so
+        vel = np.array([xgd * co + xg * cod + ygd * so * COS_N5 + yg * sod * COS_N5 + zgd * so * SIN_N5 + zg * sod * SIN_N5,
+                        -xgd * so - xg * sod + ygd * co * COS_N5 + yg * cod * COS_N5 + zgd * co * SIN_N5 + zg * cod * SIN_N5,
+                        -ygd * SIN_N5 + zgd * COS_N5])
+    else:
+        O = eph["OMG0"] + (eph["OMG_dot"] - omg_e) * tk - omg_e * eph["toe_tow"]
+        sO, cO = math.sin(O), math.cos(O)
+        Od = eph["OMG_dot"] - omg_e
+        t1 = xpd - yp * Od * ci
+        t2 = xp * Od + ypd * ci - yp * ikd * si
+        vel = np.array([t1 * cO - t2 * sO, t1 * sO + t2 * cO, ypd * si + ypd * ikd * ci])   # z as the reference (:624)
+    dt = t_rel + eph["toe_minus_toc"]
+    ddts = eph["af1"] + 2.0 * eph["af2"] * dt
+    ddts -= 2.0 * math.sqrt(mu * eph["A"]) * e * cE * Ed / LIGHT_SPEED / LIGHT_SPEED
+    return vel, ddts
+
+
+def _glo_deq(pos, vel, acc):
+    """gnss_utility.cpp:636-662."""
+    r2 = float(pos @ pos)
+    if r2 <= 0.0:
+        return np.zeros(3), np.zeros(3)
+    r3 = r2 * math.sqrt(r2)
+    omg2 = EARTH_OMG_GLO * EARTH_OMG_GLO
+    a = 1.5 * J2_GLO * MU * EARTH_SEMI_MAJOR_GLO * EARTH_SEMI_MAJOR_GLO / r2 / r3
+    b = 5.0 * pos[2] * pos[2] / r2
+    c = -MU / r3 - a * (1.0 - b)
+    vd = np.array([(c + omg2) * pos[0] + 2.0 * EARTH_OMG_GLO * vel[1] + acc[0],
+                   (c + omg2) * pos[1] - 2.0 * EARTH_OMG_GLO * vel[0] + acc[1],
+                   (c - 2.0 * a) * pos[2] + acc[2]])
+    return vel.copy(), vd
+
+
+def _glo_orbit(dt, pos, vel, acc):
+    """RK4 step, gnss_utility.cpp:664-682."""
+    p1, v1 = _glo_deq(pos, vel, acc)
+    p2, v2 = _glo_deq(pos + 0.5 * p1 * dt, vel + 0.5 * v1 * dt, acc)
+    p3, v3 = _glo_deq(pos + 0.5 * p2 * dt, vel + 0.5 * v2 * dt, acc)
+    p4, v4 = _glo_deq(pos + p3 * dt, vel + v3 * dt, acc)
+    return pos + (p1 + 2.0 * p2 + 2.0 * p3 + p4) * dt / 6.0, vel + (v1 + 2.0 * v2 + 2.0 * v3 + v4) * dt / 6.0
+
+
+def geph2svdt(t_rel, g):
+    """gnss_utility.cpp:684-696."""
+    dt = _wrap_week(t_rel)
+    for _ in range(2):
+        dt -= -g["tau_n"] + g["gamma"] * dt
+    return -g["tau_n"] + g["gamma"] * dt
+
+
+def geph2posvel(t_rel, g):
+    """geph2pos / geph2vel (gnss_utility.cpp:698-733): the same integration, run once here."""
+    pos = np.array([g["px"], g["py"], g["pz"]], float)
+    vel = np.array([g["vx"], g["vy"], g["vz"]], float)
+    acc = np.array([g["ax"], g["ay"], g["az"]], float)
+    dt = t_rel
+    dts = -g["tau_n"] + g["gamma"] * dt
+    tt = -TSTEP if dt < 0.0 else TSTEP
+    while abs(dt) > 1e-9:
+        if abs(dt) < TSTEP:
+            tt = dt
+        pos, vel = _glo_orbit(tt, pos, vel, acc)
+        dt -= tt
+    return pos, vel, dts, g["gamma"]
+
+
+def sat_state(t_obs_rel, psr, sys, eph):
+    """One satellite of gnss_comm::sat_states (gnss_spp.cpp:57-94). t_obs_rel = time_diff(obs->time, toe); psr <= 0
+    stands for "no L1 observation" (the reference leaves the default-constructed, all-zero SatState).
+    Returns dict(pos, vel, dt, ddt, tgd, ttx_rel)."""
+    out = dict(pos=np.zeros(3), vel=np.zeros(3), dt=0.0, ddt=0.0, tgd=0.0, ttx_rel=0.0)
+    if not psr > 0:
+        return out
+    tx = t_obs_rel - psr / LIGHT_SPEED
+    if sys == SYS_GLO:
+        tx -= geph2svdt(tx, eph)
+        pos, vel, dts, ddts = geph2posvel(tx, eph)
+        tgd = 0.0
+    else:
+        tx -= eph2svdt(tx, eph)
+        pos, dts = eph2pos(tx, eph, sys)
+        vel, ddts = eph2vel(tx, eph, sys)
+        tgd = eph["tgd"]
+    out.update(pos=pos, vel=vel, dt=dts, ddt=ddts, tgd=tgd, ttx_rel=tx)
+    return out

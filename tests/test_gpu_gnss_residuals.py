@@ -94,3 +94,29 @@ def test_residuals_chain_into_gnss_update():
                        el=ref["azel"][:, 1])
         f.gnss.update_tracked_sys(f.state, ep, Re)
     assert_state_close(g, orc, wl.sw, what="raw epoch -> residuals -> gnss update")
+
+
+def test_sat_states_match_oracle():
+    """igv_sat_states (gnss_comm::sat_states on the device) for Kepler (GPS, GAL, BDS MEO and GEO) and GLONASS records."""
+    from ingvio_b200.synth import random_ephemerides
+    wl = WORKLOADS["tiny"]
+    fp = filter_params(wl)
+    B, S = 2, 12
+    _, st, orc, g = tp._warm(wl, B, 2, fp=fp, max_sats=12)
+    rng = np.random.default_rng(21)
+    eph, sys_, t_obs, psr = random_ephemerides(rng, B, S, geo=(7,))
+    psr[:, 4] = 0.0                                   # no L1 observation
+    out = g.sat_states(eph, t_obs, psr, sys_)
+    for b in range(B):
+        for i in range(S):
+            k = int(sys_[b, i])
+            rec = dict(zip(gc.GLO_FIELDS if k == gc.SYS_GLO else gc.KEPLER_FIELDS, eph[b, i]))
+            ref = gc.sat_state(t_obs[b, i], psr[b, i], k, rec)
+            assert np.abs(out["sat_pos"][b, i] - ref["pos"]).max() < 1e-5, (b, i, k)
+            assert np.abs(out["sat_vel"][b, i] - ref["vel"]).max() < 1e-8, (b, i, k)
+            assert abs(out["sat_clk"][b, i, 0] - ref["dt"]) < 1e-16 and abs(out["sat_clk"][b, i, 1] - ref["ddt"]) < 1e-20
+            assert out["sat_clk"][b, i, 2] == ref["tgd"]
+            assert abs(out["ttx_rel"][b, i] - ref["ttx_rel"]) < 1e-12
+    assert np.all(out["sat_pos"][:, 4] == 0.0) and np.all(out["sat_clk"][:, 4] == 0.0)
+    r = np.linalg.norm(out["sat_pos"][:, [0, 1, 2, 3, 7]], axis=-1)
+    assert np.all(r > 2.4e7) and np.all(r < 4.3e7)

@@ -93,3 +93,85 @@ def test_psr_and_dopp_residuals_vanish_for_consistent_measurements():
     res4, J4, _, _ = gc.psr_res(xyzt, sat, ION)
     d4, Jv4 = gc.dopp_res(rv, rcv, sat)
     assert res4[2] == 0.0 and np.all(J4[2] == 0.0) and d4[2] == 0.0 and np.all(Jv4[2] == 0.0)
+
+
+# ---- ephemeris -> satellite state ------------------------------------------------------------------------------
+def _circular(A=26.56e6, sys=0):
+    return dict(A=A, e=0.0, i0=0.96, OMG0=0.7, omg=0.0, M0=0.4, delta_n=0.0, OMG_dot=0.0, i_dot=0.0, cuc=0.0, cus=0.0,
+                crc=0.0, crs=0.0, cic=0.0, cis=0.0, af0=0.0, af1=0.0, af2=0.0, toe_tow=1.0e5, tgd=0.0, toe_minus_toc=0.0, prn=9)
+
+
+def test_kepler_returns_the_previous_iterate_and_solves_the_equation():
+    for mk, es in ((0.3, 0.01), (2.5, 0.02), (-1.0, 0.3)):
+        E = gc.kepler(mk, es)
+        assert abs(E - es * math.sin(E) - mk) < 1e-12
+
+
+def test_circular_orbit_radius_period_and_velocity():
+    eph = _circular()
+    mu, omg_e = gc.MU_GPS, gc.EARTH_OMG_GPS
+    n = math.sqrt(mu / eph["A"] ** 3)
+    p0, _ = gc.eph2pos(50.0, eph, 0)
+    assert abs(np.linalg.norm(p0) - eph["A"]) < 1e-6
+    T = 2 * math.pi / n
+    p1, _ = gc.eph2pos(50.0 + T, eph, 0)           # one revolution later the Earth has turned by omg_e * T
+    c, s = math.cos(omg_e * T), math.sin(omg_e * T)
+    Rz = np.array([[c, s, 0.0], [-s, c, 0.0], [0.0, 0.0, 1.0]])
+    assert np.abs(p1 - Rz @ p0).max() < 1e-4
+    v, _ = gc.eph2vel(50.0, eph, 0)
+    h = 1e-3
+    pm, _ = gc.eph2pos(50.0 - h, eph, 0)
+    pp, _ = gc.eph2pos(50.0 + h, eph, 0)
+    assert np.abs(v - (pp - pm) / (2 * h)).max() < 1e-5     # with i_dot = cis = cic = 0 the reference's z term is exact
+
+
+def test_eccentric_orbit_velocity_matches_the_position_derivative_in_the_plane_terms():
+    eph = _circular()
+    eph.update(e=0.015, omg=0.8, delta_n=4e-9, OMG_dot=-8e-9, cuc=2e-6, cus=4e-6, crc=250.0, crs=40.0, af0=1e-4, af1=1e-11)
+    v, ddt = gc.eph2vel(300.0, eph, 2)
+    h = 1e-3
+    pm, dm = gc.eph2pos(300.0 - h, eph, 2)
+    pp, dp = gc.eph2pos(300.0 + h, eph, 2)
+    assert np.abs(v - (pp - pm) / (2 * h)).max() < 1e-4
+    assert abs(ddt - (dp - dm) / (2 * h)) < 1e-13
+    r, _ = gc.eph2pos(300.0, eph, 2)
+    assert 0.98 * eph["A"] < np.linalg.norm(r) < 1.02 * eph["A"]
+
+
+def test_bds_geo_branch_is_a_rotation_of_the_inclined_frame():
+    eph = _circular(A=42.164e6)
+    eph.update(i0=0.09, prn=3)
+    p, _ = gc.eph2pos(120.0, eph, gc.SYS_BDS)
+    assert abs(np.linalg.norm(p) - eph["A"]) < 1e-6        # the -5 degree tilt and the Earth rotation preserve length
+    v, _ = gc.eph2vel(120.0, eph, gc.SYS_BDS)
+    h = 1e-3
+    pm, _ = gc.eph2pos(120.0 - h, eph, gc.SYS_BDS)
+    pp, _ = gc.eph2pos(120.0 + h, eph, gc.SYS_BDS)
+    assert np.abs(v - (pp - pm) / (2 * h)).max() < 1e-4
+
+
+def test_glonass_integration_round_trip_and_clock():
+    g = dict(px=1.2e7, py=-1.5e7, pz=1.6e7, vx=1200.0, vy=2500.0, vz=1500.0, ax=1e-6, ay=-1e-6, az=0.0, tau_n=1e-5, gamma=1e-12)
+    p1, v1, dts, ddts = gc.geph2posvel(400.0, g)
+    g2 = dict(g, px=p1[0], py=p1[1], pz=p1[2], vx=v1[0], vy=v1[1], vz=v1[2])
+    p0, v0, _, _ = gc.geph2posvel(-400.0, g2)
+    assert np.abs(p0 - [g["px"], g["py"], g["pz"]]).max() < 1e-3 and np.abs(v0 - [g["vx"], g["vy"], g["vz"]]).max() < 1e-6
+    assert abs(dts - (-1e-5 + 1e-12 * 400.0)) < 1e-18 and ddts == 1e-12
+    # 60 s RK4 steps against 1 s steps
+    pf, vf = np.array([g["px"], g["py"], g["pz"]]), np.array([g["vx"], g["vy"], g["vz"]])
+    acc = np.array([g["ax"], g["ay"], g["az"]])
+    for _ in range(400):
+        pf, vf = gc._glo_orbit(1.0, pf, vf, acc)
+    assert np.abs(pf - p1).max() < 1e-3
+
+
+def test_sat_state_transmit_time_and_missing_l1():
+    eph = _circular()
+    eph.update(af0=2e-4, af1=1e-11, tgd=4e-9)
+    s = gc.sat_state(100.0, 2.3e7, 0, eph)
+    tof = 2.3e7 / gc.LIGHT_SPEED
+    assert abs(s["ttx_rel"] - (100.0 - tof - 2e-4)) < 1e-9 and s["tgd"] == 4e-9
+    p, dts = gc.eph2pos(s["ttx_rel"], eph, 0)
+    assert np.all(s["pos"] == p) and s["dt"] == dts
+    z = gc.sat_state(100.0, 0.0, 0, eph)
+    assert np.all(z["pos"] == 0) and z["dt"] == 0.0 and z["ttx_rel"] == 0.0
