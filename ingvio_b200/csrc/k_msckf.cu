@@ -63,7 +63,7 @@ __host__ __device__ inline int feat_per_warp(int Mmax, int ssz) {
 // QT: largest projected block (rows) whose gate runs in registers, see (5a). FUSE: one CTA of up to 16 warps per
 // sequence; instead of writing the projected blocks to HBM the kernel accumulates their Gram matrix, see (6').
 template <int RHO, bool PS_SMEM, int QT, bool FUSE>
-__global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msckf_features(FeatArgs a) {
+__global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ? 1 : 2) k_msckf_features(FeatArgs a) {
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -484,26 +484,37 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, FUSE ? 1 : 2) k_msck
       }
       __syncwarp();
       // ---- (5b) Cholesky of S = sS[3:M,3:M] (lower) with the rhs as row M: L y = r_proj rides along ----
+      // Left-looking, one column at a time: lane = row; entry (i, j) first subtracts the dot product of the finished
+      // parts of rows i and j (row j is a broadcast read), then the column is scaled by 1/sqrt(pivot). Every entry
+      // is written once and a column costs one barrier (the right-looking version rewrote the whole trailing
+      // block per column and took ~3x the instructions for the 41-row stereo / wide-window blocks).
       for (int j = 3; j < M; ++j) {
-        const double d = sS[j * ldm + j];
-        if (!(d > 0.0)) { pd = false; break; }
-        const double inv = rsqrt(d);
-        __syncwarp();
-        for (int i = j + 1 + lane; i <= M; i += 32) sS[i * ldm + j] *= inv;   // rows j+1..M (incl. rhs row)
-        if (lane == 0) sS[j * ldm + j] = d * inv;
-        __syncwarp();
-        for (int i0 = j + 1; i0 <= M; i0 += 32) {
+        const double* rowj = sS + j * ldm;
+        double dj = 0.0;
+        double accs[2] = {0.0, 0.0};
+        for (int pass = 0, i0 = j; i0 <= M; i0 += 32, ++pass) {
           const int i = i0 + lane;
-          const bool on = i <= M;
-          const int ii = on ? i : j + 1;
-          double* srow = sS + ii * ldm;
-          const double lij = srow[j];
-          const int cmax = min(M - 1, i0 + 31);   // columns j+1..min(i, M-1): rhs row only has columns < M
-          for (int c = j + 1; c <= cmax; ++c) {
-            const double lcj = sS[c * ldm + j];
-            if (on && c <= i) srow[c] = fma(-lij, lcj, srow[c]);
+          const int ii = (i <= M) ? i : j;
+          const double* rowi = sS + ii * ldm;
+          double s0 = rowi[j], s1 = 0.0;
+          int k = 3;
+          for (; k + 1 < j; k += 2) {
+            s0 = fma(-rowi[k], rowj[k], s0);
+            s1 = fma(-rowi[k + 1], rowj[k + 1], s1);
           }
+          if (k < j) s0 = fma(-rowi[k], rowj[k], s0);
+          const double acc = s0 + s1;
+          if (pass == 0) dj = __shfl_sync(0xffffffffu, acc, 0);   // row j is lane 0 of the first pass
+          if (pass < 2) accs[pass] = acc;
+          else if (i <= M) sS[ii * ldm + j] = acc;                 // > 64 rows below the pivot: scaled after the barrier
         }
+        if (!(dj > 0.0)) { pd = false; break; }
+        const double inv = rsqrt(dj);
+        __syncwarp();
+        if (lane == 0) sS[j * ldm + j] = dj * inv;
+        else if (j + lane <= M) sS[(j + lane) * ldm + j] = accs[0] * inv;
+        if (j + 32 + lane <= M) sS[(j + 32 + lane) * ldm + j] = accs[1] * inv;
+        for (int i = j + 64 + lane; i <= M; i += 32) sS[i * ldm + j] *= inv;
         __syncwarp();
       }
       if (pd) {
