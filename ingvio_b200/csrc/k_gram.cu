@@ -345,9 +345,9 @@ __global__ void __launch_bounds__(256) k_gram_factor(FactorArgs a) {
   for (int j = 0; j < n; ++j) {
     const int oj = off(j);
     const double d = U[oj + j];
-    const bool live = d > a.tol * dref[j];
+    const bool live = d > a.tol * dref[j] && d > 1e-280;   // (the second test keeps the fast reciprocal in range)
     if (live) {
-      const double inv = 1.0 / d;
+      const double inv = rcp_nobranch(d);   // d > 0 and normal here; every thread needs it, so no slow-path division
       for (int i = j + 1 + warp; i < n; i += nw) {
         const int oi = off(i);
         const double lij = U[oj + i] * inv;

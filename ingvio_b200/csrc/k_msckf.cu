@@ -119,6 +119,21 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
   for (int fbase = blockIdx.x * nwarps; fbase < a.F; fbase += gridDim.x * nwarps) {
     const int f = fbase + warp;
     int flag = 0;      // FUSE: 0 = no contribution, else 1 + anchor slot (ncl + 1: anchor outside the window)
+    {
+      // pull the NEXT track's inputs towards L1/L2 while this one is processed (they are read by dependent global
+      // loads at the top of the body; no registers are held across the body)
+      const int fn = f + gridDim.x * nwarps;
+      if (fn < a.F) {
+        const size_t bn = (size_t)b * a.F + fn;
+        const char* po = reinterpret_cast<const char*>(a.obs + bn * a.obs_slots * RHO);
+        const int obytes = a.obs_slots * RHO * 8;
+        if (lane * 128 < obytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(po + lane * 128));
+        if (lane == 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.mask + bn * a.obs_slots));
+        if (lane == 9) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pf + bn * 3));
+        if (lane == 10) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.anchor + bn));
+        if (lane == 11) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.dof + bn));
+      }
+    }
     if (f < a.F) do {
     const size_t bf = (size_t)b * a.F + f;          // index into the caller's arrays
     const size_t bo = (size_t)b * a.F_alloc + f;    // index into f_rows / f_gamma
