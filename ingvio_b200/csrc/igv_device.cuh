@@ -327,21 +327,34 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z
   for (int jb = 0; jb < r; jb += NB) {
     const int nb = min(NB, r - jb);
     double* D = S + jb + (long)jb * lds;   // diagonal block, element (i,k) at D[i + k*r]
-    // (a) unblocked Cholesky of the diagonal block by warp 0 (lane = row)
+    // (a) unblocked Cholesky of the diagonal block by warp 0: lane = row, the row's lower part in REGISTERS, column
+    // k's entries exchanged by shuffles -- the other warps wait for this serial section, so it has no shared-memory
+    // round trips or warp barriers on its critical path
     if (warp == 0) {
-      for (int k = 0; k < nb; ++k) {
-        const double d = D[k + (long)k * lds];
-        if (!(d > 0.0)) { if (lane == 0) *s_ok = 0; break; }
+      double arow[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) arow[c] = (lane < nb && c <= lane) ? D[lane + (long)c * lds] : 0.0;
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        if (k >= nb) break;
+        const double d = __shfl_sync(0xffffffffu, arow[k], k);
+        if (!(d > 0.0)) { ok = false; break; }
         const double inv = rsqrt(d);
-        __syncwarp();
-        if (lane > k && lane < nb) D[lane + (long)k * lds] *= inv;
-        if (lane == k) { D[k + (long)k * lds] = d * inv; s_rdiag[k] = inv; }
-        __syncwarp();
-        if (lane > k && lane < nb) {
-          const double lik = D[lane + (long)k * lds];
-          for (int c = k + 1; c <= lane; ++c) D[lane + (long)c * lds] = fma(-lik, D[c + (long)k * lds], D[lane + (long)c * lds]);
+        const double l = arow[k] * inv;          // L[lane][k] (lane == k: sqrt(d))
+        arow[k] = l;
+        if (lane == k) s_rdiag[k] = inv;
+#pragma unroll
+        for (int c = k + 1; c < NB; ++c) {
+          const double lc = __shfl_sync(0xffffffffu, l, c);
+          if (c <= lane) arow[c] = fma(-l, lc, arow[c]);
         }
-        __syncwarp();
+      }
+      if (!ok && lane == 0) *s_ok = 0;
+      if (lane < nb) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+          if (c <= lane && c < nb) D[lane + (long)c * lds] = arow[c];
       }
     }
     __syncthreads();
