@@ -317,9 +317,11 @@ __device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int r
 // Per block of NB columns: (a) warp 0 factors the NB x NB diagonal block, (b) one thread per row of the
 // panel / per right-hand side solves against it, (c) the trailing update of [S | Z] is a K = NB
 // register-tiled GEMM over all threads.  3 barriers per block; the right-hand sides ride along, so
-// there is no separate triangular solve.  Returns false (uniformly) on a non-positive pivot.
+// there is no separate triangular solve.  Returns false (uniformly) on a non-positive pivot; with `dref` (the
+// original diagonal) the factorisation is the semi-definite one described at (a) and never fails.
 template <int NB>
-__device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z, int ldz, int c0, int nc, int* s_ok) {
+__device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z, int ldz, int c0, int nc, int* s_ok,
+                                            const double* dref = nullptr, double tol = 0.0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ double s_rdiag[NB];   // 1 / L[k][k] of the current diagonal block
   if (tid == 0) *s_ok = 1;
@@ -339,8 +341,11 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z
       for (int k = 0; k < NB; ++k) {
         if (k >= nb) break;
         const double d = __shfl_sync(0xffffffffu, arow[k], k);
-        if (!(d > 0.0)) { ok = false; break; }
-        const double inv = rsqrt(d);
+        // semi-definite mode (dref given): a pivot at rounding level relative to the original diagonal marks a
+        // dependent column -- its column of L and its entry of the solved right-hand sides become zero
+        const bool dead = dref && !(d > tol * dref[jb + k] && d > 1e-280);
+        if (!dref && !(d > 0.0)) { ok = false; break; }
+        const double inv = dead ? 0.0 : rsqrt(d);
         const double l = arow[k] * inv;          // L[lane][k] (lane == k: sqrt(d))
         arow[k] = l;
         if (lane == k) s_rdiag[k] = inv;

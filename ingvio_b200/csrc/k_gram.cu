@@ -365,6 +365,35 @@ __global__ void __launch_bounds__(256) k_gram_factor(FactorArgs a) {
   }
 }
 
+// Blocked version for n <= 160: G (lower, column-major) and the right-hand side sit in shared memory and the
+// factorisation is cta_chol_solve_fused<8> in its semi-definite mode -- 8-column panels, the trailing update on DMMA,
+// the right-hand side riding along -- instead of one barrier and one rank-1 update per column.
+__global__ void __launch_bounds__(256) k_gram_factor_blocked(FactorArgs a) {
+  extern __shared__ double sm[];
+  __shared__ int s_ok;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int n = a.n, n1 = n + 1;
+  const int lds = n + ((4 - n % 8) + 8) % 8;     // 4 (mod 8): conflict-free DMMA fragments
+  double* S = sm;                 // [n][lds] lower triangle, column-major: S[i + j*lds] = G[j][i], i >= j
+  double* Zr = S + (size_t)n * lds;   // [lds] right-hand side H^T r
+  double* dref = Zr + lds;        // [n] original diagonal
+  const double* Gb = a.G + (size_t)b * a.g_seq_stride;
+  const size_t pstride = (size_t)a.n1p * a.n1p;
+  for (int j = warp; j < n; j += nw)
+    for (int i = j + lane; i < n1; i += 32) {
+      double v = 0.0;
+      for (int p = 0; p < a.nparts; ++p) v += Gb[p * pstride + (size_t)j * a.n1p + i];   // fixed order
+      if (i < n) S[i + (size_t)j * lds] = v; else Zr[j] = v;
+      if (i == j) dref[j] = v;
+    }
+  __syncthreads();
+  cta_chol_solve_fused<8>(S, n, lds, Zr, lds, 0, 1, &s_ok, dref, a.tol);
+  double* out = a.out + (size_t)b * a.out_stride;
+  for (int i = warp; i < n; i += nw)
+    for (int k = lane; k < n1; k += 32)
+      out[(size_t)i * n1 + k] = (k < i) ? 0.0 : ((k < n) ? S[k + (size_t)i * lds] : Zr[i]);
+}
+
 template <int SPW>
 void launch_accum(const GramArgs& a, int split, int B, int warps, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
@@ -431,12 +460,20 @@ void igv_launch_gram_factor(igv_batch* h, int nparts) {
   f.n1p = 24 * ((n + 1 + 23) / 24) + 8; f.nparts = nparts;
   f.n = n; f.out = h->Hc; f.out_stride = (long)h->ncols_max * (h->ncols_max + 1);
   f.tol = 1e-13;
-  const size_t fsmem = sizeof(double) * ((size_t)n * (n + 3) / 2 + 2 * n);
   static bool fattr = false;
   if (!fattr) {
     cudaFuncSetAttribute(k_gram_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_gram_factor_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     fattr = true;
   }
-  k_gram_factor<<<h->B, 256, fsmem, h->stream>>>(f);
+  const char* ev = getenv("IGV_FACTOR_CFG");      // test knob: 1 forces the column-by-column kernel
+  const int lds = n + ((4 - n % 8) + 8) % 8;
+  const size_t bsmem = sizeof(double) * ((size_t)n * lds + lds + n);
+  if (bsmem <= 200 * 1024 && !(ev && atoi(ev) == 1)) {
+    k_gram_factor_blocked<<<h->B, 256, bsmem, h->stream>>>(f);
+  } else {
+    const size_t fsmem = sizeof(double) * ((size_t)n * (n + 3) / 2 + 2 * n);
+    k_gram_factor<<<h->B, 256, fsmem, h->stream>>>(f);
+  }
   h->launches += 1;
 }

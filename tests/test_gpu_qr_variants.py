@@ -121,3 +121,10 @@ def _c1_frames():
             f.step(fr.seq(b))
         assert_state_close(g, orc, wl.sw, what=f"c1 frame {i}")
     assert np.all((g.flags() & 3) == 0)
+
+
+def test_column_factor_kernel_c2(monkeypatch):
+    """k_gram_factor (column by column, packed storage: the fallback of wide windows) on the c2 frames; the default
+    for n <= 160 is the blocked k_gram_factor_blocked."""
+    monkeypatch.setenv("IGV_FACTOR_CFG", "1")
+    tp.test_c2_frames_against_oracle()
