@@ -65,7 +65,9 @@ enum { IGV_COMPRESS_AUTO = 0,         /* GRAM where supported (<= 215 columns), 
 /* per-sequence status bits (igv_get_flags) */
 enum { IGV_FLAG_NEG_DIAG = 1,      /* negative covariance diagonal after an update (StateManager.cpp:413-421) */
        IGV_FLAG_CHOL_FAIL = 2,     /* innovation covariance not positive definite; update skipped            */
-       IGV_FLAG_GNSS_REJECTED = 4  /* joint chi^2 "strong reject" fired (GnssUpdate.cpp:286-287)             */ };
+       IGV_FLAG_GNSS_REJECTED = 4, /* joint chi^2 "strong reject" fired (GnssUpdate.cpp:286-287)             */
+       IGV_FLAG_TRACKS_FULL = 8,   /* track table full: new tracks of a frame were dropped (igv_tracks_collect) */
+       IGV_FLAG_GATHER_CUT = 16    /* more selected tracks than max_feats: the highest ids were left out        */ };
 
 typedef struct {
   int batch;        /* B >= 1                                                                    */
@@ -299,6 +301,81 @@ typedef struct {
   double* ttx_rel;           /* out B x S, optional */
 } igv_sat_state_args;
 igv_status igv_sat_states(igv_batch* h, const igv_sat_state_args* a);
+
+/* ---- track table ("next" row) ------------------------------------------------------
+ * The MapServer (MapServer.h:69-134: std::map<int, FeatureInfo> with per-feature observation maps keyed by clone
+ * timestamp) as a device-resident table per sequence, fed from the tracker's wire format
+ * (feature_tracker/msg/MonoMeas.msg, StereoMeas.msg: uint64 id, float64 u0 v0 [u1 v1]) and emitting the dense
+ * per-track arrays igv_triangulate / igv_msckf_update consume, so a whole frame stays on the device.
+ * A track holds: id (the message id narrowed to `int` like MapServer.cpp:24), one observation per clone of the
+ * window, the anchor clone (AnchoredLandmark::getAnchoredPose), _isToMarg, _isTri and the landmark value / FEJ
+ * position. Observations are stored per PHYSICAL clone column; the handle maps window slots to columns and follows
+ * igv_augment_clone* / igv_marginalize_clone, so nothing moves when the window slides. Only MSCKF-type features are
+ * modelled (SLAM landmarks are section 8f rank 3). Every call is one launch over all B sequences; selections come out
+ * in ascending id order, the iteration order of the reference's std::map.                                          */
+igv_status igv_tracks_create(igv_batch* h, int max_tracks /* per sequence, <= 4096 */);
+igv_status igv_tracks_reset(igv_batch* h);                /* map_server.reset(new MapServer()) */
+/* MapServerManager::collectMonoMeas / collectStereoMeas (MapServerManager.cpp:189-219) with
+ * FeatureInfoManager::collect*Meas (:101-187) for one frame message per sequence, at the NEWEST clone (the reference
+ * asserts state->_timestamp is in the window, :107-111). n_meas: B counts (<= meas_stride <= 4096); ids:
+ * B x meas_stride; uv: B x meas_stride x rho. Message order is kept: a repeated id inside one message keeps its first
+ * measurement (":126-130 skip adding"); new tracks take free table entries in message order. */
+igv_status igv_tracks_collect(igv_batch* h, const int* n_meas, int meas_stride, const unsigned long long* ids,
+                              const double* uv);
+/* MapServerManager::markMargMonoFeatures / markMargStereoFeatures (:221-273): tracks without an observation at the
+ * newest clone get _isToMarg. */
+igv_status igv_tracks_mark_lost(igv_batch* h);
+
+enum { IGV_TRK_LOST = 0,      /* RemoveLostUpdate.cpp:45-59 / :280-294: MSCKF tracks with _isToMarg               */
+       IGV_TRK_SEEN_AT = 1    /* SwMargUpdate.cpp:61-85, KeyframeUpdate.cpp:455-480: observed at every selected clone */ };
+typedef struct {
+  int rule;                      /* IGV_TRK_LOST | IGV_TRK_SEEN_AT                                                 */
+  int n_selected;                /* SEEN_AT: number of selected clones                                             */
+  const int* selected_slots;     /* SEEN_AT: their window slots (HOST array)                                       */
+  int min_obs;                   /* LOST: feat_ok needs this many observations (4 mono :51, 3 stereo :287)          */
+  int dof_fixed;                 /* SEEN_AT: > 0 fixed gate dof (KeyframeUpdate.cpp:525-526: 2); else n_selected-1  */
+  int n_feats;                   /* F <= max_feats: capacity of the outputs                                         */
+  int obs_slots;                 /* SW >= clone count: slot dimension of the outputs                                */
+  int* track_entry;              /* B x F      table entry of the f-th selected track, -1 beyond n_sel              */
+  int* n_sel;                    /* B          selected tracks (capped at F, IGV_FLAG_GATHER_CUT)                   */
+  int* track_id;                 /* optional B x F ids (0 beyond n_sel)                                             */
+  double* obs;                   /* B x F x SW x rho  -> igv_triangulate.obs / igv_msckf_update.obs                 */
+  unsigned char* mask_all;       /* B x F x SW  every observation of the track -> igv_triangulate.obs_mask          */
+  unsigned char* mask_upd;       /* B x F x SW  LOST: = mask_all; SEEN_AT: observations at the selected clones
+                                                -> igv_msckf_update.obs_mask                                       */
+  int* anchor_slot;              /* B x F      window slot of the anchor clone (0 beyond n_sel)                     */
+  int* chi2_dof;                 /* B x F      LOST: #obs-1; SEEN_AT: n_selected-1 or dof_fixed                     */
+  unsigned char* feat_ok;        /* B x F      LOST: #obs >= min_obs; SEEN_AT: 1; 0 beyond n_sel                    */
+} igv_track_gather_args;
+igv_status igv_tracks_gather(igv_batch* h, const igv_track_gather_args* a);
+/* Second half of FeatureInfoManager::triangulateFeatureInfo{Mono,Stereo} (MapServerManager.cpp:284-306): where ok,
+ * the landmark value (and, at the first success, the FEJ value) is stored and _isTri set; feat_ok (optional, in/out)
+ * is and-ed with ok so that it can go straight into igv_msckf_update. pf / ok: outputs of igv_triangulate.
+ * (_numOfTri, read nowhere in the reference, is not kept.) */
+igv_status igv_tracks_commit_tri(igv_batch* h, int n_feats, const int* track_entry, const double* pf,
+                                 const unsigned char* ok, unsigned char* feat_ok);
+/* map_server->erase(id) for the gathered tracks (RemoveLostUpdate.cpp:58-59,165-166). */
+igv_status igv_tracks_erase(igv_batch* h, int n_feats, const int* track_entry);
+/* SwMargUpdate::clean{Mono,Stereo}ObsAtMargTime (SwMargUpdate.cpp:191-213, :389-411), KeyframeUpdate twin
+ * (KeyframeUpdate.cpp:251-278): drop the observations at these window slots, erase tracks left without any. */
+igv_status igv_tracks_clean_obs(igv_batch* h, int n_slots, const int* clone_slots /* HOST */);
+/* SwMargUpdate::changeMSCKFAnchor (SwMargUpdate.cpp:216-259; min_depth 0) / KeyframeUpdate::changeMSCKFAnchor
+ * (KeyframeUpdate.cpp:280-327; min_depth 0.3): tracks anchored at one of old_slots move to the newest clone if
+ * triangulated and deeper than min_depth in it, else they are erased. */
+igv_status igv_tracks_change_anchor(igv_batch* h, int n_old, const int* old_slots /* HOST */, double min_depth);
+/* MapServerManager::eraseInvalidFeatures (MapServerManager.cpp:454-490): triangulated tracks whose depth in the
+ * anchor camera is <= min_depth (reference: 0.2) or whose anchor left the window are erased. */
+igv_status igv_tracks_erase_invalid(igv_batch* h, double min_depth);
+/* Dump in table-entry order (tests, checkpoints). All outputs optional. used/to_marg/is_tri: B x T; id: B x T;
+ * slot_mask: B x T, bit s = observation at window slot s; anchor_slot: B x T (-1: none / left the window);
+ * pf, pf_fej: B x T x 3; obs: B x T x obs_slots x rho (zeros where no observation); n_tracks: B. */
+typedef struct {
+  int obs_slots;
+  int* id; unsigned char* used; unsigned char* to_marg; unsigned char* is_tri; unsigned long long* slot_mask;
+  int* anchor_slot; double* pf; double* pf_fej; double* obs; int* n_tracks;
+} igv_track_dump;
+igv_status igv_tracks_get(igv_batch* h, const igv_track_dump* d);
+int igv_tracks_capacity(const igv_batch* h);   /* max_tracks, 0 before igv_tracks_create */
 
 /* ---- delayed initialisation / linear replacement ------------------------------------------------
  * StateManager::addVariableDelayed (StateManager.cpp:547-630, with :462-541): new 1-dim variable.

@@ -15,7 +15,8 @@ GPS, GLO, GAL, BDS, FS, YOF = range(6)
 R_ISO, R_DIAG, R_FULL = 0, 1, 2
 VIS_ALL_OBS, VIS_SELECTED = 0, 1
 COMPRESS_AUTO, COMPRESS_HOUSEHOLDER, COMPRESS_GRAM = 0, 1, 2
-FLAG_NEG_DIAG, FLAG_CHOL_FAIL, FLAG_GNSS_REJECTED = 1, 2, 4
+FLAG_NEG_DIAG, FLAG_CHOL_FAIL, FLAG_GNSS_REJECTED, FLAG_TRACKS_FULL, FLAG_GATHER_CUT = 1, 2, 4, 8, 16
+TRK_LOST, TRK_SEEN_AT = 0, 1
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -72,6 +73,20 @@ class igv_sat_state_args(C.Structure):
                 ("ttx_rel", C.c_void_p)]
 
 
+class igv_track_gather_args(C.Structure):
+    _fields_ = [("rule", C.c_int), ("n_selected", C.c_int), ("selected_slots", c_ip), ("min_obs", C.c_int),
+                ("dof_fixed", C.c_int), ("n_feats", C.c_int), ("obs_slots", C.c_int), ("track_entry", C.c_void_p),
+                ("n_sel", C.c_void_p), ("track_id", C.c_void_p), ("obs", C.c_void_p), ("mask_all", C.c_void_p),
+                ("mask_upd", C.c_void_p), ("anchor_slot", C.c_void_p), ("chi2_dof", C.c_void_p),
+                ("feat_ok", C.c_void_p)]
+
+
+class igv_track_dump(C.Structure):
+    _fields_ = [("obs_slots", C.c_int), ("id", C.c_void_p), ("used", C.c_void_p), ("to_marg", C.c_void_p),
+                ("is_tri", C.c_void_p), ("slot_mask", C.c_void_p), ("anchor_slot", C.c_void_p), ("pf", C.c_void_p),
+                ("pf_fej", C.c_void_p), ("obs", C.c_void_p), ("n_tracks", C.c_void_p)]
+
+
 EPH_STRIDE = 24
 
 # every symbol include/ingvio_b200.h declares: (restype, argtypes)
@@ -124,6 +139,18 @@ SIGNATURES = {
     "igv_add_variable_delayed": (C.c_int, [_H, C.c_int, _VP, C.c_int, c_ip, c_ip, C.c_int, _VP, _VP, _VP,
                                            C.c_double, C.c_double, C.c_int, C.c_double, _VP, _VP]),
     "igv_replace_var_linear": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, c_ip, c_ip, _VP]),
+    "igv_tracks_create": (C.c_int, [_H, C.c_int]),
+    "igv_tracks_reset": (C.c_int, [_H]),
+    "igv_tracks_capacity": (C.c_int, [_H]),
+    "igv_tracks_collect": (C.c_int, [_H, _VP, C.c_int, _VP, _VP]),
+    "igv_tracks_mark_lost": (C.c_int, [_H]),
+    "igv_tracks_gather": (C.c_int, [_H, C.POINTER(igv_track_gather_args)]),
+    "igv_tracks_commit_tri": (C.c_int, [_H, C.c_int, _VP, _VP, _VP, _VP]),
+    "igv_tracks_erase": (C.c_int, [_H, C.c_int, _VP]),
+    "igv_tracks_clean_obs": (C.c_int, [_H, C.c_int, c_ip]),
+    "igv_tracks_change_anchor": (C.c_int, [_H, C.c_int, c_ip, C.c_double]),
+    "igv_tracks_erase_invalid": (C.c_int, [_H, C.c_double]),
+    "igv_tracks_get": (C.c_int, [_H, C.POINTER(igv_track_dump)]),
     "igv_get_flags": (C.c_int, [_H, _VP, C.c_int]),
     "igv_cov_trace": (C.c_int, [_H, _VP]),
     "igv_profile_enable": (C.c_int, [_H, C.c_int]),

@@ -158,6 +158,30 @@ void reindex(igv_batch* h) {
   h->N = idx;
 }
 
+// ---- track-table column bookkeeping (igv_tracks_*): window slot -> physical column, following the clone list ----
+void trk_on_augment(igv_batch* h) {
+  if (h->trk.T == 0) return;
+  igv_trk_col_alloc(h->trk);   // never -1: the window holds at most cfg.max_clones = C clones
+}
+void trk_on_marg_clone(igv_batch* h, int slot) {
+  if (h->trk.T == 0 || slot < 0 || slot >= (int)h->trk.col_of_slot.size()) return;
+  // Observations at a clone that left the window cannot be used by anything; with the reference's call order
+  // (clean*ObsAtMargTime -> changeMSCKFAnchor -> margSwPose) the column is already empty and this is a no-op.
+  igv_launch_trk_clean(h, 1ull << h->trk.col_of_slot[slot], 0);
+  igv_trk_col_release(h->trk, slot);
+}
+igv_status trk_ready(igv_batch* h) {
+  if (!h) return IGV_ERR_INVALID;
+  if (h->trk.T == 0) return fail(h, IGV_ERR_STATE, "track table not created (igv_tracks_create)");
+  return IGV_OK;
+}
+igv_status trk_slot_bits(igv_batch* h, int n, const int* slots, unsigned long long* bits) {
+  *bits = 0ull;
+  if (n < 0 || (n > 0 && !slots)) return IGV_ERR_INVALID;
+  if (!igv_trk_slot_bits(h->trk, n, slots, bits)) return fail(h, IGV_ERR_STATE, "clone slot not in the sliding window");
+  return IGV_OK;
+}
+
 }  // namespace
 
 IgvLayout igv_batch::layout() const {
@@ -267,6 +291,8 @@ igv_status igv_destroy(igv_batch* h) {
                   h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws};
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   for (void* p : ptrs) if (p) cudaFree(p);
+  void* tptrs[] = {h->trk.id, h->trk.mask, h->trk.st, h->trk.anchor, h->trk.pf, h->trk.pf_fej, h->trk.obs};
+  for (void* p : tptrs) if (p) cudaFree(p);
   for (auto& sl : h->slots) { if (sl.mem) cudaFree(sl.mem); if (sl.consumed) cudaEventDestroy(sl.consumed); }
   for (auto& f : h->fences) if (f) cudaEventDestroy(f);
   if (h->copied) cudaEventDestroy(h->copied);
@@ -348,6 +374,7 @@ igv_status igv_state_init(igv_batch* h, const double* R_i2w, const double* p, co
   reindex(h);
   IGV_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * B, h->stream));
   igv_launch_state_init(h, dR, dp, dv, dbg, dba, dRe, dpe, dd);
+  if (h->trk.T > 0) { h->trk.col_of_slot.clear(); igv_launch_trk_reset(h); }   // a new State starts with an empty map
   return check_launch(h);
 }
 
@@ -455,6 +482,7 @@ static igv_status marginalize_var(igv_batch* h, size_t vi) {
     for (size_t k = 0; k < vi; ++k) if (h->vars[k].kind == VK_CLONE) ++clone_slot;
   }
   igv_launch_marginalize(h, v.idx, v.size, clone_slot);
+  if (clone_slot >= 0) trk_on_marg_clone(h, clone_slot);
   h->vars.erase(h->vars.begin() + vi);
   reindex(h);
   return check_launch(h);
@@ -527,6 +555,7 @@ static igv_status augment(igv_batch* h, const double* R, const double* cR, const
   igv_launch_augment(h, R, cR, cp);
   h->vars.push_back({VK_CLONE, h->N, 6, 0});
   reindex(h);
+  trk_on_augment(h);
   return check_launch(h);
 }
 igv_status igv_augment_clone(igv_batch* h) {
@@ -862,6 +891,199 @@ igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size,
 }
 
 // ---- read-outs --------------------------------------------------------------------------------------------
+// ---- track table (MapServer on the device) ------------------------------------------------------------------------
+igv_status igv_tracks_create(igv_batch* h, int max_tracks) {
+  if (!h || max_tracks < 1 || max_tracks > 4096) return IGV_ERR_INVALID;
+  if (h->trk.T != 0) return fail(h, IGV_ERR_STATE, "track table already created");
+  if (h->cfg.max_clones < 1) return fail(h, IGV_ERR_CAPACITY, "track table needs max_clones >= 1");
+  IgvTrackTable& t = h->trk;
+  const size_t n = (size_t)h->B * max_tracks, C = (size_t)h->cfg.max_clones;
+  IGV_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&t.id), sizeof(int) * n));
+  IGV_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&t.mask), sizeof(unsigned long long) * n));
+  IGV_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&t.st), n));
+  IGV_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&t.anchor), sizeof(int) * n));
+  IGV_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&t.pf), sizeof(double) * 3 * n));
+  IGV_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&t.pf_fej), sizeof(double) * 3 * n));
+  IGV_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&t.obs), sizeof(double) * n * C * h->rho));
+  IGV_CUDA(h, cudaMemsetAsync(t.obs, 0, sizeof(double) * n * C * h->rho, h->stream));
+  t.T = max_tracks;
+  t.C = (int)C;
+  t.col_of_slot.clear();
+  const int nc = h->layout().n_clones;
+  for (int s = 0; s < nc; ++s) t.col_of_slot.push_back(s);
+  igv_launch_trk_reset(h);
+  return check_launch(h);
+}
+
+igv_status igv_tracks_reset(igv_batch* h) {
+  IGV_TRY(trk_ready(h));
+  igv_launch_trk_reset(h);
+  return check_launch(h);
+}
+
+int igv_tracks_capacity(const igv_batch* h) { return h ? h->trk.T : 0; }
+
+igv_status igv_tracks_collect(igv_batch* h, const int* n_meas, int meas_stride, const unsigned long long* ids,
+                              const double* uv) {
+  IGV_TRY(trk_ready(h));
+  if (!n_meas || meas_stride < 0 || meas_stride > 4096) return IGV_ERR_INVALID;
+  if (meas_stride == 0) return IGV_OK;
+  if (!ids || !uv) return IGV_ERR_INVALID;
+  if (h->trk.col_of_slot.empty())
+    return fail(h, IGV_ERR_STATE, "[FeatureInfoManager]: Meas timestamp not in sw!");   // MapServerManager.cpp:107-111
+  arena_reset(h);
+  const size_t B = h->B, M = meas_stride;
+  const int* dn; const unsigned long long* did; const double* duv;
+  IGV_TRY(stage(h, n_meas, B, &dn));
+  IGV_TRY(stage(h, ids, B * M, &did));
+  IGV_TRY(stage(h, uv, B * M * h->rho, &duv));
+  igv_launch_trk_collect(h, dn, meas_stride, did, duv);
+  return check_launch(h);
+}
+
+igv_status igv_tracks_mark_lost(igv_batch* h) {
+  IGV_TRY(trk_ready(h));
+  igv_launch_trk_mark_lost(h);
+  return check_launch(h);
+}
+
+igv_status igv_tracks_gather(igv_batch* h, const igv_track_gather_args* a) {
+  IGV_TRY(trk_ready(h));
+  if (!a || !a->track_entry || !a->n_sel || !a->obs || !a->mask_all || !a->mask_upd || !a->anchor_slot ||
+      !a->chi2_dof || !a->feat_ok)
+    return IGV_ERR_INVALID;
+  if (a->rule != IGV_TRK_LOST && a->rule != IGV_TRK_SEEN_AT) return IGV_ERR_INVALID;
+  if (a->n_feats < 1 || a->n_feats > h->cfg.max_feats) return fail(h, IGV_ERR_CAPACITY, "n_feats exceeds max_feats");
+  const int nc = (int)h->trk.col_of_slot.size();
+  if (a->obs_slots < nc || a->obs_slots < 1) return fail(h, IGV_ERR_INVALID, "obs_slots smaller than the clone count");
+  IgvTrkGatherLaunch g{};
+  g.rule = a->rule; g.n_selected = a->n_selected; g.min_obs = a->min_obs; g.dof_fixed = a->dof_fixed;
+  g.F = a->n_feats; g.SW = a->obs_slots;
+  if (a->rule == IGV_TRK_SEEN_AT) {
+    if (a->n_selected < 1) return fail(h, IGV_ERR_INVALID, "SEEN_AT needs at least one selected clone");
+    IGV_TRY(trk_slot_bits(h, a->n_selected, a->selected_slots, &g.sel_cols));
+  }
+  arena_reset(h);
+  const size_t B = h->B, F = a->n_feats, SW = a->obs_slots;
+  IGV_TRY(out_buf(h, a->track_entry, B * F, &g.entry));
+  IGV_TRY(out_buf(h, a->n_sel, B, &g.n_sel));
+  IGV_TRY(out_buf(h, a->track_id, B * F, &g.track_id));
+  IGV_TRY(out_buf(h, a->obs, B * F * SW * h->rho, &g.obs));
+  IGV_TRY(out_buf(h, a->mask_all, B * F * SW, &g.mask_all));
+  IGV_TRY(out_buf(h, a->mask_upd, B * F * SW, &g.mask_upd));
+  IGV_TRY(out_buf(h, a->anchor_slot, B * F, &g.anchor_slot));
+  IGV_TRY(out_buf(h, a->chi2_dof, B * F, &g.dof));
+  IGV_TRY(out_buf(h, a->feat_ok, B * F, &g.feat_ok));
+  igv_launch_trk_gather(h, g);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, a->track_entry, g.entry, B * F));
+  IGV_TRY(fetch(h, a->n_sel, g.n_sel, B));
+  IGV_TRY(fetch(h, a->track_id, g.track_id, B * F));
+  IGV_TRY(fetch(h, a->obs, g.obs, B * F * SW * h->rho));
+  IGV_TRY(fetch(h, a->mask_all, g.mask_all, B * F * SW));
+  IGV_TRY(fetch(h, a->mask_upd, g.mask_upd, B * F * SW));
+  IGV_TRY(fetch(h, a->anchor_slot, g.anchor_slot, B * F));
+  IGV_TRY(fetch(h, a->chi2_dof, g.dof, B * F));
+  IGV_TRY(fetch(h, a->feat_ok, g.feat_ok, B * F));
+  return IGV_OK;
+}
+
+igv_status igv_tracks_commit_tri(igv_batch* h, int n_feats, const int* track_entry, const double* pf,
+                                 const unsigned char* ok, unsigned char* feat_ok) {
+  IGV_TRY(trk_ready(h));
+  if (n_feats < 0 || !track_entry || !pf || !ok) return IGV_ERR_INVALID;
+  if (n_feats == 0) return IGV_OK;
+  arena_reset(h);
+  const size_t n = (size_t)h->B * n_feats;
+  const int* de; const double* dpf; const unsigned char* dok; unsigned char* dfo = nullptr;
+  IGV_TRY(stage(h, track_entry, n, &de));
+  IGV_TRY(stage(h, pf, 3 * n, &dpf));
+  IGV_TRY(stage(h, ok, n, &dok));
+  if (feat_ok) {
+    if (h->ptr_mode == IGV_PTR_DEVICE) {
+      dfo = feat_ok;
+    } else {   // in/out argument: staged copy in, fetched back
+      const unsigned char* in;
+      IGV_TRY(stage(h, static_cast<const unsigned char*>(feat_ok), n, &in));
+      dfo = const_cast<unsigned char*>(in);
+    }
+  }
+  igv_launch_trk_commit_tri(h, n_feats, de, dpf, dok, dfo);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, feat_ok, static_cast<const unsigned char*>(dfo), n));
+  return IGV_OK;
+}
+
+igv_status igv_tracks_erase(igv_batch* h, int n_feats, const int* track_entry) {
+  IGV_TRY(trk_ready(h));
+  if (n_feats < 0 || !track_entry) return IGV_ERR_INVALID;
+  if (n_feats == 0) return IGV_OK;
+  arena_reset(h);
+  const int* de;
+  IGV_TRY(stage(h, track_entry, (size_t)h->B * n_feats, &de));
+  igv_launch_trk_erase(h, n_feats, de);
+  return check_launch(h);
+}
+
+igv_status igv_tracks_clean_obs(igv_batch* h, int n_slots, const int* clone_slots) {
+  IGV_TRY(trk_ready(h));
+  unsigned long long bits;
+  IGV_TRY(trk_slot_bits(h, n_slots, clone_slots, &bits));
+  if (bits == 0ull) return IGV_OK;
+  igv_launch_trk_clean(h, bits, 1);
+  return check_launch(h);
+}
+
+igv_status igv_tracks_change_anchor(igv_batch* h, int n_old, const int* old_slots, double min_depth) {
+  IGV_TRY(trk_ready(h));
+  unsigned long long bits;
+  IGV_TRY(trk_slot_bits(h, n_old, old_slots, &bits));
+  if (bits == 0ull) return IGV_OK;
+  igv_launch_trk_change_anchor(h, bits, min_depth);
+  return check_launch(h);
+}
+
+igv_status igv_tracks_erase_invalid(igv_batch* h, double min_depth) {
+  IGV_TRY(trk_ready(h));
+  if (h->trk.col_of_slot.empty()) return IGV_OK;
+  igv_launch_trk_erase_invalid(h, min_depth);
+  return check_launch(h);
+}
+
+igv_status igv_tracks_get(igv_batch* h, const igv_track_dump* d) {
+  IGV_TRY(trk_ready(h));
+  if (!d) return IGV_ERR_INVALID;
+  if (d->obs && d->obs_slots < (int)h->trk.col_of_slot.size())
+    return fail(h, IGV_ERR_INVALID, "obs_slots smaller than the clone count");
+  arena_reset(h);
+  const size_t n = (size_t)h->B * h->trk.T, SW = d->obs ? d->obs_slots : 0;
+  igv_track_dump dev = *d;
+  IGV_TRY(out_buf(h, d->id, n, &dev.id));
+  IGV_TRY(out_buf(h, d->used, n, &dev.used));
+  IGV_TRY(out_buf(h, d->to_marg, n, &dev.to_marg));
+  IGV_TRY(out_buf(h, d->is_tri, n, &dev.is_tri));
+  IGV_TRY(out_buf(h, d->slot_mask, n, &dev.slot_mask));
+  IGV_TRY(out_buf(h, d->anchor_slot, n, &dev.anchor_slot));
+  IGV_TRY(out_buf(h, d->pf, 3 * n, &dev.pf));
+  IGV_TRY(out_buf(h, d->pf_fej, 3 * n, &dev.pf_fej));
+  IGV_TRY(out_buf(h, d->obs, n * SW * h->rho, &dev.obs));
+  IGV_TRY(out_buf(h, d->n_tracks, (size_t)h->B, &dev.n_tracks));
+  igv_launch_trk_dump(h, dev);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, d->id, dev.id, n));
+  IGV_TRY(fetch(h, d->used, dev.used, n));
+  IGV_TRY(fetch(h, d->to_marg, dev.to_marg, n));
+  IGV_TRY(fetch(h, d->is_tri, dev.is_tri, n));
+  IGV_TRY(fetch(h, d->slot_mask, dev.slot_mask, n));
+  IGV_TRY(fetch(h, d->anchor_slot, dev.anchor_slot, n));
+  IGV_TRY(fetch(h, d->pf, dev.pf, 3 * n));
+  IGV_TRY(fetch(h, d->pf_fej, dev.pf_fej, 3 * n));
+  IGV_TRY(fetch(h, d->obs, dev.obs, n * SW * h->rho));
+  IGV_TRY(fetch(h, d->n_tracks, dev.n_tracks, (size_t)h->B));
+  if (h->ptr_mode == IGV_PTR_DEVICE) IGV_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IGV_OK;
+}
+
 igv_status igv_get_flags(igv_batch* h, int* flags_out, int clear) {
   if (!h || !flags_out) return IGV_ERR_INVALID;
   const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;

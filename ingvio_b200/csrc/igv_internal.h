@@ -35,6 +35,27 @@ struct IgvDevParams {
   double pc[3];
 };
 
+// Track table (k_tracks.cu): the MapServer of every sequence, SoA over T table entries. Observations live in C
+// PHYSICAL clone columns; `col_of_slot` (host metadata, passed by value like IgvLayout) maps window slots to them.
+struct IgvTrackTable {
+  int T = 0, C = 0;                        // entries per sequence, physical clone columns (= cfg.max_clones)
+  int* id = nullptr;                       // B x T   MapServer key (message id narrowed to int)
+  unsigned long long* mask = nullptr;      // B x T   bit c: observation at physical column c
+  unsigned char* st = nullptr;             // B x T   IGV_TRK_USED | IGV_TRK_TO_MARG | IGV_TRK_TRI
+  int* anchor = nullptr;                   // B x T   physical column of the anchor clone, -1 none
+  double* pf = nullptr;                    // B x T x 3 landmark value (world)
+  double* pf_fej = nullptr;                // B x T x 3
+  double* obs = nullptr;                   // B x T x C x rho
+  std::vector<int> col_of_slot;            // window slot -> physical column
+};
+enum { IGV_TRK_USED = 1, IGV_TRK_TO_MARG = 2, IGV_TRK_TRI = 4 };
+struct IgvTrkCols {                        // by-value kernel argument
+  int n_slots;                             // clones in the window
+  int cur_col;                             // physical column of the newest clone, -1 if the window is empty
+  signed char col_of_slot[IGV_MAX_CLONES];
+  signed char slot_of_col[IGV_MAX_CLONES];
+};
+
 enum IgvVarKind { VK_SE23, VK_BG, VK_BA, VK_EXT, VK_GNSS, VK_CLONE, VK_OPAQUE };
 struct IgvVar {
   IgvVarKind kind;
@@ -105,6 +126,7 @@ struct igv_batch {
   bool copies_pending = false;          // staged copies the compute stream has not been ordered after yet
   cudaEvent_t fences[4] = {nullptr, nullptr, nullptr, nullptr};   // igv_fence_record / igv_fence_wait
   std::vector<char*> retired;
+  IgvTrackTable trk;                    // igv_tracks_* (empty until igv_tracks_create)
 
   IgvLayout layout() const;
   double* Pc() const { return P[cur]; }
@@ -194,6 +216,30 @@ struct IgvGnssResLaunch {
 void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l);
 void igv_launch_sat_states(igv_batch* h, int S, const double* eph, const double* t_obs, const double* psr, const int* sys,
                            double* pos, double* vel, double* clk, double* ttx);
+
+// ---- track table (k_tracks.cu) ----
+IgvTrkCols igv_trk_cols(const IgvTrackTable& t);
+int igv_trk_col_alloc(IgvTrackTable& t);
+int igv_trk_col_release(IgvTrackTable& t, int slot);
+bool igv_trk_slot_bits(const IgvTrackTable& t, int n, const int* slots, unsigned long long* bits);
+void igv_launch_trk_reset(igv_batch* h);
+void igv_launch_trk_collect(igv_batch* h, const int* n_meas, int meas_stride, const unsigned long long* ids,
+                            const double* uv);
+void igv_launch_trk_mark_lost(igv_batch* h);
+struct IgvTrkGatherLaunch {
+  int rule, n_selected, min_obs, dof_fixed, F, SW;
+  unsigned long long sel_cols;   // physical-column bit mask of the selected clones
+  int* entry; int* n_sel; int* track_id; double* obs; unsigned char* mask_all; unsigned char* mask_upd;
+  int* anchor_slot; int* dof; unsigned char* feat_ok;
+};
+void igv_launch_trk_gather(igv_batch* h, const IgvTrkGatherLaunch& g);
+void igv_launch_trk_commit_tri(igv_batch* h, int F, const int* entry, const double* pf, const unsigned char* ok,
+                               unsigned char* feat_ok);
+void igv_launch_trk_erase(igv_batch* h, int F, const int* entry);
+void igv_launch_trk_clean(igv_batch* h, unsigned long long col_bits, int erase_empty);
+void igv_launch_trk_change_anchor(igv_batch* h, unsigned long long old_cols, double min_depth);
+void igv_launch_trk_erase_invalid(igv_batch* h, double min_depth);
+void igv_launch_trk_dump(igv_batch* h, const igv_track_dump& d);
 
 void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
                              const double* res, double noise_iso, double chi2_mult, int do_chi2,

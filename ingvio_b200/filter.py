@@ -37,7 +37,8 @@ class _Arg:
             return
         if _is_torch(x):
             import torch
-            tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8}[dtype]
+            tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8,
+                   np.uint64: torch.int64}[dtype]   # message ids: same 64 bits
             if x.dtype != tdt or not x.is_contiguous():
                 x = x.to(tdt).contiguous()
             self.keep = x
@@ -480,6 +481,109 @@ class BatchFilter:
             out["gnss_dx"] = self.gnss_update(g.unit, g.res_pos, g.res_vel, g.sigma_psr(psr_amp), g.sigma_dopp(dopp_amp),
                                               g.sys, g.R_enu2ecef, is_adjust_yof, gnss_chi2_test, gnss_strong_reject,
                                               want_dx=want)
+        return out
+
+    # ---- track table: MapServer / MapServerManager on the device -------------------------
+    def create_map_server(self, max_tracks):
+        """map_server = std::make_shared<MapServer>() with room for `max_tracks` features per sequence."""
+        self._ck(self.lib.igv_tracks_create(self.h, int(max_tracks)))
+        self.max_tracks = int(max_tracks)
+
+    def reset_map_server(self):
+        self._ck(self.lib.igv_tracks_reset(self.h))
+
+    def collect_meas(self, n_meas, ids, uv):
+        """MapServerManager::collectMonoMeas / collectStereoMeas: one frame message per sequence at the newest clone.
+        n_meas (B,), ids (B,M) uint64 as in feature_tracker/msg/*Meas.msg, uv (B,M,rho)."""
+        a = [_Arg(n_meas, np.int32), _Arg(ids, np.uint64), _Arg(uv, np.float64)]
+        self._set_mode(a)
+        M = int(a[1].keep.shape[1])
+        self._ck(self.lib.igv_tracks_collect(self.h, a[0].ptr, M, a[1].ptr, a[2].ptr))
+
+    def mark_marg_features(self):
+        """MapServerManager::markMargMonoFeatures / markMargStereoFeatures."""
+        self._ck(self.lib.igv_tracks_mark_lost(self.h))
+
+    def gather_tracks(self, rule, selected_slots=(), min_obs=None, dof_fixed=0, n_feats=None, obs_slots=None, out=None):
+        """Track selection of RemoveLostUpdate (rule TRK_LOST) or SwMargUpdate / KeyframeUpdate (TRK_SEEN_AT), emitted
+        in ascending id order in the array layout of triangulate() / msckf_update(). `out`: dict of CUDA tensors
+        (track_entry, n_sel, track_id, obs, mask_all, mask_upd, anchor_slot, chi2_dof, feat_ok) to stay on the device;
+        otherwise host arrays are returned."""
+        F = int(n_feats or self.max_feats)
+        SW = int(obs_slots or self.max_clones)
+        B = self.B
+        if out is None:
+            out = dict(track_entry=np.zeros((B, F), np.int32), n_sel=np.zeros(B, np.int32),
+                       track_id=np.zeros((B, F), np.int32), obs=np.zeros((B, F, SW, self.rho)),
+                       mask_all=np.zeros((B, F, SW), np.uint8), mask_upd=np.zeros((B, F, SW), np.uint8),
+                       anchor_slot=np.zeros((B, F), np.int32), chi2_dof=np.zeros((B, F), np.int32),
+                       feat_ok=np.zeros((B, F), np.uint8))
+        dt = dict(track_entry=np.int32, n_sel=np.int32, track_id=np.int32, obs=np.float64, mask_all=np.uint8,
+                  mask_upd=np.uint8, anchor_slot=np.int32, chi2_dof=np.int32, feat_ok=np.uint8)
+        a = {k: _Arg(out[k], dt[k]) for k in dt}
+        for k in dt:   # outputs must be written in place
+            if a[k].keep is not out[k]:
+                raise ValueError(f"gather_tracks: `{k}` must be a contiguous {dt[k].__name__} array")
+        self._set_mode(list(a.values()))
+        g = capi.igv_track_gather_args()
+        g.rule = int(rule)
+        sel = np.ascontiguousarray(list(selected_slots), dtype=np.int32)
+        g.n_selected = len(sel)
+        g.selected_slots = sel.ctypes.data_as(capi.c_ip) if len(sel) else None
+        g.min_obs = int(min_obs if min_obs is not None else (3 if self.stereo else 4))
+        g.dof_fixed = int(dof_fixed)
+        g.n_feats, g.obs_slots = F, SW
+        for k in dt:
+            setattr(g, k, a[k].ptr)
+        self._ck(self.lib.igv_tracks_gather(self.h, C.byref(g)))
+        return out
+
+    def commit_triangulation(self, track_entry, pf, ok, feat_ok=None):
+        """Second half of FeatureInfoManager::triangulateFeatureInfo*: store landmark values, set _isTri; feat_ok
+        (in/out, optional) &= ok."""
+        a = [_Arg(track_entry, np.int32), _Arg(pf, np.float64), _Arg(ok, np.uint8), _Arg(feat_ok, np.uint8)]
+        if feat_ok is not None and a[3].keep is not feat_ok:
+            raise ValueError("commit_triangulation: feat_ok must be a contiguous uint8 array (updated in place)")
+        self._set_mode(a)
+        F = int(a[0].keep.shape[1])
+        self._ck(self.lib.igv_tracks_commit_tri(self.h, F, a[0].ptr, a[1].ptr, a[2].ptr, a[3].ptr))
+        return feat_ok
+
+    def erase_tracks(self, track_entry):
+        a = [_Arg(track_entry, np.int32)]
+        self._set_mode(a)
+        self._ck(self.lib.igv_tracks_erase(self.h, int(a[0].keep.shape[1]), a[0].ptr))
+
+    def clean_obs_at(self, slots):
+        """SwMargUpdate / KeyframeUpdate ::clean{Mono,Stereo}ObsAtMargTime for the clones at these window slots."""
+        s = np.ascontiguousarray(list(slots), dtype=np.int32)
+        self._ck(self.lib.igv_tracks_clean_obs(self.h, len(s), s.ctypes.data_as(capi.c_ip)))
+
+    def change_msckf_anchor(self, old_slots, min_depth):
+        """changeMSCKFAnchor: SwMargUpdate uses min_depth 0, KeyframeUpdate 0.3."""
+        s = np.ascontiguousarray(list(old_slots), dtype=np.int32)
+        self._ck(self.lib.igv_tracks_change_anchor(self.h, len(s), s.ctypes.data_as(capi.c_ip), float(min_depth)))
+
+    def erase_invalid_features(self, min_depth=0.2):
+        """MapServerManager::eraseInvalidFeatures."""
+        self._ck(self.lib.igv_tracks_erase_invalid(self.h, float(min_depth)))
+
+    def get_map_server(self, obs_slots=None, with_obs=True):
+        """Host dump of the table in entry order (see igv_track_dump)."""
+        B, T = self.B, self.max_tracks
+        SW = int(obs_slots or self.max_clones)
+        out = dict(id=np.zeros((B, T), np.int32), used=np.zeros((B, T), np.uint8), to_marg=np.zeros((B, T), np.uint8),
+                   is_tri=np.zeros((B, T), np.uint8), slot_mask=np.zeros((B, T), np.uint64),
+                   anchor_slot=np.zeros((B, T), np.int32), pf=np.zeros((B, T, 3)), pf_fej=np.zeros((B, T, 3)),
+                   n_tracks=np.zeros(B, np.int32))
+        if with_obs:
+            out["obs"] = np.zeros((B, T, SW, self.rho))
+        self._set_mode([_Arg(out["id"], np.int32)])
+        d = capi.igv_track_dump()
+        d.obs_slots = SW
+        for k, v in out.items():
+            setattr(d, k, C.c_void_p(v.ctypes.data))
+        self._ck(self.lib.igv_tracks_get(self.h, C.byref(d)))
         return out
 
     def flags(self, clear=True):

@@ -315,3 +315,56 @@ def random_ephemerides(rng, B, S, geo=()):
     t_obs = rng.uniform(-3600.0, 3600.0, (B, S))
     psr = rng.uniform(2.0e7, 2.6e7, (B, S))
     return eph, sys, t_obs, psr
+
+
+# ------------------------------------------------------------------------------------------------
+# Tracker messages (the inputs of igv_tracks_collect = feature_tracker/msg/{Mono,Stereo}Frame.msg)
+# ------------------------------------------------------------------------------------------------
+class TrackerStream:
+    """Persistent landmarks seen from a SyntheticStream's true camera: per frame one message per sequence with
+    (id: uint64, u0 v0 [u1 v1]: float64) in shuffled order, tracks being born in front of the camera and dying at random
+    or when they leave the field of view. Open loop and seeded like the stream."""
+
+    def __init__(self, stream: "SyntheticStream", n_tracks: int, meas_stride: int, death_prob=0.12, id_base=0):
+        self.s = stream
+        self.n, self.M = n_tracks, meas_stride
+        self.death = death_prob
+        self.id_base = id_base
+        self.rngs = [np.random.Generator(np.random.PCG64(seed + 77_000)) for seed in stream.seeds]
+        self.lm = [dict() for _ in range(stream.B)]
+        self.next_id = [1] * stream.B
+
+    def message(self, t):
+        B, rho = self.s.B, self.s.wl.rho
+        R, p = self.s.cam_pose(t)
+        n_meas = np.zeros(B, np.int32)
+        ids = np.zeros((B, self.M), np.uint64)
+        uv = np.zeros((B, self.M, rho))
+        for b in range(B):
+            rng, lm = self.rngs[b], self.lm[b]
+            vis = {}
+            for k, x in list(lm.items()):
+                q = R[b].T @ (x - p[b])
+                if q[2] < 1.0 or abs(q[0] / q[2]) > 0.8 or abs(q[1] / q[2]) > 0.8 or rng.random() < self.death:
+                    del lm[k]
+                else:
+                    vis[k] = q
+            while len(lm) < self.n:
+                d = rng.uniform(3.0, 40.0)
+                q = np.array([rng.uniform(-0.45, 0.45) * d, rng.uniform(-0.45, 0.45) * d, d])
+                k = self.next_id[b]
+                self.next_id[b] += 1
+                lm[k] = R[b] @ q + p[b]
+                vis[k] = q
+            keys = list(vis.keys())
+            keys = [keys[i] for i in rng.permutation(len(keys))][:self.M]
+            n_meas[b] = len(keys)
+            for i, k in enumerate(keys):
+                q = vis[k]
+                z = [q[0] / q[2], q[1] / q[2]]
+                if rho == 4:
+                    qr = R_CL2CR @ q + P_CL2CR
+                    z += [qr[0] / qr[2], qr[1] / qr[2]]
+                ids[b, i] = np.uint64(self.id_base + k)
+                uv[b, i] = np.array(z) + rng.normal(0.0, SyntheticStream.obs_noise, rho)
+        return n_meas, ids, uv

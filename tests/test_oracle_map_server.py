@@ -1,0 +1,107 @@
+"""Pins oracle/ingvio_oracle/map_server.py with the reference's own test of this code:
+/root/reference/ingvio_estimator/test/TestMapServer.cpp:184-308 (TEST_F(TestMapServer, collectFeatureAndMarg)),
+restated 1:1 for the mono and the stereo message, and runs the same assertions against the track-table kernels
+(CPU-emulated here; tests/test_gpu_tracks.py repeats them on the device)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import ingvio_oracle as o
+from ingvio_oracle import map_server as oms
+from ingvio_oracle.types import SE3
+from ingvio_oracle.visual_update import MSCKF
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+
+
+def _augment(state, t, rng):
+    """propagateToExpectedPoseAndAugment(state, t, T) as far as the map server sees it: a clone at timestamp t."""
+    c = SE3()
+    w = rng.standard_normal(3)
+    c.set_value(o.gamma_func(w, 0), rng.standard_normal(3))
+    state.sw_camleft_poses[t] = c
+    state.timestamp = t
+    return c
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_collect_feature_and_marg(stereo):
+    rng = np.random.default_rng(5)
+    rho = 4 if stereo else 2
+    state = o.State(o.FilterParams(max_sw_clones=5, enable_gnss=0, cam_nums=2 if stereo else 1))
+    ms = oms.MapServer()
+    id1 = [i + 1 for i in range(4)]                                # TestMapServer.cpp:186-188
+    id2 = [i + 2 for i in range(4)]                                # :190-192
+    _augment(state, 2.0, rng)                                      # :201
+    oms.collect_meas(ms, state, id1, rng.uniform(-1, 1, (4, rho)), stereo)   # :203
+    assert len(ms) == 4                                            # :205
+    nframes = (lambda f: f.num_of_stereo_frames()) if stereo else (lambda f: f.num_of_mono_frames())
+    obs = (lambda f: f.stereo_obs) if stereo else (lambda f: f.mono_obs)
+    for i in range(1, 5):                                          # :207-213
+        assert ms[i].id == i and ms[i].ftype == MSCKF and nframes(ms[i]) == 1 and 2.0 in obs(ms[i])
+    _augment(state, 4.0, rng)                                      # :215
+    oms.collect_meas(ms, state, id2, rng.uniform(-1, 1, (4, rho)), stereo)   # :217
+    assert len(ms) == 5                                            # :219
+    for i in range(1, 6):                                          # :221-234
+        assert ms[i].id == i and ms[i].ftype == MSCKF
+        assert nframes(ms[i]) == (1 if i in (1, 5) else 2)
+        if i > 1:
+            assert 4.0 in obs(ms[i])
+        assert not ms[i].is_to_marg
+    oms.mark_marg_features(ms, state, stereo)                      # :236
+    assert len(ms) == 5                                            # :238
+    for i in range(1, 6):                                          # :240-246
+        assert ms[i].is_to_marg == (i == 1)
+    for i in range(1, 6):                                          # :300-306 (anchors: first observation's clone)
+        assert ms[i].anchor is state.sw_camleft_poses[2.0 if i < 5 else 4.0]
+
+
+def test_message_id_narrowing():
+    """`int _id = msg.id` with a uint64 message id (MapServer.cpp:24, MapServer.h:120)."""
+    assert oms.msg_id_to_key(7) == 7
+    assert oms.msg_id_to_key((1 << 32) + 7) == 7
+    assert oms.msg_id_to_key(0x80000000) == -(1 << 31)
+    assert oms.msg_id_to_key(0xFFFFFFFF) == -1
+
+
+def run_reference_test_on_table(tab, augment, stereo):
+    """The assertions of TestMapServer.cpp:184-308 against a backend with BatchFilter's track-table methods (B = 1)."""
+    rng = np.random.default_rng(6)
+    rho = 4 if stereo else 2
+    ids = np.zeros((1, 4), np.uint64)
+    R = np.eye(3)[None]
+    augment(R, np.zeros((1, 3)))
+    ids[0] = [1, 2, 3, 4]
+    tab.collect_meas(np.array([4], np.int32), ids, rng.uniform(-1, 1, (1, 4, rho)))
+    d = tab.get_map_server(obs_slots=tab.max_clones)
+    u = d["used"][0] == 1
+    assert d["n_tracks"][0] == 4 and sorted(d["id"][0][u].tolist()) == [1, 2, 3, 4]
+    assert np.all(d["slot_mask"][0][u] == 1) and np.all(d["anchor_slot"][0][u] == 0)
+    augment(R, np.ones((1, 3)))
+    ids[0] = [2, 3, 4, 5]
+    tab.collect_meas(np.array([4], np.int32), ids, rng.uniform(-1, 1, (1, 4, rho)))
+    tab.mark_marg_features()
+    d = tab.get_map_server(obs_slots=tab.max_clones)
+    u = d["used"][0] == 1
+    assert d["n_tracks"][0] == 5
+    by_id = {int(i): k for k, i in enumerate(d["id"][0]) if d["used"][0][k]}
+    for i in range(1, 6):
+        k = by_id[i]
+        nobs = bin(int(d["slot_mask"][0][k])).count("1")
+        assert nobs == (1 if i in (1, 5) else 2)
+        if i > 1:
+            assert (int(d["slot_mask"][0][k]) >> 1) & 1
+        assert d["to_marg"][0][k] == (1 if i == 1 else 0)
+        assert d["anchor_slot"][0][k] == (0 if i < 5 else 1)
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_reference_test_on_emulated_kernels(stereo):
+    from trk_emul import EmulatedTrackTable
+    tab = EmulatedTrackTable(1, 4, 8, 16, stereo)
+    try:
+        run_reference_test_on_table(tab, tab.augment, stereo)
+    finally:
+        tab.close()
