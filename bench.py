@@ -256,6 +256,82 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def track_table_extra(wl, B, dev, ts, local, rank):
+    """Extra (outside the metric): the device track table fed with tracker messages of wl.feats measurements
+    per frame (15 % of the tracks replaced every frame, shuffled order), steady-state window. Times, per frame, the calls
+    that replace the MapServer bookkeeping: collect, mark-lost, the two track selections (lost / seen-at), clean,
+    re-anchor, erase-invalid. Triangulation and the updates themselves are measured elsewhere."""
+    import torch
+    from ingvio_b200 import capi
+    from ingvio_b200.filter import BatchFilter
+    M, SW, T = wl.feats, wl.sw, 4 * wl.feats
+    rng = np.random.default_rng(99 + rank)
+    g = BatchFilter(B, SW, max(M, 1), 1, stereo=wl.stereo, stream=ts.cuda_stream, device=local)
+    try:
+        eye = np.tile(np.eye(3).reshape(1, 9), (B, 1))
+        z = np.zeros((B, 3))
+        g.init_state_and_cov(eye, z, z, z, z, eye, z, np.full(21, 1e-2))
+        g.create_map_server(T)
+        n_frames = SW + 6
+        cur = np.tile(np.arange(1, M + 1, dtype=np.uint64), (B, 1))
+        nxt = M + 1
+        msgs = []
+        for _ in range(n_frames):
+            repl = rng.random((B, M)) < 0.15
+            fresh = (nxt + np.arange(M, dtype=np.uint64))[None, :].repeat(B, 0)
+            nxt += M
+            cur = np.where(repl, fresh, cur)
+            perm = rng.permuted(np.tile(np.arange(M), (B, 1)), axis=1)
+            ids = np.take_along_axis(cur, perm, 1)
+            msgs.append((torch.full((B,), M, dtype=torch.int32, device=dev), torch.from_numpy(ids.astype(np.int64)).to(dev),
+                         torch.from_numpy(rng.standard_normal((B, M, wl.rho)) * 0.3).to(dev)))
+        F = max(M, 1)
+        z_ = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
+        out = dict(track_entry=z_((B, F), torch.int32), n_sel=z_((B,), torch.int32), track_id=z_((B, F), torch.int32),
+                   obs=z_((B, F, SW, wl.rho), torch.float64), mask_all=z_((B, F, SW), torch.uint8),
+                   mask_upd=z_((B, F, SW), torch.uint8), anchor_slot=z_((B, F), torch.int32),
+                   chi2_dof=z_((B, F), torch.int32), feat_ok=z_((B, F), torch.uint8))
+        Rd = torch.from_numpy(eye).to(dev)
+        torch.cuda.synchronize(dev)
+        ms_total, timed = 0.0, 0
+        lost_acc, seen_acc = z_((B,), torch.int32), z_((B,), torch.int32)   # same stream as the handle: ordered
+        for k, (n_d, ids_d, uv_d) in enumerate(msgs):
+            pd = torch.from_numpy(np.tile(np.array([0.3 * k, 0.0, 0.0]), (B, 1))).to(dev)
+            torch.cuda.synchronize(dev)
+            g.augment_sliding_window_pose_cov(Rd, Rd, pd)
+            full = g.num_clones() >= SW
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            g.collect_meas(n_d, ids_d, uv_d)
+            g.mark_marg_features()
+            g.gather_tracks(capi.TRK_LOST, n_feats=F, obs_slots=SW, out=out)
+            if full:
+                lost_acc.add_(out["n_sel"])
+            g.erase_tracks(out["track_entry"])
+            if full:
+                g.gather_tracks(capi.TRK_SEEN_AT, selected_slots=[0, SW // 2], n_feats=F, obs_slots=SW, out=out)
+                seen_acc.add_(out["n_sel"])
+                g.clean_obs_at([0])
+                g.change_msckf_anchor([0], 0.0)
+            g.erase_invalid_features(0.2)
+            e1.record(ts)
+            torch.cuda.synchronize(dev)
+            if full:
+                g.marg_sliding_window_pose(0)
+                if k >= SW + 1:
+                    ms_total += e0.elapsed_time(e1)
+                    timed += 1
+        ms = ms_total / max(1, timed)
+        nf = max(1, (n_frames - SW + 1) * B)
+        lost, seen = int(lost_acc.sum().item()), int(seen_acc.sum().item())
+        return {"ms_per_step": ms, "measurements_per_sec": B * M / (ms * 1e-3), "tracks_table_entries": T,
+                "lost_per_frame": lost / nf, "seen_at_per_frame": seen / nf,
+                "note": "igv_tracks_collect + mark_lost + gather(lost) + erase + gather(seen-at) + clean_obs + change_anchor + "
+                        "erase_invalid per frame, device pointers; outside the metric (SURVEY 8f-4)"}
+    finally:
+        g.close()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -555,6 +631,13 @@ def main():
         line["gnss_frontend_extra"] = {"ms_per_step": gfe_ms, "satellites_per_sec": B * wl.sats / (gfe_ms * 1e-3),
                                        "note": "igv_sat_states + igv_gnss_residuals on synthetic ephemerides; outside the "
                                                "metric (SURVEY 8f-2)"}
+
+    if rank == 0 and world == 1 and not args.no_latency and wl.feats > 0:
+        try:
+            with torch.cuda.stream(ts):
+                line["track_table_extra"] = track_table_extra(wl, B, dev, ts, local, rank)
+        except Exception as e:   # an extra must never cost the bench line
+            line["track_table_extra"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0 and world == 1 and not args.no_latency:
         # single-sequence latency (BASELINE configs[1] as one filter): B = 1 handle, row-split QR
