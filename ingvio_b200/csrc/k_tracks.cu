@@ -38,47 +38,72 @@ __global__ void k_trk_reset(TrkPtrs p) {
   for (int i = 0; i < 3; ++i) { p.pf[3 * g + i] = 0.0; p.pf_fej[3 * g + i] = 0.0; }
 }
 
-// One CTA per sequence. Phases: (1) table ids + message ids to shared memory; (2) per measurement: first occurrence
-// of its id in the message? existing entry?; (3) warp 0 hands free entries to the new ids in message order;
-// (4) per measurement: write the observation (at most one writer per entry after (2)).
+// Dynamic shared memory of k_trk_collect / k_trk_gather (also used by tests/emul, so the two cannot drift apart).
+inline size_t trk_collect_smem(int T, int M) { return sizeof(int) * (3 * (size_t)T + 2 * (size_t)M) + (size_t)M; }
+inline size_t trk_gather_smem(int T, int F) {
+  return sizeof(int) * (2 * (size_t)T + (((size_t)F + 1) & ~size_t(1))) + sizeof(unsigned long long) * (size_t)F;
+}
+
+// One CTA per sequence. Phases: (1) warp 0 compacts the table into a list of used entries (id, entry) and a list of
+// free entries with ballots, the other warps bring the message ids to shared memory; (2) per measurement: first
+// occurrence of its id in the message? existing entry? -- both loops are branch-free with warp-uniform trip counts
+// (a `break` here lets the lanes of a warp drift apart for good: the first version of this kernel spent 0.7 ms in
+// 32 serialised copies of the scan, profiles/r01_track_table.md); (3) warp 0 hands free entries to the new ids in
+// message order; (4) per measurement: write the observation (at most one writer per entry after (2)).
 __global__ void __launch_bounds__(256) k_trk_collect(TrkPtrs p, IgvTrkCols cols, const int* __restrict__ n_meas, int M,
                                                      const unsigned long long* __restrict__ ids,
                                                      const double* __restrict__ uv) {
   IGV_DYN_SMEM(int, smem_i);
-  int* s_id = smem_i;                 // T
-  int* s_free = s_id + p.T;           // T
-  int* s_mid = s_free + p.T;          // M
-  int* s_slot = s_mid + M;            // M
-  unsigned char* s_used = reinterpret_cast<unsigned char*>(s_slot + M);  // T
-  unsigned char* s_flag = s_used + p.T;                                   // M
+  int* s_uid = smem_i;                // T   ids of the used entries, compacted
+  int* s_ut = s_uid + p.T;            // T   their table entries
+  int* s_free = s_ut + p.T;           // T   free entries, ascending
+  int* s_mid = s_free + p.T;          // M   message ids narrowed to int
+  int* s_slot = s_mid + M;            // M   table entry of each measurement (-1: none)
+  unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_slot + M);   // M   bit 0: first occurrence, bit 1: new id
+  __shared__ int s_nused, s_nfree;
   const int b = blockIdx.x, tid = threadIdx.x;
   const long tb = (long)b * p.T;
   int n = n_meas[b];
   n = n < 0 ? 0 : (n > M ? M : n);
-  for (int t = tid; t < p.T; t += blockDim.x) { s_id[t] = p.id[tb + t]; s_used[t] = p.st[tb + t] & IGV_TRK_USED; }
-  for (int i = tid; i < n; i += blockDim.x) s_mid[i] = narrow_id(ids[(long)b * M + i]);
+  if (tid < 32) {
+    const unsigned lt = (1u << tid) - 1u;
+    int nused = 0, nfree = 0;
+    for (int t0 = 0; t0 < p.T; t0 += 32) {
+      const int t = t0 + tid;
+      const bool in = t < p.T;
+      const bool us = in && (p.st[tb + t] & IGV_TRK_USED);
+      const unsigned mu = __ballot_sync(0xffffffffu, us);
+      const unsigned mf = __ballot_sync(0xffffffffu, in && !us);
+      if (us) { const int k = nused + __popc(mu & lt); s_uid[k] = p.id[tb + t]; s_ut[k] = t; }
+      if (in && !us) s_free[nfree + __popc(mf & lt)] = t;
+      nused += __popc(mu);
+      nfree += __popc(mf);
+    }
+    if (tid == 0) { s_nused = nused; s_nfree = nfree; }
+  } else {
+    for (int i = tid - 32; i < n; i += blockDim.x - 32) s_mid[i] = narrow_id(ids[(long)b * M + i]);
+  }
   __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {
-    const int mid = s_mid[i];
-    int eff = 1;
-    for (int j = 0; j < i; ++j) if (s_mid[j] == mid) { eff = 0; break; }
+  const int nused = s_nused, nfree = s_nfree;
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + tid;
+    const bool act = i < n;
+    const int mid = act ? s_mid[i] : 0;
+    const int jend = min(n, (i | 31) + 1);          // warp-uniform: the largest i of this warp, + 1
+    int dup = 0;
+    for (int j = 0; j < jend; ++j) dup |= (j < i && s_mid[j] == mid) ? 1 : 0;
     int slot = -1;
-    if (eff) for (int t = 0; t < p.T; ++t) if (s_used[t] && s_id[t] == mid) { slot = t; break; }
-    s_slot[i] = slot;
-    s_flag[i] = (unsigned char)(eff | ((eff && slot < 0) ? 2 : 0));
+    for (int k = 0; k < nused; ++k) slot = (s_uid[k] == mid) ? s_ut[k] : slot;   // ids are unique in the table
+    if (act) {
+      const int eff = dup ? 0 : 1;
+      if (!eff) slot = -1;
+      s_slot[i] = slot;
+      s_flag[i] = (unsigned char)(eff | ((eff && slot < 0) ? 2 : 0));
+    }
   }
   __syncthreads();
   if (tid < 32) {
     const unsigned lt = (1u << tid) - 1u;
-    int nfree = 0;
-    for (int t0 = 0; t0 < p.T; t0 += 32) {
-      const int t = t0 + tid;
-      const bool fr = t < p.T && !s_used[t];
-      const unsigned m = __ballot_sync(0xffffffffu, fr);
-      if (fr) s_free[nfree + __popc(m & lt)] = t;
-      nfree += __popc(m);
-    }
-    __syncwarp();
     int nnew = 0;
     bool over = false;
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -397,7 +422,7 @@ void igv_launch_trk_collect(igv_batch* h, const int* n_meas, int meas_stride, co
                             const double* uv) {
   IgvProfScope prof_scope_(h, IGV_K_OTHER);
   const int T = h->trk.T, M = meas_stride;
-  const size_t smem = sizeof(int) * (2 * (size_t)T + 2 * (size_t)M) + (size_t)T + (size_t)M;
+  const size_t smem = trk_collect_smem(T, M);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaFuncSetAttribute(k_trk_collect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -415,8 +440,7 @@ void igv_launch_trk_mark_lost(igv_batch* h) {
 
 void igv_launch_trk_gather(igv_batch* h, const IgvTrkGatherLaunch& g) {
   IgvProfScope prof_scope_(h, IGV_K_OTHER);
-  const size_t smem = sizeof(int) * (2 * (size_t)h->trk.T + (((size_t)g.F + 1) & ~size_t(1))) +
-                      sizeof(unsigned long long) * (size_t)g.F;
+  const size_t smem = trk_gather_smem(h->trk.T, g.F);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaFuncSetAttribute(k_trk_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

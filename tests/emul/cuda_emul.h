@@ -99,6 +99,9 @@ inline int __shfl_down_sync(unsigned, int v, int delta) {
   const int src = lane + delta < 32 ? lane + delta : lane;
   return (int)emul::exchange((unsigned long long)(unsigned)v, src);
 }
+#include <algorithm>
+using std::min;
+using std::max;
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

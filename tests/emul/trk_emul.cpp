@@ -60,7 +60,7 @@ void emu_collect(void* h, const int* n_meas, int M, const unsigned long long* id
   Emu* e = static_cast<Emu*>(h);
   TrkPtrs p = e->ptrs();
   IgvTrkCols c = igv_trk_cols(e->trk);
-  const size_t smem = sizeof(int) * (2 * (size_t)e->T + 2 * (size_t)M) + (size_t)e->T + (size_t)M;
+  const size_t smem = trk_collect_smem(e->T, M);
   emul::launch(e->B, 256, smem, [&] { k_trk_collect(p, c, n_meas, M, ids, uv); });
 }
 void emu_mark_lost(void* h) {
@@ -80,7 +80,7 @@ int emu_gather(void* h, int rule, int n_selected, const int* selected_slots, int
   g.anchor_slot = anchor_slot; g.dof = dof; g.feat_ok = feat_ok;
   TrkPtrs p = e->ptrs();
   IgvTrkCols c = igv_trk_cols(e->trk);
-  const size_t smem = sizeof(int) * (2 * (size_t)e->T + (((size_t)F + 1) & ~size_t(1))) + sizeof(unsigned long long) * (size_t)F;
+  const size_t smem = trk_gather_smem(e->T, F);
   emul::launch(e->B, 256, smem, [&] { k_trk_gather(p, c, g); });
   return 0;
 }
