@@ -164,10 +164,9 @@ def _check_gather(g, b, e, what):
     assert not g["obs"][b, n:].any(), what
 
 
-def check_tables(backend, orc, SW, what, pf_tol=0.0):
-    d = backend.get_map_server(obs_slots=SW)
-    for b in range(orc.B):
-        snap = oms.table_snapshot(orc.maps[b], orc.states[b], orc.stereo, SW)
+def compare_tables(d, snaps, SW, what, pf_tol=0.0):
+    """Backend dump `d` (igv_tracks_get layout) against per-sequence canonical snapshots (oracle or golden)."""
+    for b, snap in enumerate(snaps):
         used = d["used"][b].astype(bool)
         assert d["n_tracks"][b] == used.sum() == len(snap["id"]), (what, b, d["n_tracks"][b], used.sum(), len(snap["id"]))
         order = np.argsort(d["id"][b][used], kind="stable")
@@ -187,6 +186,13 @@ def check_tables(backend, orc, SW, what, pf_tol=0.0):
         assert not d["slot_mask"][b][~used].any() and np.all(d["anchor_slot"][b][~used] == -1), (what, b)
 
 
+def check_tables(backend, orc, SW, what, pf_tol=0.0, rec=None):
+    snaps = [oms.table_snapshot(orc.maps[b], orc.states[b], orc.stereo, SW) for b in range(orc.B)]
+    if rec is not None:
+        rec.append(("tables", dict(SW=SW, snaps=snaps)))
+    compare_tables(backend.get_map_server(obs_slots=SW), snaps, SW, what, pf_tol)
+
+
 def _triangulate_gathered(orc, backend_poses, g, b, n, stereo):
     """Oracle triangulation of the gathered arrays of sequence b (what igv_triangulate computes on the device)."""
     F = g["obs"].shape[1]
@@ -202,9 +208,12 @@ def _triangulate_gathered(orc, backend_poses, g, b, n, stereo):
 
 
 def run_scenario(backend, augment, marg, clone_poses, mode, B, SW, stereo, frames, seed, F, pf_tol=0.0,
-                 meas_target=14, meas_stride=24):
+                 meas_target=14, meas_stride=24, rec=None):
     """backend: object with BatchFilter's track-table methods. augment(R,p) / marg(slot) / clone_poses(b) are supplied
     by the caller (emulated window or real filter). mode: "sw_marg" | "keyframe". Returns simple coverage counters."""
+    # rec: optional list that receives every input and every oracle expectation, in order
+    # (tests/golden/make_golden_tracks.py stores it; replay() feeds it to a backend without the oracle)
+    R_ = (lambda kind, **kw: rec.append((kind, kw))) if rec is not None else (lambda kind, **kw: None)
     rho = 4 if stereo else 2
     world = World(seed, B, stereo, meas_target, meas_stride)
     orc = OracleSide(B, SW, stereo)
@@ -216,39 +225,45 @@ def run_scenario(backend, augment, marg, clone_poses, mode, B, SW, stereo, frame
         augment(R, p)
         orc.augment(R, p)
         n_meas, ids, uv = world.message()
+        R_("augment", R=R, p=p)
+        R_("collect", n_meas=n_meas, ids=ids, uv=uv)
         backend.collect_meas(n_meas, ids, uv)
         for b in range(B):
             oms.collect_meas(orc.maps[b], orc.states[b], ids[b, :n_meas[b]], uv[b, :n_meas[b]], stereo)
             cov["dup_frames"] += int(len(set(ids[b, :n_meas[b]].tolist())) < n_meas[b])
-        check_tables(backend, orc, cap, f"frame {k} collect", pf_tol)
+        check_tables(backend, orc, cap, f"frame {k} collect", pf_tol, rec)
 
         # ---- RemoveLostUpdate::updateState* : track selection, triangulation, erase -----------------------------
         backend.mark_marg_features()
         g = backend.gather_tracks(TRK_LOST, n_feats=F, obs_slots=cap)
         pf = np.zeros((B, F, 3))
         ok = np.zeros((B, F), np.uint8)
-        exp_update = []
+        exp_update, exp_g = [], []
         for b in range(B):
             ms, st = orc.maps[b], orc.states[b]
             oms.mark_marg_features(ms, st, stereo)
             keys = [key for key in ms.ids() if ms[key].is_to_marg]
             e = _expected_gather(ms, st, keys, stereo, cap, rho, TRK_LOST, (), 0, min_obs)
+            exp_g.append(e)
             _check_gather(g, b, e, f"frame {k} gather lost")
             pf[b], ok[b] = _triangulate_gathered(orc, clone_poses(b), g, b, len(keys), stereo)
             upd = oms.select_lost(ms, orc.tri, st, stereo)
             exp_update.append(upd)
             cov["lost"] += len(keys)
             cov["lost_ok"] += len(upd)
+        R_("mark_gather", rule=TRK_LOST, sel_slots=[], dof_fixed=0, F=F, SW=cap, expect=exp_g)
+        R_("commit", pf=pf, ok=ok, expect_update=exp_update)
         feat_ok = g["feat_ok"].copy()
         backend.commit_triangulation(g["track_entry"], pf, ok, feat_ok)
         for b in range(B):
             got = [int(g["track_id"][b, f]) for f in range(int(g["n_sel"][b])) if feat_ok[b, f]]
             assert got == exp_update[b], (k, b, got, exp_update[b])
+        R_("erase")
         backend.erase_tracks(g["track_entry"])
         for b in range(B):
             for key in exp_update[b]:
                 del orc.maps[b][key]
-        check_tables(backend, orc, cap, f"frame {k} remove-lost", pf_tol)
+        check_tables(backend, orc, cap, f"frame {k} remove-lost", pf_tol, rec)
 
         # ---- SwMargUpdate / KeyframeUpdate : selected clones ------------------------------------------------------
         st0 = orc.states[0]
@@ -270,49 +285,100 @@ def run_scenario(backend, augment, marg, clone_poses, mode, B, SW, stereo, frame
             g = backend.gather_tracks(TRK_SEEN_AT, selected_slots=sel_slots, dof_fixed=dof_fixed, n_feats=F, obs_slots=cap)
             pf = np.zeros((B, F, 3))
             ok = np.zeros((B, F), np.uint8)
-            exp_update = []
+            exp_update, exp_g = [], []
             for b in range(B):
                 ms, st = orc.maps[b], orc.states[b]
                 obs_of = (lambda f: f.stereo_obs) if stereo else (lambda f: f.mono_obs)
                 keys = [key for key in ms.ids() if all(t in obs_of(ms[key]) for t in sel_ts)]
                 e = _expected_gather(ms, st, keys, stereo, cap, rho, TRK_SEEN_AT, sel_ts, dof_fixed, min_obs)
+                exp_g.append(e)
                 _check_gather(g, b, e, f"frame {k} gather seen-at")
                 pf[b], ok[b] = _triangulate_gathered(orc, clone_poses(b), g, b, len(keys), stereo)
                 upd = oms.select_seen_at(ms, orc.tri, st, sel_ts, stereo)
                 exp_update.append(upd)
                 cov["seen"] += len(keys)
                 cov["seen_ok"] += len(upd)
+            R_("gather", rule=TRK_SEEN_AT, sel_slots=sel_slots, dof_fixed=dof_fixed, F=F, SW=cap, expect=exp_g)
+            R_("commit", pf=pf, ok=ok, expect_update=exp_update)
             feat_ok = g["feat_ok"].copy()
             backend.commit_triangulation(g["track_entry"], pf, ok, feat_ok)
             for b in range(B):
                 got = [int(g["track_id"][b, f]) for f in range(int(g["n_sel"][b])) if feat_ok[b, f]]
                 assert got == exp_update[b], (k, b, got, exp_update[b])
-            check_tables(backend, orc, cap, f"frame {k} selected update", pf_tol)
+            check_tables(backend, orc, cap, f"frame {k} selected update", pf_tol, rec)
 
             # clean*ObsAtMargTime -> changeMSCKFAnchor -> margSwPose
+            R_("clean", slots=marg_slots)
             backend.clean_obs_at(marg_slots)
             for b in range(B):
                 oms.clean_obs_at(orc.maps[b], marg_ts, stereo)
-            check_tables(backend, orc, cap, f"frame {k} clean", pf_tol)
+            check_tables(backend, orc, cap, f"frame {k} clean", pf_tol, rec)
+            R_("anchor", slots=marg_slots, thr=depth_thr)
             backend.change_msckf_anchor(marg_slots, depth_thr)
             for b in range(B):
                 before = {key: f.anchor for key, f in orc.maps[b].items()}
                 oms.change_msckf_anchor(orc.maps[b], orc.states[b], marg_ts, depth_thr)
                 cov["reanchored"] += sum(1 for key, f in orc.maps[b].items() if f.anchor is not before[key])
-            check_tables(backend, orc, cap, f"frame {k} change anchor", pf_tol)
+            check_tables(backend, orc, cap, f"frame {k} change anchor", pf_tol, rec)
+            R_("marg", slots=sorted(marg_slots, reverse=True))
             for s in sorted(marg_slots, reverse=True):
                 marg(s)
             for b in range(B):
                 orc.marg_times(b, marg_ts)
-            check_tables(backend, orc, cap, f"frame {k} marg", pf_tol)
+            check_tables(backend, orc, cap, f"frame {k} marg", pf_tol, rec)
 
         # ---- eraseInvalidFeatures -----------------------------------------------------------------------------------
+        R_("erase_invalid", thr=0.2)
         backend.erase_invalid_features(0.2)
         for b in range(B):
             n0 = len(orc.maps[b])
             oms.erase_invalid_features(orc.maps[b], 0.2)
             cov["erased_invalid"] += n0 - len(orc.maps[b])
             cov["max_tracks"] = max(cov["max_tracks"], len(orc.maps[b]))
-        check_tables(backend, orc, cap, f"frame {k} erase invalid", pf_tol)
+        check_tables(backend, orc, cap, f"frame {k} erase invalid", pf_tol, rec)
         assert not backend.flags(clear=True).any()
     return cov
+
+
+def replay(backend, augment, marg, events, pf_tol=0.0):
+    """Feeds a recorded scenario (inputs + oracle expectations, tests/golden/tracks_*.pkl.gz) to a backend; no oracle."""
+    g = None
+    n_checks = 0
+    for i, (kind, kw) in enumerate(events):
+        what = f"event {i} {kind}"
+        if kind == "augment":
+            augment(kw["R"], kw["p"])
+        elif kind == "collect":
+            backend.collect_meas(kw["n_meas"], kw["ids"], kw["uv"])
+        elif kind in ("mark_gather", "gather"):
+            if kind == "mark_gather":
+                backend.mark_marg_features()
+            g = backend.gather_tracks(kw["rule"], selected_slots=kw["sel_slots"], dof_fixed=kw["dof_fixed"], n_feats=kw["F"],
+                                      obs_slots=kw["SW"])
+            for b, e in enumerate(kw["expect"]):
+                _check_gather(g, b, e, what)
+            n_checks += 1
+        elif kind == "commit":
+            feat_ok = g["feat_ok"].copy()
+            backend.commit_triangulation(g["track_entry"], kw["pf"], kw["ok"], feat_ok)
+            for b, exp in enumerate(kw["expect_update"]):
+                got = [int(g["track_id"][b, f]) for f in range(int(g["n_sel"][b])) if feat_ok[b, f]]
+                assert got == exp, (what, b, got, exp)
+        elif kind == "erase":
+            backend.erase_tracks(g["track_entry"])
+        elif kind == "clean":
+            backend.clean_obs_at(kw["slots"])
+        elif kind == "anchor":
+            backend.change_msckf_anchor(kw["slots"], kw["thr"])
+        elif kind == "marg":
+            for s in kw["slots"]:
+                marg(s)
+        elif kind == "erase_invalid":
+            backend.erase_invalid_features(kw["thr"])
+        elif kind == "tables":
+            compare_tables(backend.get_map_server(obs_slots=kw["SW"]), kw["snaps"], kw["SW"], what, pf_tol)
+            n_checks += 1
+        else:
+            raise ValueError(kind)
+    assert not backend.flags(clear=True).any()
+    return n_checks
