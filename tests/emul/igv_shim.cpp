@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE: the subset of the C-ABI (include/ingvio_b200.h) that the C++ map-server mirror
+// (ingvio_b200/host/ingvio_map_server.hpp) calls, backed by the track-table kernel source executed on the CPU
+// (tests/emul/trk_emul.cpp). It exists so that tests/cpp/test_map_server_mirror.cpp -- the reference's MapServer gtest
+// restated against the mirror -- can check the mirror's own logic on a machine without a GPU; the GPU test links the same
+// source against libingvio_b200.so. Covariance / mean algebra is NOT provided here (those entry points are exercised on the
+// GPU only); B = 1.
+#include "trk_emul.cpp"
+
+// The opaque handle of the C-ABI is the library's own igv_batch (igv_internal.h; cfg / err / launches are reused), extended
+// by what the shim needs. No CUDA call is ever made on it.
+struct Shim : igv_batch {
+  void* emu = nullptr;           // created by igv_tracks_create (the table size is not known before)
+  int n_clones = 0;
+  std::vector<double> Xh;        // mean mirror: only the clone poses are kept
+};
+static Shim* S(igv_batch* h) { return static_cast<Shim*>(h); }
+static const Shim* S(const igv_batch* h) { return static_cast<const Shim*>(h); }
+
+extern "C" {
+
+igv_status igv_create(const igv_config* cfg, igv_batch** out) {
+  if (!cfg || !out || cfg->batch != 1) return IGV_ERR_INVALID;
+  Shim* h = new Shim();
+  h->cfg = *cfg;
+  h->Xh.assign(IGV_X_CORE + 12 * (size_t)cfg->max_clones, 0.0);
+  *out = h;
+  return IGV_OK;
+}
+igv_status igv_destroy(igv_batch* hb) {
+  Shim* h = S(hb);
+  if (h) { if (h->emu) emu_destroy(h->emu); delete h; }
+  return IGV_OK;
+}
+const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "null handle"; }
+long long igv_launch_count(const igv_batch* h) { return h ? h->launches : 0; }
+igv_status igv_set_params(igv_batch*, const igv_params*) { return IGV_OK; }
+igv_status igv_state_init(igv_batch* hb, const double*, const double*, const double*, const double*, const double*,
+                          const double*, const double*, const double*) {
+  Shim* h = S(hb);
+  if (!h) return IGV_ERR_INVALID;
+  h->n_clones = 0;
+  if (h->emu) {   // a new State starts with an empty map (igv_api.cu: igv_state_init)
+    Emu* e = static_cast<Emu*>(h->emu);
+    e->trk.col_of_slot.clear();
+    TrkPtrs p = e->ptrs();
+    emul::launch(e->per_track_grid(), 256, 0, [&] { k_trk_reset(p); });
+  }
+  ++h->launches;
+  return IGV_OK;
+}
+int igv_dim(const igv_batch* h) { return h ? 21 + 6 * S(h)->n_clones : -1; }
+igv_status igv_augment_clone_cov(igv_batch* hb, const double*, const double* clone_R, const double* clone_p) {
+  Shim* h = S(hb);
+  if (!h) return IGV_ERR_INVALID;
+  if (h->n_clones >= h->cfg.max_clones) { h->err = "sliding window is full"; return IGV_ERR_CAPACITY; }
+  double* c = h->Xh.data() + IGV_X_CORE + 12 * h->n_clones;
+  for (int i = 0; i < 9; ++i) c[i] = clone_R ? clone_R[i] : 0.0;
+  for (int i = 0; i < 3; ++i) c[9 + i] = clone_p ? clone_p[i] : 0.0;
+  ++h->n_clones;
+  if (h->emu) emu_on_augment(h->emu);
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_marginalize(igv_batch* hb, int idx) {
+  Shim* h = S(hb);
+  if (!h) return IGV_ERR_INVALID;
+  const int slot = (idx - 21) / 6;
+  if (idx < 21 || (idx - 21) % 6 != 0 || slot >= h->n_clones) { h->err = "Marg is not in the current state"; return IGV_ERR_STATE; }
+  if (h->emu) emu_on_marg(h->emu, slot);
+  double* base = h->Xh.data() + IGV_X_CORE;
+  for (int s = slot; s + 1 < h->n_clones; ++s) std::memcpy(base + 12 * s, base + 12 * (s + 1), sizeof(double) * 12);
+  --h->n_clones;
+  ++h->launches;
+  return IGV_OK;
+}
+int igv_tracks_capacity(const igv_batch* h) { return (h && S(h)->emu) ? static_cast<Emu*>(S(h)->emu)->T : 0; }
+igv_status igv_tracks_create(igv_batch* hb, int max_tracks) {
+  Shim* h = S(hb);
+  if (!h || max_tracks < 1 || max_tracks > 4096) return IGV_ERR_INVALID;
+  if (h->emu) { h->err = "track table already created"; return IGV_ERR_STATE; }
+  h->emu = emu_create(1, max_tracks, h->cfg.max_clones, h->cfg.stereo ? 4 : 2, (int)h->Xh.size());
+  for (int s = 0; s < h->n_clones; ++s) emu_on_augment(h->emu);   // igv_tracks_create: existing clones take columns 0..n-1
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_collect(igv_batch* hb, const int* n_meas, int meas_stride, const unsigned long long* ids, const double* uv) {
+  Shim* h = S(hb);
+  if (!h || !h->emu) { if (h) h->err = "track table not created (igv_tracks_create)"; return IGV_ERR_STATE; }
+  if (!n_meas || meas_stride < 0 || meas_stride > 4096) return IGV_ERR_INVALID;
+  if (meas_stride == 0) return IGV_OK;
+  if (h->n_clones == 0) { h->err = "[FeatureInfoManager]: Meas timestamp not in sw!"; return IGV_ERR_STATE; }
+  emu_collect(h->emu, n_meas, meas_stride, ids, uv);
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_mark_lost(igv_batch* hb) {
+  Shim* h = S(hb);
+  if (!h || !h->emu) return IGV_ERR_STATE;
+  emu_mark_lost(h->emu);
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_erase_invalid(igv_batch* hb, double min_depth) {
+  Shim* h = S(hb);
+  if (!h || !h->emu) return IGV_ERR_STATE;
+  if (h->n_clones == 0) return IGV_OK;
+  emu_set_X(h->emu, h->Xh.data());
+  emu_erase_invalid(h->emu, min_depth);
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_get(igv_batch* hb, const igv_track_dump* d) {
+  Shim* h = S(hb);
+  if (!h || !h->emu || !d) return IGV_ERR_STATE;
+  if (d->obs && d->obs_slots < h->n_clones) return IGV_ERR_INVALID;
+  emu_dump(h->emu, d->obs_slots, d->id, d->used, d->to_marg, d->is_tri, d->slot_mask, d->anchor_slot, d->pf, d->pf_fej, d->obs,
+           d->n_tracks);
+  ++h->launches;
+  return IGV_OK;
+}
+}
