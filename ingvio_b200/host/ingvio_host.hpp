@@ -219,6 +219,7 @@ struct StateParams {
   double _init_cov_ext_rot = 0, _init_cov_ext_pos = 0;
   bool _enable_gnss = true;
   Mat3 _T_cl2i_R; Vec3d _T_cl2i_p;
+  Mat3 _T_cl2cr_R; Vec3d _T_cl2cr_p;                   // left -> right camera (State.cpp:33), identity / zero by default
   double gravity[3] = {0, 0, -9.8};
 };
 
@@ -226,14 +227,15 @@ class StateManager;
 class State {
  public:
   enum GNSSType { GPS = 0, GLO, GAL, BDS, FS, YOF };
-  explicit State(const StateParams& p, int max_feats = 400, int max_sats = 40) : _state_params(p) {
+  explicit State(const StateParams& p, int max_feats = 400, int max_sats = 40) : _state_params(p), _max_feats(max_feats) {
     igv_config cfg{1, 21 + 6 + 6 * (p._max_sw_poses + 1), p._max_sw_poses + 1, max_feats, max_sats, p._cam_nums == 2, 0, nullptr};
     if (igv_create(&cfg, &_gpu) != IGV_OK) throw std::runtime_error("igv_create failed (no CUDA device / library?)");
     igv_params ip{};
     ip.noise_g = p._noise_g; ip.noise_a = p._noise_a; ip.noise_bg = p._noise_bg; ip.noise_ba = p._noise_ba;
     ip.noise_clockbias = p._noise_clockbias; ip.noise_cb_rw = p._noise_cb_rw;
     for (int i = 0; i < 3; ++i) ip.gravity[i] = p.gravity[i];
-    for (int i = 0; i < 9; ++i) ip.T_cl2cr_R[i] = (i % 4 == 0);
+    for (int i = 0; i < 9; ++i) ip.T_cl2cr_R[i] = p._T_cl2cr_R.m[i];
+    for (int i = 0; i < 3; ++i) ip.T_cl2cr_p[i] = p._T_cl2cr_p[i];
     igv_set_params(_gpu, &ip);
     _extended_pose = std::make_shared<SE23>(); _bg = std::make_shared<Vec3>(); _ba = std::make_shared<Vec3>();
     _camleft_imu_extrinsics = std::make_shared<SE3>();
@@ -272,6 +274,7 @@ class State {
 
   double _timestamp = -1;
   StateParams _state_params;
+  int _max_feats;                                     // capacity of one fused visual update (igv_config::max_feats)
   std::shared_ptr<SE23> _extended_pose;
   std::shared_ptr<Vec3> _bg, _ba;
   std::shared_ptr<SE3> _camleft_imu_extrinsics;

@@ -71,8 +71,7 @@ class MapServer {
   std::map<int, std::shared_ptr<FeatureInfo>>::const_iterator end() { refresh(); return _view.end(); }
   std::map<int, std::shared_ptr<FeatureInfo>>::const_iterator find(int id) { refresh(); return _view.find(id); }
 
- private:
-  friend class MapServerManager;
+  // Attach to the State whose handle holds the table (done by the first MapServerManager / updater call).
   void bind(const std::shared_ptr<State>& state) {
     if (_state.lock() == state) return;
     if (!_state.expired()) throw std::runtime_error("[MapServer]: already bound to another State");
@@ -82,6 +81,10 @@ class MapServer {
     _stereo = state->_state_params._cam_nums == 2;
     _dirty = true;
   }
+  void touch() { _dirty = true; }   // the table was changed through the C-ABI directly
+
+ private:
+  friend class MapServerManager;
   void refresh() {
     auto state = _state.lock();
     if (!state) { _view.clear(); return; }

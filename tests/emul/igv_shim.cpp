@@ -3,7 +3,9 @@
 // (tests/emul/trk_emul.cpp). It exists so that tests/cpp/test_map_server_mirror.cpp -- the reference's MapServer gtest
 // restated against the mirror -- can check the mirror's own logic on a machine without a GPU; the GPU test links the same
 // source against libingvio_b200.so. Covariance / mean algebra is NOT provided here (those entry points are exercised on the
-// GPU only); B = 1.
+// GPU only: here igv_propagate_imu only drifts the position, igv_triangulate places every track with two or more observations
+// five metres in front of the newest clone, igv_msckf_update and igv_set_chi2_table do nothing and igv_cov_get returns the
+// identity -- enough for tests/cpp/test_updaters_frames.cpp to exercise the wiring of the updater mirror, nothing more); B = 1.
 #include "trk_emul.cpp"
 
 // The opaque handle of the C-ABI is the library's own igv_batch (igv_internal.h; cfg / err / launches are reused), extended
@@ -34,11 +36,14 @@ igv_status igv_destroy(igv_batch* hb) {
 const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "null handle"; }
 long long igv_launch_count(const igv_batch* h) { return h ? h->launches : 0; }
 igv_status igv_set_params(igv_batch*, const igv_params*) { return IGV_OK; }
-igv_status igv_state_init(igv_batch* hb, const double*, const double*, const double*, const double*, const double*,
-                          const double*, const double*, const double*) {
+igv_status igv_state_init(igv_batch* hb, const double* R, const double* p, const double* v, const double* bg, const double* ba,
+                          const double* Re, const double* pe, const double*) {
   Shim* h = S(hb);
   if (!h) return IGV_ERR_INVALID;
   h->n_clones = 0;
+  std::fill(h->Xh.begin(), h->Xh.end(), 0.0);
+  for (int i = 0; i < 9; ++i) { h->Xh[i] = R[i]; h->Xh[21 + i] = Re[i]; }
+  for (int i = 0; i < 3; ++i) { h->Xh[9 + i] = p[i]; h->Xh[12 + i] = v[i]; h->Xh[15 + i] = bg[i]; h->Xh[18 + i] = ba[i]; h->Xh[30 + i] = pe[i]; }
   if (h->emu) {   // a new State starts with an empty map (igv_api.cu: igv_state_init)
     Emu* e = static_cast<Emu*>(h->emu);
     e->trk.col_of_slot.clear();
@@ -115,6 +120,84 @@ igv_status igv_tracks_get(igv_batch* hb, const igv_track_dump* d) {
   if (d->obs && d->obs_slots < h->n_clones) return IGV_ERR_INVALID;
   emu_dump(h->emu, d->obs_slots, d->id, d->used, d->to_marg, d->is_tri, d->slot_mask, d->anchor_slot, d->pf, d->pf_fej, d->obs,
            d->n_tracks);
+  ++h->launches;
+  return IGV_OK;
+}
+
+// ---- stubs / table calls used by the updater mirror (tests/cpp/test_updaters_frames.cpp) ----
+int igv_state_size(const igv_batch* h) { return h ? (int)S(h)->Xh.size() : -1; }
+igv_status igv_state_get(igv_batch* hb, double* dst) {
+  Shim* h = S(hb);
+  if (!h || !dst) return IGV_ERR_INVALID;
+  std::memcpy(dst, h->Xh.data(), sizeof(double) * h->Xh.size());
+  return IGV_OK;
+}
+igv_status igv_cov_get(igv_batch* hb, double* dst, int ld) {
+  Shim* h = S(hb);
+  const int N = igv_dim(hb);
+  if (!h || !dst || ld < N) return IGV_ERR_INVALID;
+  for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) dst[(size_t)j * ld + i] = (i == j) ? 1.0 : 0.0;
+  return IGV_OK;
+}
+igv_status igv_set_chi2_table(igv_batch*, const double*, int) { return IGV_OK; }
+igv_status igv_propagate_imu(igv_batch* hb, int n_steps, const double*, const double*, const double* dt) {
+  Shim* h = S(hb);
+  if (!h) return IGV_ERR_INVALID;
+  for (int k = 0; k < n_steps; ++k) { h->Xh[9] += 2.0 * dt[k]; h->Xh[10] += 0.5 * dt[k]; }   // drift sideways: parallax
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_msckf_update(igv_batch* hb, const igv_msckf_args* a) { if (!hb || !a) return IGV_ERR_INVALID; ++S(hb)->launches; return IGV_OK; }
+igv_status igv_triangulate(igv_batch* hb, const igv_tri_args* a) {
+  Shim* h = S(hb);
+  if (!h || !a || h->n_clones == 0) return IGV_ERR_INVALID;
+  const double* c = h->Xh.data() + IGV_X_CORE + 12 * (h->n_clones - 1);
+  for (int f = 0; f < a->n_feats; ++f) {
+    int n = 0;
+    for (int s = 0; s < a->obs_slots; ++s) n += a->obs_mask[(size_t)f * a->obs_slots + s] ? 1 : 0;
+    a->ok_out[f] = n >= 2 ? 1 : 0;
+    for (int i = 0; i < 3; ++i) a->pf_out[3 * f + i] = n >= 2 ? c[9 + i] + 5.0 * c[3 * i + 2] : 0.0;   // p + 5 R e_z
+  }
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_gather(igv_batch* hb, const igv_track_gather_args* a) {
+  Shim* h = S(hb);
+  if (!h || !h->emu || !a) return IGV_ERR_STATE;
+  if (a->obs_slots < h->n_clones || a->n_feats < 1 || a->n_feats > h->cfg.max_feats) return IGV_ERR_INVALID;
+  std::vector<int> ids((size_t)a->n_feats);
+  if (emu_gather(h->emu, a->rule, a->n_selected, a->selected_slots, a->min_obs, a->dof_fixed, a->n_feats, a->obs_slots, a->track_entry,
+                 a->n_sel, a->track_id ? a->track_id : ids.data(), a->obs, a->mask_all, a->mask_upd, a->anchor_slot, a->chi2_dof,
+                 a->feat_ok) != 0) { h->err = "clone slot not in the sliding window"; return IGV_ERR_STATE; }
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_commit_tri(igv_batch* hb, int F, const int* entry, const double* pf, const unsigned char* ok, unsigned char* feat_ok) {
+  Shim* h = S(hb);
+  if (!h || !h->emu) return IGV_ERR_STATE;
+  emu_commit_tri(h->emu, F, entry, pf, ok, feat_ok);
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_erase(igv_batch* hb, int F, const int* entry) {
+  Shim* h = S(hb);
+  if (!h || !h->emu) return IGV_ERR_STATE;
+  emu_erase(h->emu, F, entry);
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_clean_obs(igv_batch* hb, int n, const int* slots) {
+  Shim* h = S(hb);
+  if (!h || !h->emu) return IGV_ERR_STATE;
+  if (emu_clean(h->emu, n, slots) != 0) { h->err = "clone slot not in the sliding window"; return IGV_ERR_STATE; }
+  ++h->launches;
+  return IGV_OK;
+}
+igv_status igv_tracks_change_anchor(igv_batch* hb, int n, const int* slots, double min_depth) {
+  Shim* h = S(hb);
+  if (!h || !h->emu) return IGV_ERR_STATE;
+  emu_set_X(h->emu, h->Xh.data());
+  if (emu_change_anchor(h->emu, n, slots, min_depth) != 0) { h->err = "clone slot not in the sliding window"; return IGV_ERR_STATE; }
   ++h->launches;
   return IGV_OK;
 }

@@ -1,0 +1,142 @@
+"""The C++ updater mirror (ingvio_b200/host/ingvio_updaters.hpp: RemoveLostUpdate / SwMargUpdate / KeyframeUpdate with the
+reference's interfaces, MapServerManager, State / StateManager) driven frame by frame in the reference's call order by
+tests/cpp/test_updaters_frames.cpp on a recorded stream (IMU + tracker messages).
+
+  * CPU: the driver runs against tests/emul/igv_shim.cpp (table calls on the kernel source executed on the CPU, algebra
+    stubbed): window policy, slot bookkeeping and the call chain of the mirror are exercised without a GPU;
+  * GPU: the same driver against libingvio_b200.so, state and covariance after every frame compared with the oracle filter
+    driven by the oracle MapServer (tests/track_frames.py) at the parity bar of the other tests.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import cov_diag21, filter_params, make_oracles, oracle_packed_state
+from ingvio_b200.synth import K_IMU, SyntheticStream, TrackerStream, Workload
+from track_frames import OracleFrontEnd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_updaters_frames.cpp")
+LIBDIR = os.path.join(ROOT, "ingvio_b200", "lib")
+EMUL = os.path.join(ROOT, "tests", "emul")
+SW, F, M, T, FRAMES = 5, 32, 32, 96, 14
+
+
+def _stream(keyframe, stereo):
+    wl = Workload("trk", 11 + int(stereo), SW + (0 if keyframe else 1), F, 0, stereo=stereo)
+    fp = filter_params(wl, max_sw_clones=SW, frame_select_interval=2)
+    st = SyntheticStream(wl, 1)
+    trk = TrackerStream(st, 18, M)
+    frames = []
+    for _ in range(FRAMES):
+        st.n_clones = 0
+        fr = st.next_frame(with_visual=False, with_gnss=False, marg_oldest=False)
+        frames.append((fr,) + trk.message(fr.t))
+    return wl, fp, st, frames
+
+
+def _write_input(path, wl, fp, st, frames, keyframe):
+    import ingvio_oracle as o
+    sp = o.StateParams(fp)
+    ini = st.initial_state()
+    rho = wl.rho
+    out = [FRAMES, K_IMU, M, rho, int(keyframe), SW, F, fp.frame_select_interval, T,
+           sp.noise_g, sp.noise_a, sp.noise_bg, sp.noise_ba, sp.noise_clockbias, sp.noise_cb_rw, 0.0, 0.0, -fp.gravity_norm]
+    out += list(np.asarray(fp.T_cl2i_R).reshape(9)) + list(fp.T_cl2i_p) + list(np.asarray(fp.T_cl2cr_R).reshape(9)) + list(fp.T_cl2cr_p)
+    out += [sp.init_cov_rot, sp.init_cov_pos, sp.init_cov_vel, sp.init_cov_bg, sp.init_cov_ba, sp.init_cov_ext_rot, sp.init_cov_ext_pos]
+    out += [fp.visual_noise, fp.chi2_thres]
+    out += list(ini["R"][0].reshape(9)) + list(ini["p"][0]) + list(ini["v"][0]) + list(ini["bg"][0]) + list(ini["ba"][0])
+    for fr, n, ids, uv in frames:
+        out += [fr.t] + list(fr.gyro[0].reshape(-1)) + list(fr.accel[0].reshape(-1)) + list(fr.dt[0]) + [int(n[0])]
+        out += [float(i) for i in ids[0]] + list(uv[0].reshape(-1))
+    np.asarray(out, dtype=np.float64).tofile(path)
+
+
+def _read_output(path, max_clones):
+    d = np.fromfile(path, dtype=np.float64)
+    xs = 39 + 12 * max_clones
+    recs, pos = [], 0
+    while pos < len(d):
+        N, ncl, ntr = int(d[pos]), int(d[pos + 1]), int(d[pos + 2])
+        x = d[pos + 3:pos + 3 + xs]
+        P = d[pos + 3 + xs:pos + 3 + xs + N * N].reshape(N, N).T     # column-major
+        recs.append(dict(N=N, ncl=ncl, ntr=ntr, x=x, P=P))
+        pos += 3 + xs + N * N
+    return recs
+
+
+def _build(exe, libdir, libname):
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", SRC, "-o", exe, f"-L{libdir}", f"-l{libname}", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return exe
+
+
+@pytest.mark.parametrize("keyframe,stereo", [(False, False), (True, False), (False, True)])
+def test_updater_mirror_wiring_on_cpu_shim(tmp_path, keyframe, stereo):
+    bdir = os.path.join(EMUL, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-I" + cuda_inc, "-I" + EMUL,
+                        os.path.join(EMUL, "igv_shim.cpp"), "-o", os.path.join(bdir, "libigv_shim.so")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = _build(os.path.join(bdir, "test_updaters_frames_cpu"), bdir, "igv_shim")
+    wl, fp, st, frames = _stream(keyframe, stereo)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_input(fin, wl, fp, st, frames, keyframe)
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and f"FRAMES DONE {FRAMES}" in r.stdout, r.stdout + r.stderr
+    recs = _read_output(fout, SW + 1)
+    assert len(recs) == FRAMES
+    # window policy of the reference: SwMargUpdate keeps SW clones after each frame once full (marginalises when SW+1 are
+    # present); KeyframeUpdate drops two clones whenever SW are present
+    ncl = [r_["ncl"] for r_ in recs]
+    if keyframe:
+        exp, n = [], 0
+        for _ in range(FRAMES):
+            n += 1
+            if n >= SW:
+                n -= 2
+            exp.append(n)
+    else:
+        exp = [min(k + 1, SW) for k in range(FRAMES)]
+    assert ncl == exp, (ncl, exp)
+    assert all(r_["N"] == 21 + 6 * r_["ncl"] for r_ in recs)
+    assert all(r_["ntr"] > 0 for r_ in recs)
+    # lost tracks leave the table (RemoveLostUpdate erases what it selected): it cannot grow without bound
+    assert max(r_["ntr"] for r_ in recs) <= 2 * 18 + 8
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(LIBDIR, "libingvio_b200.so")), reason="library not built")
+def test_updater_mirror_links_against_the_library():
+    _build(os.path.join(ROOT, "tests", "cpp", "_build", "test_updaters_frames"), LIBDIR, "ingvio_b200")
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: compiled, linked and run against the CPU "
+                                        "shim, not yet run on hardware (the C-ABI calls it chains are GPU-verified through the "
+                                        "Python mirror, tests/test_gpu_tracks.py)")
+@pytest.mark.parametrize("keyframe,stereo", [(False, False), (True, False), (False, True)])
+def test_updater_mirror_vs_oracle(tmp_path, keyframe, stereo):
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "_build", "test_updaters_frames"), LIBDIR, "ingvio_b200")
+    wl, fp, st, frames = _stream(keyframe, stereo)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_input(fin, wl, fp, st, frames, keyframe)
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and f"FRAMES DONE {FRAMES}" in r.stdout, r.stdout + r.stderr
+    recs = _read_output(fout, SW + 1)
+    fe = OracleFrontEnd(make_oracles(wl, st, fp, with_gnss=False)[0], keyframe)
+    for k, (fr, n, ids, uv) in enumerate(frames):
+        fe.frame(fr.seq(0), int(n[0]), ids[0], uv[0])
+        Po = fe.f.cov()
+        rec = recs[k]
+        assert rec["N"] == Po.shape[0] and rec["ncl"] == len(fe.f.state.sw_camleft_poses) and rec["ntr"] == len(fe.ms), (k, rec["N"], rec["ntr"])
+        err = np.linalg.norm(rec["P"] - Po) / max(1.0, np.linalg.norm(Po))
+        assert err <= 1e-8, f"frame {k}: |dP|_F/max(1,|P|_F) = {err:.3e}"
+        xo = oracle_packed_state(fe.f, SW + 1)
+        nu = 39 + 12 * rec["ncl"]
+        ex = np.max(np.abs(rec["x"][:nu] - xo[:nu]) / np.maximum(1.0, np.abs(xo[:nu])))
+        assert ex <= 1e-9, f"frame {k}: state mismatch {ex:.3e}"
