@@ -105,3 +105,59 @@ def test_reference_test_on_emulated_kernels(stereo):
         run_reference_test_on_table(tab, tab.augment, stereo)
     finally:
         tab.close()
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_feature_info_tri(stereo):
+    """TEST_F(TestMapServer, featureInfoTriMono / featureInfoTriStereo) (TestMapServer.cpp:310-395, :397-482): the flag
+    returned by triangulateFeatureInfo* equals isTri(); the estimate it stores is the landmark (the reference only prints it)."""
+    rng = np.random.default_rng(9)
+    T_cl2cr = (np.eye(3), np.array([0.001, -0.12, 0.003]))                         # fixture, TestMapServer.cpp:48-49
+    fp = o.FilterParams(max_sw_clones=20, enable_gnss=0, cam_nums=2 if stereo else 1)
+    fp.T_cl2cr_R, fp.T_cl2cr_p = T_cl2cr
+    state = o.State(fp)
+    ms = oms.MapServer()
+    tri = o.Triangulator(o.TriParams())
+    ids1, pfs1 = [1, 2], [np.array([1.0, 1.5, 2.0]), np.array([1.0, 2.0, 3.0])]   # :312-318
+    ids2, pfs2 = [2, 3], [pfs1[1], np.array([1.5, 2.0, 3.0])]                     # :320-326
+    times = [0.5 * (i + 1) for i in range(9)]                                     # :328-330
+    poses = []
+    for i in range(9):                                                            # :332-337
+        a = rng.normal(0.0, 0.1)
+        R = np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]])
+        poses.append((R, np.array([2.0 * i - 5.0, 2.0 * i - 6.0, 0.0])))
+
+    def frame(i, ids, pfs):                                                       # generateMonoFrame / calcMonoMeas (:101-130)
+        R, p = poses[i]
+        c = SE3()
+        c.set_value(R, p)
+        state.sw_camleft_poses[times[i]] = c
+        state.timestamp = times[i]
+        uv = []
+        for pf in pfs:
+            b = R.T @ (pf - p)
+            z = [b[0] / b[2], b[1] / b[2]]
+            if stereo:
+                br = T_cl2cr[0] @ b + T_cl2cr[1]
+                z += [br[0] / br[2], br[1] / br[2]]
+            uv.append(np.array(z) + rng.normal(0.0, 0.02, len(z)))
+        oms.collect_meas(ms, state, ids, uv, stereo)
+
+    for i in range(4):
+        frame(i, ids1, pfs1)                                                      # :346-356
+    for i in (4, 5):
+        frame(i, ids2, pfs2)                                                      # :358-362
+    for fid, ref in ((1, pfs1[0]), (2, pfs1[1])):                                 # :366-379
+        flag = oms.triangulate_feature_info(ms[fid], tri, state, stereo)
+        assert ms[fid].is_tri == flag
+        if flag:
+            assert np.linalg.norm(ms[fid].pf_w - ref) < 0.5
+    for i in (6, 7, 8):
+        frame(i, ids2, pfs2)                                                      # :381-388
+    flag = oms.triangulate_feature_info(ms[3], tri, state, stereo)                # :390-394
+    assert ms[3].is_tri == flag
+    if flag:
+        assert np.linalg.norm(ms[3].pf_w - pfs2[1]) < 0.5
+    if not stereo:
+        assert flag            # (the mono geometry of the fixture triangulates; the reference asserts only the equality above)
+    assert len(ms[2].stereo_obs if stereo else ms[2].mono_obs) == 9 and len(ms) == 3
