@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>   // host-side types only (dim3, uint3, cudaStream_t)
 
 #include <barrier>
+#include <cmath>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -102,6 +103,19 @@ inline int __shfl_down_sync(unsigned, int v, int delta) {
 #include <algorithm>
 using std::min;
 using std::max;
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  unsigned long long raw = 0;
+  std::memcpy(&raw, &v, sizeof(T));
+  raw = emul::exchange(raw, src_lane);
+  std::memcpy(&v, &raw, sizeof(T));
+  return v;
+}
+template <class T>
+inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)(threadIdx.x & 31) ^ lane_mask); }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

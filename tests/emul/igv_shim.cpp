@@ -3,8 +3,8 @@
 // (tests/emul/trk_emul.cpp). It exists so that tests/cpp/test_map_server_mirror.cpp -- the reference's MapServer gtest
 // restated against the mirror -- can check the mirror's own logic on a machine without a GPU; the GPU test links the same
 // source against libingvio_b200.so. Covariance / mean algebra is NOT provided here (those entry points are exercised on the
-// GPU only: here igv_propagate_imu only drifts the position, igv_triangulate places every track with two or more observations
-// five metres in front of the newest clone, igv_msckf_update and igv_set_chi2_table do nothing and igv_cov_get returns the
+// GPU only: here igv_propagate_imu only drifts the position, igv_triangulate IS the device kernel (k_tri.cu) run on the CPU,
+// igv_msckf_update and igv_set_chi2_table do nothing and igv_cov_get returns the
 // identity -- enough for tests/cpp/test_updaters_frames.cpp to exercise the wiring of the updater mirror, nothing more); B = 1.
 #include "trk_emul.cpp"
 
@@ -35,7 +35,12 @@ igv_status igv_destroy(igv_batch* hb) {
 }
 const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "null handle"; }
 long long igv_launch_count(const igv_batch* h) { return h ? h->launches : 0; }
-igv_status igv_set_params(igv_batch*, const igv_params*) { return IGV_OK; }
+igv_status igv_set_params(igv_batch* hb, const igv_params* p) {
+  if (!hb || !p) return IGV_ERR_INVALID;
+  for (int i = 0; i < 9; ++i) hb->params.Rc[i] = p->T_cl2cr_R[i];
+  for (int i = 0; i < 3; ++i) hb->params.pc[i] = p->T_cl2cr_p[i];
+  return IGV_OK;
+}
 igv_status igv_state_init(igv_batch* hb, const double* R, const double* p, const double* v, const double* bg, const double* ba,
                           const double* Re, const double* pe, const double*) {
   Shim* h = S(hb);
@@ -148,16 +153,13 @@ igv_status igv_propagate_imu(igv_batch* hb, int n_steps, const double*, const do
   return IGV_OK;
 }
 igv_status igv_msckf_update(igv_batch* hb, const igv_msckf_args* a) { if (!hb || !a) return IGV_ERR_INVALID; ++S(hb)->launches; return IGV_OK; }
-igv_status igv_triangulate(igv_batch* hb, const igv_tri_args* a) {
+igv_status igv_triangulate(igv_batch* hb, const igv_tri_args* a) {   // the real kernel (k_tri.cu) on the CPU
   Shim* h = S(hb);
-  if (!h || !a || h->n_clones == 0) return IGV_ERR_INVALID;
-  const double* c = h->Xh.data() + IGV_X_CORE + 12 * (h->n_clones - 1);
-  for (int f = 0; f < a->n_feats; ++f) {
-    int n = 0;
-    for (int s = 0; s < a->obs_slots; ++s) n += a->obs_mask[(size_t)f * a->obs_slots + s] ? 1 : 0;
-    a->ok_out[f] = n >= 2 ? 1 : 0;
-    for (int i = 0; i < 3; ++i) a->pf_out[3 * f + i] = n >= 2 ? c[9 + i] + 5.0 * c[3 * i + 2] : 0.0;   // p + 5 R e_z
-  }
+  if (!h || !h->emu || !a || !a->obs || !a->obs_mask || !a->pf_out || !a->ok_out) return IGV_ERR_INVALID;
+  if (a->n_feats < 0 || a->n_feats > h->cfg.max_feats || a->obs_slots < h->n_clones) return IGV_ERR_INVALID;
+  emu_set_X(h->emu, h->Xh.data());
+  emu_triangulate(h->emu, h->n_clones, a->n_feats, a->obs_slots, a->obs, a->obs_mask, a->anchor_slot, &a->prm, h->params.Rc,
+                  h->params.pc, a->pf_out, a->ok_out);
   ++h->launches;
   return IGV_OK;
 }

@@ -6,6 +6,7 @@
 #include "cuda_emul.h"
 
 #include "../../ingvio_b200/csrc/k_tracks.cu"
+#include "../../ingvio_b200/csrc/k_tri.cu"      // k_triangulate: one thread per track, plain FP64 arithmetic
 
 namespace {
 struct Emu {
@@ -120,6 +121,20 @@ void emu_erase_invalid(void* h, double min_depth) {
   const double* X = e->X.data();
   const int xs = e->xsize;
   emul::launch(e->per_track_grid(), 256, 0, [&] { k_trk_erase_invalid(p, c, X, xs, min_depth); });
+}
+// igv_launch_triangulate (k_tri.cu) on the clone poses last given with emu_set_X
+void emu_triangulate(void* h, int n_clones, int F, int obs_slots, const double* obs, const unsigned char* mask, const int* anchor,
+                     const igv_tri_params* prm, const double* Rc, const double* pc, double* pf_out, unsigned char* ok_out) {
+  Emu* e = static_cast<Emu*>(h);
+  TriArgs a;
+  a.X = e->X.data(); a.xsize = e->xsize; a.n_clones = n_clones;
+  a.F = F; a.obs_slots = obs_slots; a.rho = e->rho;
+  a.obs = obs; a.mask = mask; a.anchor = anchor; a.prm = *prm;
+  for (int i = 0; i < 9; ++i) a.Rc[i] = Rc[i];
+  for (int i = 0; i < 3; ++i) a.pc[i] = pc[i];
+  a.pf_out = pf_out; a.ok_out = ok_out; a.B = e->B;
+  const long n = (long)e->B * F;
+  emul::launch((unsigned)((n + 127) / 128), 128, 0, [&] { k_triangulate(a); });
 }
 void emu_dump(void* h, int obs_slots, int* id, unsigned char* used, unsigned char* to_marg, unsigned char* is_tri,
               unsigned long long* slot_mask, int* anchor_slot, double* pf, double* pf_fej, double* obs, int* n_tracks) {

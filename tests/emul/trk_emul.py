@@ -57,6 +57,7 @@ class EmulatedTrackTable:
         L.emu_change_anchor.argtypes = [_vp, _i, _vp, _d]
         L.emu_erase_invalid.argtypes = [_vp, _d]
         L.emu_dump.argtypes = [_vp, _i] + [_vp] * 10
+        L.emu_triangulate.argtypes = [_vp, _i, _i, _i] + [_vp] * 8
         self.B, self.max_clones, self.max_feats, self.max_tracks = batch, max_clones, max_feats, max_tracks
         self.stereo = bool(stereo)
         self.rho = 4 if stereo else 2
@@ -64,6 +65,7 @@ class EmulatedTrackTable:
         self.h = L.emu_create(batch, max_tracks, max_clones, self.rho, self.xsize)
         self.X = np.zeros((batch, self.xsize))
         self.n_clones = 0
+        self.T_cl2cr = (np.eye(3), np.zeros(3))
 
     def close(self):
         if self.h:
@@ -161,6 +163,28 @@ class EmulatedTrackTable:
                           _p(out["slot_mask"]), _p(out["anchor_slot"]), _p(out["pf"]), _p(out["pf_fej"]), _p(out["obs"]),
                           _p(out["n_tracks"]))
         return out
+
+    def triangulate(self, obs, obs_mask, anchor_slot=None, **prm):
+        """k_triangulate (ingvio_b200/csrc/k_tri.cu) on the CPU, same arguments as BatchFilter.triangulate (host arrays)."""
+        class P(C.Structure):
+            _fields_ = [("trans_thres", _d), ("huber_epsilon", _d), ("conv_precision", _d), ("init_damping", _d),
+                        ("outer_loop_max_iter", _i), ("inner_loop_max_iter", _i), ("max_depth", _d), ("min_depth", _d)]
+        d = dict(trans_thres=0.1, huber_epsilon=0.01, conv_precision=5e-7, init_damping=1e-3, outer_loop_max_iter=10,
+                 inner_loop_max_iter=10, max_depth=60.0, min_depth=0.2)
+        d.update(prm)
+        p = P(**d)
+        obs = np.ascontiguousarray(obs, np.float64)
+        mask = np.ascontiguousarray(obs_mask, np.uint8)
+        anc = np.ascontiguousarray(anchor_slot, np.int32) if anchor_slot is not None else None
+        F, SW = mask.shape[1], mask.shape[2]
+        pf = np.zeros((self.B, F, 3))
+        ok = np.zeros((self.B, F), np.uint8)
+        self._sync_X()
+        Rc = np.ascontiguousarray(self.T_cl2cr[0], np.float64).reshape(9)
+        pc = np.ascontiguousarray(self.T_cl2cr[1], np.float64).reshape(3)
+        self.lib.emu_triangulate(self.h, self.n_clones, F, SW, _p(obs), _p(mask), _p(anc), C.addressof(p), _p(Rc), _p(pc),
+                                 _p(pf), _p(ok))
+        return pf, ok.astype(bool)
 
     def flags(self, clear=True):
         f = np.array([self.lib.emu_flags(self.h)[b] for b in range(self.B)], dtype=np.int32)

@@ -109,3 +109,53 @@ def test_depth_branches_emulated():
         depth_branches(tab, tab.augment)
     finally:
         tab.close()
+
+
+@pytest.mark.parametrize("wname", ["c1", "tiny_stereo"])
+def test_emulated_triangulation_kernel_matches_oracle(wname):
+    """k_triangulate (ingvio_b200/csrc/k_tri.cu, the kernel igv_triangulate launches) executed on the CPU against the oracle
+    Triangulator on the oracle filter's clone poses: same accept / reject decisions, positions to 1e-7 relative (the GPU
+    twin is tests/test_gpu_parity.py::test_triangulate_matches_oracle)."""
+    import ingvio_oracle as o
+    from helpers import filter_params, make_oracles, oracle_packed_state
+    from ingvio_b200.synth import WORKLOADS, SyntheticStream
+    wl = WORKLOADS[wname]
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 2)
+    orc = make_oracles(wl, st, fp)
+    for _ in range(wl.sw + 1):
+        fr = st.next_frame()
+        for b, f in enumerate(orc):
+            f.step(fr.seq(b))
+    fr = st.next_frame()
+    for b, f in enumerate(orc):
+        f.propagate_augment(fr.seq(b))
+    tab = EmulatedTrackTable(2, wl.sw, wl.feats, 8, wl.stereo)
+    try:
+        tab.X[:] = np.stack([oracle_packed_state(f, wl.sw) for f in orc])
+        tab.n_clones = len(orc[0].state.sw_camleft_poses)
+        tab.T_cl2cr = (fp.T_cl2cr_R, fp.T_cl2cr_p)
+        rng = np.random.default_rng(3)
+        mask = fr.obs_mask.copy()
+        mask[:, 0, :2] = 0                       # fewer views
+        mask[:, 1, :] = 0
+        mask[:, 1, :2] = 1                       # <= 4 mono views -> reject (Triangulator.cpp:183)
+        obs = fr.obs.copy()
+        obs[:, 2] += rng.normal(0, 0.3, obs[:, 2].shape)   # garbage track
+        prm = dict(trans_thres=0.1, conv_precision=5e-7, max_depth=60.0)
+        pf, ok = tab.triangulate(obs, mask, fr.anchor_slot, **prm)
+        tri = o.Triangulator(o.TriParams(**prm))
+        n_ok = 0
+        for b, f in enumerate(orc):
+            times = f.state.sw_times()
+            poses = [(f.state.sw_camleft_poses[t].rot, f.state.sw_camleft_poses[t].vec) for t in times]
+            for k in range(wl.feats):
+                oko, pfo = tri.triangulate_feature(obs[b, k], mask[b, k], poses, int(fr.anchor_slot[b, k]), wl.stereo,
+                                                   (fp.T_cl2cr_R, fp.T_cl2cr_p))
+                assert bool(ok[b, k]) == bool(oko), (b, k)
+                if oko:
+                    n_ok += 1
+                    assert np.linalg.norm(pf[b, k] - pfo) <= 1e-7 * max(1.0, np.linalg.norm(pfo)), (b, k, pf[b, k], pfo)
+        assert n_ok > wl.feats and not ok[:, 1].any()
+    finally:
+        tab.close()
