@@ -71,6 +71,8 @@ def test_map_server_mirror_links_against_the_library():
 
 
 @pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="added after the round's last GPU run (green against the CPU shim of the same C symbols); "
+                                        "non-strict until it has run on hardware once")
 def test_map_server_mirror_reference_cases():
     exe = _build_map_server_test(os.path.join(ROOT, "tests", "cpp", "_build", "test_map_server_mirror"), LIBDIR, "ingvio_b200")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
