@@ -28,6 +28,8 @@ NCU="ncu --clock-control none"
 BARGS="bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency"
 timeout 600 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/${TAG}_launches.csv python $BARGS > $OUT/${TAG}_ncu_launch.log 2>&1
 if [ "$FULL" = "full" ]; then
+  # track-table kernels: launch list of the extra leg
+  timeout 300 $NCU --metrics gpu__time_duration.sum -k regex:k_trk -c 200 --csv --log-file $OUT/${TAG}_trk_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_trk.log 2>&1
   for K in k_msckf_features k_ekf_update; do
     timeout 400 $NCU --set full --import-source on -k regex:$K -s 14 -c 2 -f -o $OUT/${TAG}_$K python $BARGS > $OUT/${TAG}_ncu_$K.log 2>&1
     ncu -i $OUT/${TAG}_$K.ncu-rep --page raw --csv > $OUT/${TAG}_${K}_raw.csv 2>/dev/null
