@@ -1,13 +1,13 @@
-// Frame driver for the C++ updater mirror (ingvio_b200/host/ingvio_updaters.hpp): reads a recorded stream (IMU samples +
-// tracker messages, written by tests/test_cpp_updaters.py), runs every frame through the reference's own call order
-// (IngvioFilter::callbackMonoFrame / callbackStereoFrame, IngvioFilter.cpp:143-205 / :271-333) using the mirrored classes
-// only -- State, StateManager, MapServerManager, RemoveLostUpdate, SwMargUpdate / KeyframeUpdate -- and writes the state
+// Frame driver for the C++ mirror of the estimator (ingvio_b200/host/ingvio_filter.hpp: IngvioFilter with its ImuPropagator,
+// MapServer, RemoveLostUpdate, SwMargUpdate / KeyframeUpdate): reads a recorded stream (IMU samples + tracker messages,
+// written by tests/test_cpp_updaters.py), feeds it through the reference's callbacks -- callbackIMU per sample,
+// callbackMonoFrame / callbackStereoFrame per image (IngvioFilter.cpp:124-250, :252-379, :381-407) -- and writes the state
 // and covariance after each frame for the Python side to compare with the oracle.
 //   usage: test_updaters_frames <input.bin> <output.bin>
 #include <cstdio>
 #include <cstring>
 
-#include "../../ingvio_b200/host/ingvio_updaters.hpp"
+#include "../../ingvio_b200/host/ingvio_filter.hpp"
 
 using namespace ingvio;
 
@@ -49,18 +49,23 @@ int main(int argc, char** argv) {
   fp._frame_select_interval = select_interval; fp._max_sw_clones = SW; fp._chi2_max_dof = 160;
   const Mat3 R0 = in.mat3(); const Vec3d p0 = in.vec3(), v0 = in.vec3(), bg0 = in.vec3(), ba0 = in.vec3();
 
-  auto state = std::make_shared<State>(sp, max_feats, 1);
-  state->initStateAndCov(0.0, R0, p0, v0, bg0, ba0);
-  auto map_server = std::make_shared<MapServer>(max_tracks);
-  auto tri = std::make_shared<Triangulator>(fp);
-  RemoveLostUpdate remove_lost_update(fp);
-  SwMargUpdate sw_marg_update(fp);
-  KeyframeUpdate keyframe_update(fp);
+  FilterOptions opt;
+  opt._is_key_frame = keyframe != 0;
+  opt._max_tracks = max_tracks;
+  IngvioFilter filter(sp, fp, opt, max_feats);
+  {   // the first image only arms the filter (IngvioFilter.cpp:129-133); IMU samples before it are dropped (:393)
+    feature_tracker::MonoFrame first; feature_tracker::StereoFrame first_s;
+    if (rho == 2) filter.callbackMonoFrame(first); else filter.callbackStereoFrame(first_s);
+  }
+  filter.initState(0.0, R0, p0, v0, bg0, ba0);
+  auto state = filter.state();
+  auto map_server = filter.mapServer();
   igv_batch* h = StateManager::handle(state);
 
   FILE* out = std::fopen(argv[2], "wb");
   if (!out) { std::perror(argv[2]); return 2; }
   std::vector<double> gyro(3 * K), accel(3 * K), dt(K), x(igv_state_size(h));
+  double t_prev = 0.0;
   for (int k = 0; k < n_frames; ++k) {
     const double t = in.next();
     in.take(gyro.data(), 3 * K); in.take(accel.data(), 3 * K); in.take(dt.data(), K);
@@ -73,41 +78,20 @@ int main(int argc, char** argv) {
       if (rho == 2) { feature_tracker::MonoMeas m; m.id = (std::uint64_t)ids[i]; m.u0 = uv[2 * i]; m.v0 = uv[2 * i + 1]; mono.mono_features.push_back(m); }
       else { feature_tracker::StereoMeas m; m.id = (std::uint64_t)ids[i]; m.u0 = uv[4 * i]; m.v0 = uv[4 * i + 1]; m.u1 = uv[4 * i + 2]; m.v1 = uv[4 * i + 3]; stereo.stereo_features.push_back(m); }
     }
-    // _imu_propa->propagateAugmentAtEnd(_state, target_time): the IMU loop runs on the device (mean and covariance)
-    StateManager::check(state, igv_propagate_imu(h, K, gyro.data(), accel.data(), dt.data()), true);
-    StateManager::sync_mean_from_device(state);
-    state->_timestamp = t;
-    StateManager::augmentSlidingWindowPose(state);
-    if (rho == 2) {
-      MapServerManager::collectMonoMeas(map_server, state, mono);                                   // IngvioFilter.cpp:147
-      remove_lost_update.updateStateMono(state, map_server, tri);                                   // :149
-      if (keyframe) {
-        keyframe_update.updateStateMono(state, map_server, tri);                                    // :153
-        keyframe_update.cleanMonoObsAtMargTime(state, map_server);                                  // :163
-        keyframe_update.changeMSCKFAnchor(state, map_server);                                       // :165
-        keyframe_update.margSwPose(state);                                                          // :175
-      } else {
-        sw_marg_update.updateStateMono(state, map_server, tri);                                     // :179
-        sw_marg_update.cleanMonoObsAtMargTime(state, map_server);                                   // :189
-        sw_marg_update.changeMSCKFAnchor(state, map_server);                                        // :191
-        sw_marg_update.margSwPose(state);                                                           // :196
-      }
-    } else {
-      MapServerManager::collectStereoMeas(map_server, state, stereo);                               // :275
-      remove_lost_update.updateStateStereo(state, map_server, tri);
-      if (keyframe) {
-        keyframe_update.updateStateStereo(state, map_server, tri);
-        keyframe_update.cleanStereoObsAtMargTime(state, map_server);
-        keyframe_update.changeMSCKFAnchor(state, map_server);
-        keyframe_update.margSwPose(state);
-      } else {
-        sw_marg_update.updateStateStereo(state, map_server, tri);
-        sw_marg_update.cleanStereoObsAtMargTime(state, map_server);
-        sw_marg_update.changeMSCKFAnchor(state, map_server);
-        sw_marg_update.margSwPose(state);
-      }
+    // sensor_msgs/Imu stream: sample j of this interval is stamped at the END of its step; the last one at the image time
+    double acc_dt = 0.0, tot = 0.0;
+    for (int j = 0; j < K; ++j) tot += dt[j];
+    for (int j = 0; j < K; ++j) {
+      acc_dt += dt[j];
+      const double stamp = (j == K - 1) ? t : t_prev + (t - t_prev) * (acc_dt / tot);
+      Vec3d w, a;
+      for (int i = 0; i < 3; ++i) { w[i] = gyro[3 * j + i]; a[i] = accel[3 * j + i]; }
+      filter.callbackIMU(ImuCtrl(stamp, w, a));
     }
-    MapServerManager::eraseInvalidFeatures(map_server, state);                                      // :199
+    if (rho == 2) filter.callbackMonoFrame(mono); else filter.callbackStereoFrame(stereo);
+    t_prev = t;
+    if (state->_timestamp != t) { std::fprintf(stderr, "frame %d: state time %.9f != image time %.9f\n", k, state->_timestamp, t); return 1; }
+    if (filter.imuPropagator()->bufferSize() != 0) { std::fprintf(stderr, "frame %d: %zu IMU samples left in the buffer\n", k, filter.imuPropagator()->bufferSize()); return 1; }
     StateManager::check(state, igv_state_get(h, x.data()), true);
     const Matrix P = StateManager::getFullCov(state);
     const double hdr[3] = {(double)state->curr_cov_size(), (double)state->_sw_camleft_poses.size(), (double)map_server->size()};

@@ -14,6 +14,7 @@ struct Shim : igv_batch {
   void* emu = nullptr;           // created by igv_tracks_create (the table size is not known before)
   int n_clones = 0;
   std::vector<double> Xh;        // mean mirror: only the clone poses are kept
+  std::vector<double> last_gyro, last_accel, last_dt;   // arguments of the last igv_propagate_imu (igv_shim_last_propagate)
 };
 static Shim* S(igv_batch* h) { return static_cast<Shim*>(h); }
 static const Shim* S(const igv_batch* h) { return static_cast<const Shim*>(h); }
@@ -145,12 +146,26 @@ igv_status igv_cov_get(igv_batch* hb, double* dst, int ld) {
   return IGV_OK;
 }
 igv_status igv_set_chi2_table(igv_batch*, const double*, int) { return IGV_OK; }
-igv_status igv_propagate_imu(igv_batch* hb, int n_steps, const double*, const double*, const double* dt) {
+igv_status igv_propagate_imu(igv_batch* hb, int n_steps, const double* gyro, const double* accel, const double* dt) {
   Shim* h = S(hb);
   if (!h) return IGV_ERR_INVALID;
+  h->last_gyro.assign(gyro, gyro + 3 * n_steps);
+  h->last_accel.assign(accel, accel + 3 * n_steps);
+  h->last_dt.assign(dt, dt + n_steps);
   for (int k = 0; k < n_steps; ++k) { h->Xh[9] += 2.0 * dt[k]; h->Xh[10] += 0.5 * dt[k]; }   // drift sideways: parallax
   ++h->launches;
   return IGV_OK;
+}
+// shim only: what the last igv_propagate_imu was given (tests/cpp/test_imu_buffer.cpp); clears the record
+int igv_shim_last_propagate(igv_batch* hb, double* gyro, double* accel, double* dt, int cap) {
+  Shim* h = S(hb);
+  const int n = (int)h->last_dt.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    dt[i] = h->last_dt[i];
+    for (int k = 0; k < 3; ++k) { gyro[3 * i + k] = h->last_gyro[3 * i + k]; accel[3 * i + k] = h->last_accel[3 * i + k]; }
+  }
+  h->last_dt.clear(); h->last_gyro.clear(); h->last_accel.clear();
+  return n;
 }
 igv_status igv_msckf_update(igv_batch* hb, const igv_msckf_args* a) { if (!hb || !a) return IGV_ERR_INVALID; ++S(hb)->launches; return IGV_OK; }
 igv_status igv_triangulate(igv_batch* hb, const igv_tri_args* a) {   // the real kernel (k_tri.cu) on the CPU

@@ -140,3 +140,100 @@ def test_updater_mirror_vs_oracle(tmp_path, keyframe, stereo):
         nu = 39 + 12 * rec["ncl"]
         ex = np.max(np.abs(rec["x"][:nu] - xo[:nu]) / np.maximum(1.0, np.abs(xo[:nu])))
         assert ex <= 1e-9, f"frame {k}: state mismatch {ex:.3e}"
+
+
+def test_imu_buffer_matches_oracle(tmp_path):
+    """ImuPropagator::storeImu / propagateUntil of the C++ mirror vs the oracle restatement of ImuPropagator.cpp:232-292 on
+    irregular stamps and awkward end times: the steps handed to the device, the state time and the buffer must agree
+    exactly (same double arithmetic)."""
+    import ingvio_oracle as o
+    rng = np.random.default_rng(4)
+    bdir = os.path.join(EMUL, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-I" + cuda_inc, "-I" + EMUL,
+                        os.path.join(EMUL, "igv_shim.cpp"), "-o", os.path.join(bdir, "libigv_shim.so")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = os.path.join(bdir, "test_imu_buffer")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "cpp", "test_imu_buffer.cpp"), "-o", exe,
+                        f"-L{bdir}", "-ligv_shim", f"-Wl,-rpath,{bdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # events: irregular sample times, end times before the first sample, between samples, on a sample, within 1e-6 of the
+    # state time, beyond the last sample, and with an empty buffer
+    t0 = 10.0
+    events, t = [("init", t0)], t0
+    stamps = []
+    for _ in range(60):
+        t += rng.uniform(0.002, 0.008)
+        stamps.append(t)
+    cursor = 0
+
+    def store(n):
+        nonlocal cursor
+        for s in stamps[cursor:cursor + n]:
+            events.append(("imu", s, rng.standard_normal(3), rng.standard_normal(3)))
+        cursor += n
+
+    events.append(("until", t0 + 0.01))                 # empty buffer
+    store(5)
+    events.append(("until", t0 - 1.0))                  # t_end <= state time
+    events.append(("until", stamps[0] - 1e-4))          # before the first sample: nothing happens (:240)
+    events.append(("until", 0.5 * (stamps[2] + stamps[3])))   # between samples: last partial step with sample 2
+    events.append(("until", stamps[3] + 5e-7))          # the next sample is closer than 1e-6 past ... and t_end too
+    store(10)
+    events.append(("until", stamps[9]))                 # exactly on a sample
+    events.append(("until", stamps[14] + 0.02))         # beyond the last stored sample: partial step with the last one
+    store(20)                                           # these include samples OLDER than the state time now
+    events.append(("until", stamps[30]))
+    store(25)
+    events.append(("until", stamps[59] - 1e-7))
+    events.append(("until", stamps[59] + 1e-3))
+    flat = []
+    for e in events:
+        if e[0] == "init":
+            flat += [e[1]]
+        elif e[0] == "imu":
+            flat += [0.0, e[1]] + list(e[2]) + list(e[3])
+        else:
+            flat += [1.0, e[1]]
+    fin, fout = str(tmp_path / "ev.bin"), str(tmp_path / "out.bin")
+    np.asarray(flat, np.float64).tofile(fin)
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "EVENTS DONE" in r.stdout, r.stdout + r.stderr
+    got = np.fromfile(fout, np.float64)
+    # the oracle, with the transition replaced by a recorder (the loop logic is what is compared)
+    st = o.State(o.FilterParams(max_sw_clones=3, enable_gnss=0))
+    st.timestamp = t0
+    prop = o.ImuPropagator(9.8)
+    steps = []
+
+    def record(state, ctrl, dt, is_analytic=True):
+        steps.append((ctrl.gyro_raw.copy(), ctrl.accel_raw.copy(), dt))
+        state.timestamp += dt
+        return np.eye(15), np.zeros((15, 12))
+    prop.state_and_cov_transition = record
+    from ingvio_oracle import StateManager
+    orig = StateManager.propagate_state_cov
+    StateManager.propagate_state_cov = staticmethod(lambda *a, **k: None)
+    try:
+        pos, n_until, n_steps_total = 0, 0, 0
+        for e in events[1:]:
+            if e[0] == "imu":
+                prop.store_imu(o.ImuCtrl(e[1], e[2], e[3]))        # (timestamp, gyro, accel)
+                continue
+            steps.clear()
+            prop.propagate_until(st, e[1])
+            ts, nbuf, n = got[pos], int(got[pos + 1]), int(got[pos + 2])
+            assert ts == st.timestamp, (e, ts, st.timestamp)
+            assert nbuf == len(prop.imu_ctrl_buffer), (e, nbuf, len(prop.imu_ctrl_buffer))
+            assert n == len(steps), (e, n, len(steps))
+            for s in range(n):
+                rec = got[pos + 3 + 7 * s:pos + 3 + 7 * (s + 1)]
+                assert np.array_equal(rec[0:3], steps[s][0]) and np.array_equal(rec[3:6], steps[s][1]) and rec[6] == steps[s][2], (e, s)
+            pos += 3 + 7 * n
+            n_until += 1
+            n_steps_total += n
+        assert pos == len(got) and n_until == 10 and n_steps_total > 40
+    finally:
+        StateManager.propagate_state_cov = orig
+
