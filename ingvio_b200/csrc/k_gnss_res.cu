@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(128) k_sat_states(SatArgs a) {
 
 }  // namespace
 
+#ifndef IGV_EMULATE   // tests/emul compiles the kernels above for the CPU and launches them itself
 void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l) {
   IgvProfScope prof_scope_(h, IGV_K_GNSS_ROWS);
   ResArgs a;
@@ -357,3 +358,4 @@ void igv_launch_sat_states(igv_batch* h, int S, const double* eph, const double*
   k_sat_states<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
   h->launches++;
 }
+#endif  // IGV_EMULATE
