@@ -159,3 +159,37 @@ def test_emulated_triangulation_kernel_matches_oracle(wname):
         assert n_ok > wl.feats and not ok[:, 1].any()
     finally:
         tab.close()
+
+
+def test_maximum_sizes_emulated():
+    """T = M = 4096 (the limits of igv_tracks_create / igv_tracks_collect): every id of a full message gets its own entry in
+    message order, the next message finds all of them again (in another order), a third one with 4096 other ids overflows."""
+    T = M = 4096
+    tab = EmulatedTrackTable(1, 2, 8, T, False)
+    try:
+        R = np.eye(3)[None]
+        tab.augment(R, np.zeros((1, 3)))
+        rng = np.random.default_rng(1)
+        ids = (rng.permutation(M).astype(np.uint64) * np.uint64(7) + np.uint64(1 << 33))[None]      # distinct after narrowing
+        uv = rng.standard_normal((1, M, 2))
+        tab.collect_meas(np.array([M], np.int32), ids, uv)
+        d = tab.get_map_server(obs_slots=2)
+        assert d["n_tracks"][0] == T and tab.flags()[0] == 0
+        narrowed = (ids[0] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        narrowed = np.where(narrowed >= 2 ** 31, narrowed - 2 ** 32, narrowed).astype(np.int32)
+        assert np.array_equal(d["id"][0], narrowed)                        # entry k <- k-th measurement of the message
+        assert np.array_equal(d["obs"][0][:, 0, :], uv[0])
+        tab.augment(R, np.ones((1, 3)))
+        perm = rng.permutation(M)
+        uv2 = rng.standard_normal((1, M, 2))
+        tab.collect_meas(np.array([M], np.int32), ids[:, perm], uv2)
+        d = tab.get_map_server(obs_slots=2)
+        assert d["n_tracks"][0] == T and np.all(d["slot_mask"][0] == 3) and tab.flags()[0] == 0
+        inv = np.empty(M, np.int64)
+        inv[perm] = np.arange(M)
+        assert np.array_equal(d["obs"][0][:, 1, :], uv2[0][inv])
+        other = (np.arange(M, dtype=np.uint64) + np.uint64(10 ** 9))[None]
+        tab.collect_meas(np.array([M], np.int32), other, uv)
+        assert tab.flags()[0] == 8 and tab.get_map_server(obs_slots=2)["n_tracks"][0] == T      # IGV_FLAG_TRACKS_FULL
+    finally:
+        tab.close()
