@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) k_sat_states(SatArgs a) {
 
 }  // namespace
 
-#ifndef IGV_EMULATE   // tests/emul compiles the kernels above for the CPU and launches them itself
+#if !defined(IGV_EMULATE) || defined(IGV_EMULATE_LAUNCHERS)   // tests/emul: kernels only, or (full model) launchers too
 void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l) {
   IgvProfScope prof_scope_(h, IGV_K_GNSS_ROWS);
   ResArgs a;

@@ -358,7 +358,7 @@ __global__ void k_trk_count(TrkPtrs p, int* n_tracks) {
   }
 }
 
-#ifndef IGV_EMULATE
+#if !defined(IGV_EMULATE) || defined(IGV_EMULATE_LAUNCHERS)   // tests/emul: kernels only, or (full model) launchers too
 TrkPtrs ptrs(const igv_batch* h) {
   TrkPtrs p;
   p.T = h->trk.T; p.C = h->trk.C; p.rho = h->rho; p.B = h->B;
@@ -411,7 +411,7 @@ bool igv_trk_slot_bits(const IgvTrackTable& t, int n, const int* slots, unsigned
   return true;
 }
 
-#ifndef IGV_EMULATE
+#if !defined(IGV_EMULATE) || defined(IGV_EMULATE_LAUNCHERS)   // tests/emul: kernels only, or (full model) launchers too
 void igv_launch_trk_reset(igv_batch* h) {
   IgvProfScope prof_scope_(h, IGV_K_OTHER);
   k_trk_reset<<<per_track_grid(h), 256, 0, h->stream>>>(ptrs(h));

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128) k_triangulate(TriArgs a) {
 
 }  // namespace
 
-#ifndef IGV_EMULATE   // tests/emul compiles the kernel above for the CPU and launches it itself
+#if !defined(IGV_EMULATE) || defined(IGV_EMULATE_LAUNCHERS)   // tests/emul: kernels only, or (full model) launchers too
 void igv_launch_triangulate(igv_batch* h, int F, int obs_slots, const double* obs, const unsigned char* mask,
                             const int* anchor, const igv_tri_params& prm, double* pf_out, unsigned char* ok_out) {
   IgvProfScope prof_scope_(h, IGV_K_OTHER);

@@ -55,9 +55,10 @@ inline unsigned long long exchange(unsigned long long v, int src_lane) {
 // Run kernel(args...) over grid x block with `smem` bytes of dynamic shared memory. blockDim.x must be a multiple of
 // 32 and every thread of a warp that calls a warp intrinsic must reach it (true for the kernels tested here).
 template <class F>
-void launch(unsigned grid, unsigned block, size_t smem, F&& body) {
+void launch(dim3 grid3, unsigned block, size_t smem, F&& body) {
   g_blockDim = dim3(block, 1, 1);
-  g_gridDim = dim3(grid, 1, 1);
+  g_gridDim = grid3;
+  const unsigned grid = grid3.x * grid3.y * grid3.z;
   for (unsigned b = 0; b < grid; ++b) {
     g_dyn_smem.assign(smem + 16, 0);
     g_cta_bar = std::make_unique<std::barrier<>>(block);
@@ -69,12 +70,17 @@ void launch(unsigned grid, unsigned block, size_t smem, F&& body) {
     for (unsigned t = 0; t < block; ++t)
       th.emplace_back([&, b, t] {
         t_threadIdx = uint3{t, 0, 0};
-        t_blockIdx = uint3{b, 0, 0};
+        t_blockIdx = uint3{b % grid3.x, (b / grid3.x) % grid3.y, b / (grid3.x * grid3.y)};
         body();
         g_cta_bar->arrive_and_drop();   // a finished thread no longer takes part in __syncthreads
       });
     for (auto& x : th) x.join();
   }
+}
+// kernel<<<grid, block, smem, stream>>>(args) as rewritten by tests/emul/preprocess.py (synchronous; 1-D blocks)
+template <class F>
+void launch_k(F&& body, dim3 grid, dim3 block, size_t smem = 0, cudaStream_t = nullptr) {
+  launch(grid, block.x, smem, body);
 }
 }  // namespace emul
 
@@ -116,6 +122,10 @@ template <class T>
 inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)(threadIdx.x & 31) ^ lane_mask); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline double __drcp_rn(double x) { return 1.0 / x; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

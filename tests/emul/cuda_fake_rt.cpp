@@ -1,0 +1,37 @@
+// TEST INFRASTRUCTURE: the handful of CUDA runtime entry points the library's host code (igv_api.cu, the launchers) calls,
+// with host-memory semantics, so that the C-ABI's own host logic (staging, pointer modes, variable bookkeeping, hooks) runs in
+// `pytest -m "not gpu"` on top of the CPU execution model of the kernels. "Device" memory is the heap, streams and events
+// are no-ops (every emulated launch is synchronous). Only linked into tests/emul/_build/libingvio_emul.so.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+
+static cudaError_t g_last = cudaSuccess;
+extern "C" void igv_emul_set_last_error(int e) { g_last = (cudaError_t)e; }
+
+extern "C" {
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < h; ++r) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+  return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { const cudaError_t e = g_last; g_last = cudaSuccess; return e; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "kernel not available in the CPU model (FP64 tensor-pipe kernels run on the GPU only)"; }
+}
