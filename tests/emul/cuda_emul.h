@@ -38,6 +38,7 @@ inline std::vector<char> g_dyn_smem;
 struct WarpBox {
   std::unique_ptr<std::barrier<>> bar;
   unsigned long long vals[32];
+  double fa[32], fb[32];          // DMMA fragments
 };
 inline std::vector<WarpBox> g_warps;
 inline std::unique_ptr<std::barrier<>> g_cta_bar;
@@ -76,6 +77,20 @@ void launch(dim3 grid3, unsigned block, size_t smem, F&& body) {
       });
     for (auto& x : th) x.join();
   }
+}
+// mma.sync.aligned.m8n8k4.row.col.f64: lane l supplies A(l/4, l%4) and B(l%4, l/4) and owns C(l/4, 2(l%4) + {0,1}).
+inline void dmma884(double& d0, double& d1, double a, double b) {
+  WarpBox& w = my_warp();
+  const int lane = t_threadIdx.x & 31;
+  w.fa[lane] = a;
+  w.fb[lane] = b;
+  w.bar->arrive_and_wait();
+  const int row = lane >> 2, c0 = 2 * (lane & 3);
+  for (int k = 0; k < 4; ++k) {
+    d0 = std::fma(w.fa[row * 4 + k], w.fb[c0 * 4 + k], d0);
+    d1 = std::fma(w.fa[row * 4 + k], w.fb[(c0 + 1) * 4 + k], d1);
+  }
+  w.bar->arrive_and_wait();
 }
 // kernel<<<grid, block, smem, stream>>>(args) as rewritten by tests/emul/preprocess.py (synchronous; 1-D blocks)
 template <class F>
@@ -126,6 +141,7 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double __drcp_rn(double x) { return 1.0 / x; }
+inline size_t __cvta_generic_to_shared(const void*) { return 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -1,9 +1,14 @@
 """The C-ABI's OWN host code (igv_api.cu: staging of host arguments, pointer modes, variable bookkeeping, window hooks of the
 track table) together with the kernels the CPU execution model covers, built by tests/emul/build_lib.py into
 libingvio_emul.so and driven through the regular binding (ingvio_b200.capi / BatchFilter) -- so the GPU tests of those
-entry points also run, unchanged, in `pytest -m "not gpu"`. Calls that need a DMMA kernel must fail loudly, not fall back.
+entry points also run, unchanged, in `pytest -m "not gpu"`. The FP64 tensor-pipe kernels are modelled too (mma.sync.m8n8k4.f64
+as an exchange between the 32 threads of a warp, tests/emul/cuda_emul.h), so a curated set of the parity tests of propagation,
+EKF update, MSCKF update, GNSS update and delayed initialisation -- and the C++ estimator mirror against the oracle -- run here
+as well, on small workloads (one CTA thread = one OS thread: seconds per frame).
 
-(IGV_TEST_LIB=emul python -m pytest tests/test_gpu_tracks.py -m gpu   runs whole GPU test files this way; slow.)"""
+(IGV_TEST_LIB=emul python -m pytest tests/test_gpu_parity.py -m gpu   runs whole GPU test files this way; slow. Known gap: the
+forced `stream` Householder variants of tests/test_gpu_qr_variants.py do not reproduce on the model -- cause not established --
+while they are green on B200.)"""
 import os
 import subprocess
 import sys
@@ -41,15 +46,34 @@ def test_layout_and_init(cpu_model):
     test_gpu_parity.test_layout_and_init()          # state init, add / marginalise GNSS variables, covariance read-back
 
 
-def test_dmma_calls_fail_loudly(cpu_model):
-    from ingvio_b200.filter import BatchFilter
-    g = BatchFilter(1, 3, 4, 1)
-    eye, z = np.eye(3).reshape(1, 9), np.zeros((1, 3))
-    g.init_state_and_cov(eye, z, z, z, z, eye, z, np.full(21, 1e-2))
-    with pytest.raises(capi.IgvError) as e:
-        g.propagate_imu(np.zeros((1, 1, 3)), np.zeros((1, 1, 3)), np.full((1, 1), 0.01))
-    assert e.value.status == capi.IGV_ERR_CUDA and "not available in the CPU model" in str(e.value)
-    g.close()
+def test_peak_probe_is_not_modelled(cpu_model):
+    """What the model does not provide fails loudly instead of returning numbers."""
+    import ctypes as C
+    out = C.c_double(-1.0)
+    assert capi.load().igv_measure_fp64_peak(0, C.byref(out)) == capi.IGV_ERR_CUDA
+
+
+@pytest.mark.parametrize("name,args", [
+    ("test_propagate_cov_random_phi", ()), ("test_imu_propagate_and_augment", ()), ("test_marginalize_clone_and_gnss", ()),
+    ("test_ekf_update_sparse_var_order", ("iso",)), ("test_msckf_all_obs_frames", ("tiny",)),
+    ("test_gnss_update", ({},)), ("test_delayed_init_and_replace_var_linear", ())])
+def test_parity_cases_on_cpu_model(cpu_model, name, args):
+    """tests/test_gpu_parity.py, unchanged, with the kernel sources executed by the CPU model (same 1e-8 / 1e-9 bars)."""
+    import test_gpu_parity
+    getattr(test_gpu_parity, name)(*args)
+
+
+def test_cpp_estimator_mirror_vs_oracle(cpu_model, tmp_path):
+    """tests/cpp/test_updaters_frames.cpp (IngvioFilter callbacks -> ImuPropagator -> updaters -> fused device chain) against the
+    oracle filter driven by the oracle MapServer, frame by frame (the GPU twin is tests/test_cpp_updaters.py)."""
+    import test_cpp_updaters as tcu
+    saved = (tcu.LIBDIR, tcu.LIBNAME)
+    tcu.LIBDIR, tcu.LIBNAME = os.path.dirname(cpu_model), "ingvio_emul"
+    try:
+        tcu.test_updater_mirror_vs_oracle.__wrapped__(tmp_path, False, False) if hasattr(tcu.test_updater_mirror_vs_oracle, "__wrapped__") \
+            else tcu.test_updater_mirror_vs_oracle(tmp_path, False, False)
+    finally:
+        tcu.LIBDIR, tcu.LIBNAME = saved
 
 
 @pytest.mark.parametrize("stereo", [False, True])
