@@ -430,6 +430,10 @@ __global__ void __launch_bounds__(32, MINB) k_qr_stream(QrArgs a) {
           q3 = fma(tile[r + 3][sj], tile[r + 3][sj], q3);
         }
         ss = (q0 + q1) + (q2 + q3);
+        // Every lane read alpha = Rp[oj] at the top of this step and lane lj overwrites it below: without this barrier the
+        // order is only guaranteed by the lanes running in lockstep (found by the CPU execution model of tests/emul, where
+        // they do not).
+        __syncwarp();
         if constexpr (BF) {
           // every lane stores (non-owners into the dump area): no divergent region at the end of the step
           double* dst = pub ? vnext : dump;

@@ -6,9 +6,8 @@ as an exchange between the 32 threads of a warp, tests/emul/cuda_emul.h), so a c
 EKF update, MSCKF update, GNSS update and delayed initialisation -- and the C++ estimator mirror against the oracle -- run here
 as well, on small workloads (one CTA thread = one OS thread: seconds per frame).
 
-(IGV_TEST_LIB=emul python -m pytest tests/test_gpu_parity.py -m gpu   runs whole GPU test files this way; slow. Known gap: the
-forced `stream` Householder variants of tests/test_gpu_qr_variants.py do not reproduce on the model -- cause not established --
-while they are green on B200.)"""
+(IGV_TEST_LIB=emul python -m pytest tests/test_gpu_parity.py -m gpu   runs whole GPU test files this way; slow. The model's threads
+do not run in lockstep, which is how it found the one access in k_qr_stream that only lockstep execution ordered.)"""
 import os
 import subprocess
 import sys
@@ -61,6 +60,15 @@ def test_parity_cases_on_cpu_model(cpu_model, name, args):
     """tests/test_gpu_parity.py, unchanged, with the kernel sources executed by the CPU model (same 1e-8 / 1e-9 bars)."""
     import test_gpu_parity
     getattr(test_gpu_parity, name)(*args)
+
+
+def test_stream_householder_variant(cpu_model, monkeypatch):
+    """The single-warp Householder kernel (k_qr_stream, forced through IGV_QR_CFG=8 like tests/test_gpu_qr_variants.py): wrong on
+    this model until the read of R[j][j] and its overwrite by the owner lane were ordered by a __syncwarp() -- kept here as the
+    regression test of that fix."""
+    import test_gpu_parity
+    monkeypatch.setenv("IGV_QR_CFG", "8")
+    test_gpu_parity.test_msckf_all_obs_frames("tiny")
 
 
 def test_cpp_estimator_mirror_vs_oracle(cpu_model, tmp_path):
