@@ -52,7 +52,9 @@ def build():
         for cmd, r in ex.map(run, jobs):
             if r.returncode != 0:
                 raise RuntimeError("emulation build failed: " + " ".join(cmd[-3:]) + "\n" + (r.stdout + r.stderr)[:4000])
-    r = subprocess.run(["g++", "-shared", "-pthread", "-o", OUT] + objs, capture_output=True, text=True)
+    # -Bsymbolic: the model's own cuda* / igv_* definitions must win over a CUDA runtime another library (the real .so, torch)
+    # may already have brought into the process
+    r = subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", OUT] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulation link failed:\n" + (r.stdout + r.stderr)[:4000])
     return OUT
