@@ -19,14 +19,16 @@ from . import capi
 
 
 class DeviceMapServer:
-    def __init__(self, filt, max_tracks, obs_slots=None, tri_params=None):
+    def __init__(self, filt, max_tracks, obs_slots=None, tri_params=None, device="cuda"):
+        """device: where the scratch tensors live. "cuda" (default) chains the calls in DEVICE pointer mode; host tensors make
+        every call a HOST-pointer call (staged copies), which is how the CPU-side tests drive the same sequence."""
         import torch
         self.f = filt
         self.torch = torch
         filt.create_map_server(max_tracks)
         B, F = filt.B, filt.max_feats
         SW = int(obs_slots or filt.max_clones)
-        dev = torch.device("cuda")
+        dev = torch.device(device)
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
         self.buf = dict(track_entry=z((B, F), torch.int32), n_sel=z((B,), torch.int32), track_id=z((B, F), torch.int32),
                         obs=z((B, F, SW, filt.rho), torch.float64), mask_all=z((B, F, SW), torch.uint8),
@@ -36,7 +38,8 @@ class DeviceMapServer:
         self.ok = z((B, F), torch.uint8)
         self.SW, self.F = SW, F
         self.tri_params = dict(tri_params or {})
-        torch.cuda.synchronize()   # the zero-fills ran on torch's stream; the handle enqueues on its own
+        if dev.type == "cuda":
+            torch.cuda.synchronize()   # the zero-fills ran on torch's stream; the handle enqueues on its own
 
     def collect(self, n_meas, ids, uv):
         """One tracker message per sequence (host arrays or CUDA tensors) at the newest clone."""

@@ -109,6 +109,13 @@ def test_track_table_scenario(cpu_model, mode, stereo, SW):
     g.close()
 
 
+def test_frames_from_tracker_messages_host_mode(cpu_model):
+    """DeviceMapServer's frame sequence (collect -> RemoveLost -> SwMarg -> slide -> eraseInvalid) vs the oracle front end, with
+    host scratch tensors: every call goes through the staging path of HOST pointer mode."""
+    import test_gpu_tracks
+    test_gpu_tracks.frames_from_tracker_messages(False, False, "cpu", n_frames=8, B=1)
+
+
 def test_golden_replay(cpu_model):
     import test_golden_tracks
     test_golden_tracks.test_cuda_vs_golden("mono")

@@ -174,18 +174,24 @@ def test_errors():
 @pytest.mark.parametrize("keyframe,stereo", [(False, False), (True, False), (False, True)])
 def test_frames_from_tracker_messages(keyframe, stereo):
     """Tracker messages in, filter state out: DeviceMapServer (device-pointer chain) vs the oracle front end."""
+    frames_from_tracker_messages(keyframe, stereo, "cuda")
+
+
+def frames_from_tracker_messages(keyframe, stereo, device, n_frames=14, B=3):
+    """device "cpu": the same sequence with host scratch tensors, i.e. HOST pointer mode on every call
+    (tests/test_capi_on_cpu_model.py runs that on the CPU model of the library)."""
     import torch
     from ingvio_b200.map_server import DeviceMapServer
-    SW, B, F = 5, 3, 32
+    SW, F = 5, 32
     wl = Workload("trk", 11 + int(stereo), SW + (0 if keyframe else 1), F, 0, stereo=stereo)
     fp = filter_params(wl, max_sw_clones=SW, frame_select_interval=2)
     st = SyntheticStream(wl, B)
     trk = TrackerStream(st, 18, 32, id_base=(1 << 33))
     fes = [OracleFrontEnd(f, keyframe) for f in make_oracles(wl, st, fp, with_gnss=False)]
     g = make_gpu(wl, st, fp, with_gnss=False)
-    dms = DeviceMapServer(g, 96)
+    dms = DeviceMapServer(g, 96, device=device)
     used = 0
-    for k in range(14):
+    for k in range(n_frames):
         st.n_clones = 0
         fr = st.next_frame(with_visual=False, with_gnss=False, marg_oldest=False)
         n, ids, uv = trk.message(fr.t)
@@ -211,5 +217,6 @@ def test_frames_from_tracker_messages(keyframe, stereo):
         orc.states = [fe.f.state for fe in fes]
         check_tables(g, orc, wl.sw, f"frame {k} tables", pf_tol=1e-7)
     assert used > 0 and not g.flags().any()
-    torch.cuda.synchronize()
+    if device == "cuda":
+        torch.cuda.synchronize()
     g.close()
