@@ -104,6 +104,9 @@ igv_status igv_set_params(igv_batch* h, const igv_params* p);
 /* chi^2 quantile table: table[d-1] = quantile(d), d = 1..max_dof.  Replaces
  * UpdateBase::setChiSquaredTable (Update.cpp:27-34, boost::math::quantile). */
 igv_status igv_set_chi2_table(igv_batch* h, const double* table, int max_dof);
+/* quantile(chi_squared(dof), p) without Boost (Update.cpp:31-32); igv_add_variable_delayed uses it with the
+ * reference's hard-coded p = 0.95 (StateManager.cpp:613-615), independent of the table above. NaN on bad input. */
+double igv_chi2_quantile(double p, int dof);
 
 /* ---- state: variables and mean --------------------------------------------------------------
  * State::State + State::initStateAndCov (State.cpp:60-91,126-167): variables SE23@0, bg@9, ba@12,

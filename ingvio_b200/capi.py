@@ -107,6 +107,7 @@ SIGNATURES = {
     "igv_launch_count": (C.c_longlong, [_H]),
     "igv_set_params": (C.c_int, [_H, C.POINTER(igv_params)]),
     "igv_set_chi2_table": (C.c_int, [_H, c_dp, C.c_int]),
+    "igv_chi2_quantile": (C.c_double, [C.c_double, C.c_int]),
     "igv_state_init": (C.c_int, [_H] + [_VP] * 7 + [c_dp]),
     "igv_dim": (C.c_int, [_H]),
     "igv_num_variables": (C.c_int, [_H]),

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "igv_internal.h"
@@ -182,6 +183,34 @@ igv_status trk_slot_bits(igv_batch* h, int n, const int* slots, unsigned long lo
   return IGV_OK;
 }
 
+// Regularised lower incomplete gamma P(a, x): series below a + 1, Lentz continued fraction above.
+double reg_gamma_p(double a, double x) {
+  if (!(x > 0.0)) return 0.0;
+  const double pre = std::exp(a * std::log(x) - x - std::lgamma(a));
+  if (x < a + 1.0) {
+    double term = 1.0 / a, sum = term;
+    for (int k = 1; k < 2000; ++k) {
+      term *= x / (a + k);
+      sum += term;
+      if (term < sum * 1e-17) break;
+    }
+    return pre * sum;
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, f = d;
+  for (int k = 1; k < 2000; ++k) {
+    const double an = -k * (k - a);
+    b += 2.0;
+    d = an * d + b; if (std::fabs(d) < tiny) d = tiny;
+    c = b + an / c; if (std::fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double delta = c * d;
+    f *= delta;
+    if (std::fabs(delta - 1.0) < 1e-16) break;
+  }
+  return 1.0 - pre * f;
+}
+
 }  // namespace
 
 IgvLayout igv_batch::layout() const {
@@ -218,8 +247,21 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
     igv_destroy(h);
     return IGV_ERR_CUDA;
   };
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) return bail("cudaSetDevice", e);
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore_{prev_dev == cfg->device ? -1 : prev_dev};
+  {
+    auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+    h->knobs.fuse = knob("IGV_FUSE", -1);
+    h->knobs.qr_cfg = knob("IGV_QR_CFG", 0);
+    h->knobs.qr_split = knob("IGV_QR_SPLIT", 0);
+    h->knobs.gram_cfg = knob("IGV_GRAM_CFG", 0);
+    h->knobs.factor_cfg = knob("IGV_FACTOR_CFG", 0);
+    h->knobs.tri_cfg = knob("IGV_TRI_CFG", 0);
+    h->knobs.graph = knob("IGV_GRAPH", -1);
+  }
   if (cfg->stream) {
     h->stream = static_cast<cudaStream_t>(cfg->stream);
   } else {
@@ -285,6 +327,7 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
 }
 
 igv_status igv_destroy(igv_batch* h) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
@@ -306,12 +349,14 @@ igv_status igv_destroy(igv_batch* h) {
 const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "null handle"; }
 
 igv_status igv_set_pointer_mode(igv_batch* h, int mode) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || (mode != IGV_PTR_HOST && mode != IGV_PTR_DEVICE)) return IGV_ERR_INVALID;
   h->ptr_mode = mode;
   return IGV_OK;
 }
 
 igv_status igv_set_compression(igv_batch* h, int kind) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || kind < IGV_COMPRESS_AUTO || kind > IGV_COMPRESS_GRAM) return IGV_ERR_INVALID;
   h->compress = kind;
   return IGV_OK;
@@ -320,6 +365,7 @@ igv_status igv_set_compression(igv_batch* h, int kind) {
 int igv_last_visual_path(const igv_batch* h) { return h ? h->last_visual_path : -1; }
 
 igv_status igv_synchronize(igv_batch* h) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_ERR_INVALID;
   IGV_CUDA(h, cudaStreamSynchronize(h->stream));
   return IGV_OK;
@@ -328,6 +374,7 @@ igv_status igv_synchronize(igv_batch* h) {
 long long igv_launch_count(const igv_batch* h) { return h ? h->launches : 0; }
 
 igv_status igv_set_params(igv_batch* h, const igv_params* p) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !p) return IGV_ERR_INVALID;
   h->params.noise_g = p->noise_g; h->params.noise_a = p->noise_a;
   h->params.noise_bg = p->noise_bg; h->params.noise_ba = p->noise_ba;
@@ -337,7 +384,36 @@ igv_status igv_set_params(igv_batch* h, const igv_params* p) {
   return IGV_OK;
 }
 
+// chi^2 quantile by safeguarded Newton on P(dof/2, x/2) = p, started from the Wilson-Hilferty cube
+// (replaces boost::math::quantile(chi_squared(dof), p), Update.cpp:31-32, StateManager.cpp:613-615).
+double igv_chi2_quantile(double p, int dof) {
+  if (!(p > 0.0 && p < 1.0) || dof < 1) return NAN;
+  const double a = 0.5 * dof;
+  // normal quantile for the start: bisection on erfc is plenty (only a starting point)
+  double zlo = -8.0, zhi = 8.0;
+  for (int it = 0; it < 60; ++it) {
+    const double zm = 0.5 * (zlo + zhi);
+    if (0.5 * std::erfc(-zm / std::sqrt(2.0)) < p) zlo = zm; else zhi = zm;
+  }
+  const double z = 0.5 * (zlo + zhi), t = 2.0 / (9.0 * dof);
+  double x = dof * std::pow(1.0 - t + z * std::sqrt(t), 3.0);
+  if (!(x > 0.0)) x = a;
+  double lo = 0.0, hi = std::max(2.0 * x, 4.0 * dof + 60.0);
+  for (int it = 0; it < 300; ++it) {
+    const double f = reg_gamma_p(a, 0.5 * x) - p;
+    if (f > 0.0) hi = x; else lo = x;
+    const double dens = 0.5 * std::exp((a - 1.0) * std::log(0.5 * x) - 0.5 * x - std::lgamma(a));
+    double xn = x - f / dens;
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    const bool done = std::fabs(xn - x) <= 2e-15 * std::max(1.0, x);
+    x = xn;
+    if (done) break;
+  }
+  return x;
+}
+
 igv_status igv_set_chi2_table(igv_batch* h, const double* table, int max_dof) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !table || max_dof < 1 || max_dof > 1024) return IGV_ERR_INVALID;
   IGV_CUDA(h, cudaMemcpyAsync(h->chi2, table, sizeof(double) * max_dof, cudaMemcpyHostToDevice, h->stream));
   IGV_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -349,6 +425,7 @@ igv_status igv_set_chi2_table(igv_batch* h, const double* table, int max_dof) {
 // ---- state ----------------------------------------------------------------------------------------
 igv_status igv_state_init(igv_batch* h, const double* R_i2w, const double* p, const double* v, const double* bg,
                           const double* ba, const double* R_ext, const double* p_ext, const double* cov_diag21) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !R_i2w || !p || !v || !bg || !ba || !R_ext || !p_ext || !cov_diag21) return IGV_ERR_INVALID;
   arena_reset(h);
   const size_t B = h->B;
@@ -393,6 +470,7 @@ int igv_gnss_idx(const igv_batch* h, int gtype) {
 int igv_state_size(const igv_batch* h) { return h ? h->xsize : -1; }
 
 igv_status igv_state_get(igv_batch* h, double* dst) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !dst) return IGV_ERR_INVALID;
   const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   IGV_CUDA(h, cudaMemcpyAsync(dst, h->Xc(), sizeof(double) * h->B * h->xsize, k, h->stream));
@@ -400,12 +478,14 @@ igv_status igv_state_get(igv_batch* h, double* dst) {
   return IGV_OK;
 }
 igv_status igv_state_get_async(igv_batch* h, double* dst) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !dst) return IGV_ERR_INVALID;
   const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   IGV_CUDA(h, cudaMemcpyAsync(dst, h->Xc(), sizeof(double) * h->B * h->xsize, k, h->stream));
   return IGV_OK;
 }
 igv_status igv_state_set(igv_batch* h, const double* src) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !src) return IGV_ERR_INVALID;
   const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   IGV_CUDA(h, cudaMemcpyAsync(h->Xc(), src, sizeof(double) * h->B * h->xsize, k, h->stream));
@@ -414,6 +494,7 @@ igv_status igv_state_set(igv_batch* h, const double* src) {
 
 // ---- covariance -------------------------------------------------------------------------------------
 igv_status igv_cov_get(igv_batch* h, double* dst, int ld) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !dst || ld < h->N) return IGV_ERR_INVALID;
   arena_reset(h);
   double* dev;
@@ -425,6 +506,7 @@ igv_status igv_cov_get(igv_batch* h, double* dst, int ld) {
   return IGV_OK;
 }
 igv_status igv_cov_set(igv_batch* h, const double* src, int ld) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !src || ld < h->N) return IGV_ERR_INVALID;
   arena_reset(h);
   const double* dev;
@@ -433,6 +515,7 @@ igv_status igv_cov_set(igv_batch* h, const double* src, int ld) {
   return check_launch(h);
 }
 igv_status igv_cov_get_blocks(igv_batch* h, int n_blocks, const int* idx, const int* size, double* dst) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !dst) return IGV_ERR_INVALID;
   arena_reset(h);
   IgvBlocks blk;
@@ -462,6 +545,7 @@ static igv_status add_variable(igv_batch* h, IgvVarKind kind, int tag, int size,
 }
 
 igv_status igv_add_gnss_variable(igv_batch* h, int gtype, const double* value, double cov) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || gtype < 0 || gtype > 5) return IGV_ERR_INVALID;
   arena_reset(h);
   if (h->layout().idx_gnss[gtype] >= 0) return fail(h, IGV_ERR_STATE, "GNSS variable already in the state");
@@ -489,6 +573,7 @@ static igv_status marginalize_var(igv_batch* h, size_t vi) {
 }
 
 igv_status igv_marg_gnss_variable(igv_batch* h, int gtype) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || gtype < 0 || gtype > 5) return IGV_ERR_INVALID;
   for (size_t i = 0; i < h->vars.size(); ++i)
     if (h->vars[i].kind == VK_GNSS && h->vars[i].tag == gtype) {
@@ -501,12 +586,14 @@ igv_status igv_marg_gnss_variable(igv_batch* h, int gtype) {
 }
 
 igv_status igv_add_variable_independent(igv_batch* h, int size, const double* cov_block) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || size < 1 || size > 6 || !cov_block) return IGV_ERR_INVALID;
   arena_reset(h);
   return add_variable(h, VK_OPAQUE, 0, size, cov_block);
 }
 
 igv_status igv_marginalize(igv_batch* h, int idx) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_ERR_INVALID;
   for (size_t i = 0; i < h->vars.size(); ++i)
     if (h->vars[i].idx == idx) return marginalize_var(h, i);
@@ -514,6 +601,7 @@ igv_status igv_marginalize(igv_batch* h, int idx) {
 }
 
 igv_status igv_marginalize_clone(igv_batch* h, int slot) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_ERR_INVALID;
   int s = 0;
   for (size_t i = 0; i < h->vars.size(); ++i)
@@ -526,7 +614,10 @@ igv_status igv_marginalize_clone(igv_batch* h, int slot) {
 
 // ---- propagation ------------------------------------------------------------------------------------
 igv_status igv_propagate_cov(igv_batch* h, const double* Phi, const double* G, const double* dt) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !Phi || !G || !dt) return IGV_ERR_INVALID;
+  if ((size_t)20 * h->N * sizeof(double) > 96 * 1024)
+    return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds the propagation strip");
   arena_reset(h);
   const double *dP, *dG, *ddt;
   IGV_TRY(stage(h, Phi, (size_t)h->B * 225, &dP));
@@ -537,8 +628,11 @@ igv_status igv_propagate_cov(igv_batch* h, const double* Phi, const double* G, c
 }
 
 igv_status igv_propagate_imu(igv_batch* h, int n_steps, const double* gyro, const double* accel, const double* dt) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || n_steps < 0 || !gyro || !accel || !dt) return IGV_ERR_INVALID;
   if (n_steps == 0) return IGV_OK;
+  if ((size_t)20 * h->N * sizeof(double) > 96 * 1024)   // k_propagate's strip (checked BEFORE the mean is advanced)
+    return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds the propagation strip");
   arena_reset(h);
   const double *dg, *da, *ddt;
   IGV_TRY(stage(h, gyro, (size_t)h->B * n_steps * 3, &dg));
@@ -559,10 +653,12 @@ static igv_status augment(igv_batch* h, const double* R, const double* cR, const
   return check_launch(h);
 }
 igv_status igv_augment_clone(igv_batch* h) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_ERR_INVALID;
   return augment(h, nullptr, nullptr, nullptr);
 }
 igv_status igv_augment_clone_cov(igv_batch* h, const double* R_i2w, const double* clone_R, const double* clone_p) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !R_i2w || ((clone_R == nullptr) != (clone_p == nullptr))) return IGV_ERR_INVALID;
   arena_reset(h);
   const double *dR, *dcR, *dcp;
@@ -576,6 +672,7 @@ igv_status igv_augment_clone_cov(igv_batch* h, const double* R_i2w, const double
 static igv_status ekf_common(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows,
                              const double* H, int ldh, const double* res, const double* R, int r_kind, double* dx_out,
                              double* gamma_out, bool gamma_only) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !H || !res || rows < 1 || ldh < rows) return IGV_ERR_INVALID;
   if (r_kind != IGV_R_ISO && r_kind != IGV_R_DIAG && r_kind != IGV_R_FULL) return IGV_ERR_INVALID;
   if (!R) return IGV_ERR_INVALID;
@@ -604,15 +701,18 @@ static igv_status ekf_common(igv_batch* h, int n_blocks, const int* blk_idx, con
 
 igv_status igv_ekf_update(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows, const double* H,
                           int ldh, const double* res, const double* R, int r_kind, double* dx_out) {
+  IgvDeviceGuard dev_guard_(h);
   return ekf_common(h, n_blocks, blk_idx, blk_size, rows, H, ldh, res, R, r_kind, dx_out, nullptr, false);
 }
 igv_status igv_chi2_whiten(igv_batch* h, int n_blocks, const int* blk_idx, const int* blk_size, int rows, const double* H,
                            int ldh, const double* res, const double* R, int r_kind, double* gamma_out) {
+  IgvDeviceGuard dev_guard_(h);
   if (!gamma_out) return IGV_ERR_INVALID;
   return ekf_common(h, n_blocks, blk_idx, blk_size, rows, H, ldh, res, R, r_kind, nullptr, gamma_out, true);
 }
 
 igv_status igv_box_plus(igv_batch* h, const double* dx) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !dx) return IGV_ERR_INVALID;
   arena_reset(h);
   const double* d;
@@ -623,6 +723,7 @@ igv_status igv_box_plus(igv_batch* h, const double* dx) {
 
 // ---- fused visual update ------------------------------------------------------------------------------
 igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !a) return IGV_ERR_INVALID;
   if (a->n_feats < 0 || a->n_feats > h->cfg.max_feats) return fail(h, IGV_ERR_CAPACITY, "n_feats exceeds max_feats");
   IgvLayout L = h->layout();
@@ -676,6 +777,7 @@ igv_status igv_msckf_update(igv_batch* h, const igv_msckf_args* a) {
 
 // ---- triangulation ----------------------------------------------------------------------------------------
 igv_status igv_triangulate(igv_batch* h, const igv_tri_args* a) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !a || !a->obs || !a->obs_mask || !a->pf_out || !a->ok_out) return IGV_ERR_INVALID;
   if (a->n_feats < 0 || a->n_feats > h->cfg.max_feats) return fail(h, IGV_ERR_CAPACITY, "n_feats exceeds max_feats");
   IgvLayout L = h->layout();
@@ -700,6 +802,7 @@ igv_status igv_triangulate(igv_batch* h, const igv_tri_args* a) {
 
 // ---- GNSS residual generator (gnss_comm::psr_res / dopp_res) ------------------------------------------------
 igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !a) return IGV_ERR_INVALID;
   if (a->n_sats < 0 || a->n_sats > h->cfg.max_sats) return fail(h, IGV_ERR_CAPACITY, "n_sats exceeds max_sats");
   if (a->n_sats == 0) return IGV_OK;
@@ -742,6 +845,7 @@ igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a) {
 
 // ---- ephemeris -> satellite states (gnss_comm::sat_states) ------------------------------------------------------
 igv_status igv_sat_states(igv_batch* h, const igv_sat_state_args* a) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !a) return IGV_ERR_INVALID;
   if (a->n_sats < 0 || a->n_sats > h->cfg.max_sats) return fail(h, IGV_ERR_CAPACITY, "n_sats exceeds max_sats");
   if (a->n_sats == 0) return IGV_OK;
@@ -774,6 +878,7 @@ igv_status igv_sat_states(igv_batch* h, const igv_sat_state_args* a) {
 
 // ---- fused GNSS update --------------------------------------------------------------------------------
 igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !a) return IGV_ERR_INVALID;
   if (a->n_sats < 0 || a->n_sats > h->cfg.max_sats) return fail(h, IGV_ERR_CAPACITY, "n_sats exceeds max_sats");
   if (a->n_sats == 0) return IGV_OK;                       // GnssUpdate.cpp:92-93
@@ -832,12 +937,12 @@ igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value
                                     const int* blk_size, int rows, const double* H_old, const double* H_new,
                                     const double* res, double noise_iso, double chi2_mult, int do_chi2,
                                     double prior_cov_if_rejected, int* accepted_out, double* dx_out) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !H_old || !H_new || !res || rows < 1 || rows > 128 || gtype > 5) return IGV_ERR_INVALID;
   if (rows <= 1) return fail(h, IGV_ERR_INVALID, "H_new rows should be larger than H_new cols");  // StateManager.cpp:574-578
   if (gtype >= 0 && h->layout().idx_gnss[gtype] >= 0) return fail(h, IGV_ERR_STATE, "New var already in state");
   if (h->N + 1 > h->cfg.max_dim) return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds max_dim");
   if (rows - 1 > h->max_rows) return fail(h, IGV_ERR_CAPACITY, "rows exceed the EKF workspace");
-  if (do_chi2 && h->chi2_n < rows) return fail(h, IGV_ERR_STATE, "chi^2 table too short");
   arena_reset(h);
   IgvBlocks blk;
   IGV_TRY(make_blocks(h, n_blocks, blk_idx, blk_size, &blk));
@@ -877,6 +982,7 @@ igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value
 
 igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size, int n_blocks, const int* blk_idx,
                                   const int* blk_size, const double* H) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !H || target_size < 1 || target_size > 6) return IGV_ERR_INVALID;
   bool found = false;
   for (const auto& v : h->vars) if (v.idx == target_idx && v.size == target_size) found = true;
@@ -893,6 +999,7 @@ igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size,
 // ---- read-outs --------------------------------------------------------------------------------------------
 // ---- track table (MapServer on the device) ------------------------------------------------------------------------
 igv_status igv_tracks_create(igv_batch* h, int max_tracks) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || max_tracks < 1 || max_tracks > 4096) return IGV_ERR_INVALID;
   if (h->trk.T != 0) return fail(h, IGV_ERR_STATE, "track table already created");
   if (h->cfg.max_clones < 1) return fail(h, IGV_ERR_CAPACITY, "track table needs max_clones >= 1");
@@ -916,6 +1023,7 @@ igv_status igv_tracks_create(igv_batch* h, int max_tracks) {
 }
 
 igv_status igv_tracks_reset(igv_batch* h) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   igv_launch_trk_reset(h);
   return check_launch(h);
@@ -925,6 +1033,7 @@ int igv_tracks_capacity(const igv_batch* h) { return h ? h->trk.T : 0; }
 
 igv_status igv_tracks_collect(igv_batch* h, const int* n_meas, int meas_stride, const unsigned long long* ids,
                               const double* uv) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   if (!n_meas || meas_stride < 0 || meas_stride > 4096) return IGV_ERR_INVALID;
   if (meas_stride == 0) return IGV_OK;
@@ -942,12 +1051,14 @@ igv_status igv_tracks_collect(igv_batch* h, const int* n_meas, int meas_stride, 
 }
 
 igv_status igv_tracks_mark_lost(igv_batch* h) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   igv_launch_trk_mark_lost(h);
   return check_launch(h);
 }
 
 igv_status igv_tracks_gather(igv_batch* h, const igv_track_gather_args* a) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   if (!a || !a->track_entry || !a->n_sel || !a->obs || !a->mask_all || !a->mask_upd || !a->anchor_slot ||
       !a->chi2_dof || !a->feat_ok)
@@ -990,6 +1101,7 @@ igv_status igv_tracks_gather(igv_batch* h, const igv_track_gather_args* a) {
 
 igv_status igv_tracks_commit_tri(igv_batch* h, int n_feats, const int* track_entry, const double* pf,
                                  const unsigned char* ok, unsigned char* feat_ok) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   if (n_feats < 0 || !track_entry || !pf || !ok) return IGV_ERR_INVALID;
   if (n_feats == 0) return IGV_OK;
@@ -1015,6 +1127,7 @@ igv_status igv_tracks_commit_tri(igv_batch* h, int n_feats, const int* track_ent
 }
 
 igv_status igv_tracks_erase(igv_batch* h, int n_feats, const int* track_entry) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   if (n_feats < 0 || !track_entry) return IGV_ERR_INVALID;
   if (n_feats == 0) return IGV_OK;
@@ -1026,6 +1139,7 @@ igv_status igv_tracks_erase(igv_batch* h, int n_feats, const int* track_entry) {
 }
 
 igv_status igv_tracks_clean_obs(igv_batch* h, int n_slots, const int* clone_slots) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   unsigned long long bits;
   IGV_TRY(trk_slot_bits(h, n_slots, clone_slots, &bits));
@@ -1035,6 +1149,7 @@ igv_status igv_tracks_clean_obs(igv_batch* h, int n_slots, const int* clone_slot
 }
 
 igv_status igv_tracks_change_anchor(igv_batch* h, int n_old, const int* old_slots, double min_depth) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   unsigned long long bits;
   IGV_TRY(trk_slot_bits(h, n_old, old_slots, &bits));
@@ -1044,6 +1159,7 @@ igv_status igv_tracks_change_anchor(igv_batch* h, int n_old, const int* old_slot
 }
 
 igv_status igv_tracks_erase_invalid(igv_batch* h, double min_depth) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   if (h->trk.col_of_slot.empty()) return IGV_OK;
   igv_launch_trk_erase_invalid(h, min_depth);
@@ -1051,6 +1167,7 @@ igv_status igv_tracks_erase_invalid(igv_batch* h, double min_depth) {
 }
 
 igv_status igv_tracks_get(igv_batch* h, const igv_track_dump* d) {
+  IgvDeviceGuard dev_guard_(h);
   IGV_TRY(trk_ready(h));
   if (!d) return IGV_ERR_INVALID;
   if (d->obs && d->obs_slots < (int)h->trk.col_of_slot.size())
@@ -1085,6 +1202,7 @@ igv_status igv_tracks_get(igv_batch* h, const igv_track_dump* d) {
 }
 
 igv_status igv_get_flags(igv_batch* h, int* flags_out, int clear) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !flags_out) return IGV_ERR_INVALID;
   const cudaMemcpyKind k = h->ptr_mode == IGV_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   IGV_CUDA(h, cudaMemcpyAsync(flags_out, h->flags, sizeof(int) * h->B, k, h->stream));
@@ -1094,6 +1212,7 @@ igv_status igv_get_flags(igv_batch* h, int* flags_out, int clear) {
 }
 
 igv_status igv_cov_trace(igv_batch* h, double* trace_out) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !trace_out) return IGV_ERR_INVALID;
   arena_reset(h);
   double* dev;
@@ -1106,6 +1225,7 @@ igv_status igv_cov_trace(igv_batch* h, double* trace_out) {
 }
 
 igv_status igv_cov_trace_async(igv_batch* h, double* trace_out) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !trace_out) return IGV_ERR_INVALID;
   arena_reset(h);
   double* dev;
@@ -1118,23 +1238,27 @@ igv_status igv_cov_trace_async(igv_batch* h, double* trace_out) {
 }
 
 igv_status igv_fence_record(igv_batch* h, int fence) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || fence < 0 || fence >= 4) return IGV_ERR_INVALID;
   IGV_CUDA(h, cudaEventRecord(h->fences[fence], h->stream));
   return IGV_OK;
 }
 igv_status igv_fence_wait(igv_batch* h, int fence) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || fence < 0 || fence >= 4) return IGV_ERR_INVALID;
   IGV_CUDA(h, cudaEventSynchronize(h->fences[fence]));
   return IGV_OK;
 }
 
 igv_status igv_profile_enable(igv_batch* h, int on) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_ERR_INVALID;
   h->prof_on = on != 0;
   return IGV_OK;
 }
 
 igv_status igv_profile_read(igv_batch* h, double* ms_out, long long* launches_out, int reset) {
+  IgvDeviceGuard dev_guard_(h);
   if (!h || !ms_out || !launches_out) return IGV_ERR_INVALID;
   IGV_CUDA(h, cudaStreamSynchronize(h->stream));
   for (auto& ev : h->prof_events) {

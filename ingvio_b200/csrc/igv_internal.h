@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -63,8 +64,35 @@ struct IgvVar {
   int tag;                       // gnss type for VK_GNSS
 };
 
+// Test / tuning knobs, read from the environment ONCE per handle (igv_create), never on the launch path.
+struct IgvKnobs {
+  int fuse = -1;        // IGV_FUSE: 1 forces the fused per-track kernel, 0 forbids it
+  int qr_cfg = 0;       // IGV_QR_CFG: forces one compression kernel (k_qr.cu launch_qr)
+  int qr_split = 0;     // IGV_QR_SPLIT: forces the row split
+  int gram_cfg = 0;     // IGV_GRAM_CFG: 1 forces the super-block Gram kernel
+  int factor_cfg = 0;   // IGV_FACTOR_CFG: 1 forces the column-by-column factorisation
+  int tri_cfg = 0;      // IGV_TRI_CFG: 1 forces the thread-per-track triangulation kernel
+  int graph = -1;       // IGV_GRAPH: 0 disables CUDA-graph replay of igv_frame_step
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: one bit per device ordinal,
+// set the first time a handle of that device launches the kernel (place the macro in the launcher: the static
+// is per launcher instantiation, hence per kernel).
+#define IGV_SMEM_OPTIN(kernel, bytes)                                                                 \
+  do {                                                                                                \
+    static std::atomic<unsigned long long> done_{0ull};                                               \
+    int dev_ = 0;                                                                                     \
+    cudaGetDevice(&dev_); /* the entry point's IgvDeviceGuard made the handle's device current */     \
+    const unsigned long long bit_ = 1ull << (dev_ & 63);                                              \
+    if (!(done_.load(std::memory_order_acquire) & bit_)) {                                            \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));        \
+      done_.fetch_or(bit_, std::memory_order_release);                                                \
+    }                                                                                                 \
+  } while (0)
+
 struct igv_batch {
   igv_config cfg{};
+  IgvKnobs knobs;
   int B = 0, ld = 0, xsize = 0, max_rows = 0, qmax = 0, ncols_max = 0, rho = 2;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -131,6 +159,19 @@ struct igv_batch {
   IgvLayout layout() const;
   double* Pc() const { return P[cur]; }
   double* Xc() const { return X[xcur]; }
+};
+
+// Every C-ABI entry point that touches the device runs under this guard: the handle's device becomes current for
+// the call (allocations, events and launches all use the CURRENT device) and the caller's device is restored.
+struct IgvDeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit IgvDeviceGuard(const igv_batch* h) {
+    if (!h) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != h->cfg.device) switched = (cudaSetDevice(h->cfg.device) == cudaSuccess);
+  }
+  ~IgvDeviceGuard() { if (switched) cudaSetDevice(prev); }
+  IgvDeviceGuard(const IgvDeviceGuard&) = delete;
+  IgvDeviceGuard& operator=(const IgvDeviceGuard&) = delete;
 };
 
 // Order the compute stream after every host->device copy staged so far (called before the first kernel that may

@@ -193,11 +193,7 @@ void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& l) {
   if (a.z_in_smem) smem += zb;
   a.s_in_smem = (smem + sb <= cap) ? 1 : 0;
   if (a.s_in_smem) smem += sb;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_ekf_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_ekf_update), 220 * 1024);
   k_ekf_update<<<h->B, kEkfThreads, smem, h->stream>>>(a);
   h->launches++;
 }

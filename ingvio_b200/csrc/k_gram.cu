@@ -303,11 +303,7 @@ void launch_stream_gram(const GramArgs& a, int split, int B, int frange, cudaStr
   constexpr int NTT = NT * (NT + 1) / 2, LDS = 8 * NT + 4;
   constexpr size_t STAGE = 4 * 2 * 8 * LDS, FOLD = 2 * NTT * 64;
   const size_t smem = sizeof(double) * (STAGE > FOLD ? STAGE : FOLD) + sizeof(int) * (frange + 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_gram_stream<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_gram_stream<NT, MINB>), 200 * 1024);
   dim3 grid(split, B);
   k_gram_stream<NT, MINB><<<grid, 128, smem, st>>>(a);
 }
@@ -396,11 +392,7 @@ __global__ void __launch_bounds__(256) k_gram_factor_blocked(FactorArgs a) {
 
 template <int SPW>
 void launch_accum(const GramArgs& a, int split, int B, int warps, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_gram_accum<SPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_gram_accum<SPW>), 200 * 1024);
   dim3 grid(split, B);
   k_gram_accum<SPW><<<grid, warps * 32, smem, st>>>(a);
 }
@@ -432,12 +424,12 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
   const size_t smem = sizeof(double) * (size_t)KC * a.lds + sizeof(int) * ((F + split - 1) / split + 2);
   const int nt = (n + 1 + 7) / 8;
   const int frange = (F + split - 1) / split;
-  const char* ev = getenv("IGV_GRAM_CFG");           // test knob: 1 forces the super-block kernel
-  const bool wide = (ev && atoi(ev) == 1) || nt > 9;
+  const int gram_cfg = h->knobs.gram_cfg;            // test knob: 1 forces the super-block kernel
+  const bool wide = gram_cfg == 1 || nt > 9;
   if (!wide) {
     if (nt <= 4) launch_stream_gram<4, 6>(a, split, h->B, frange, h->stream);
     else if (nt <= 6) launch_stream_gram<6, 4>(a, split, h->B, frange, h->stream);
-    else if (ev && atoi(ev) == 2) launch_stream_gram<9, 3>(a, split, h->B, frange, h->stream);   // A/B: 3 CTAs/SM, spills
+    else if (gram_cfg == 2) launch_stream_gram<9, 3>(a, split, h->B, frange, h->stream);   // A/B: 3 CTAs/SM, spills
     else launch_stream_gram<9, 2>(a, split, h->B, frange, h->stream);
   } else
   switch (spw) {
@@ -460,16 +452,12 @@ void igv_launch_gram_factor(igv_batch* h, int nparts) {
   f.n1p = 24 * ((n + 1 + 23) / 24) + 8; f.nparts = nparts;
   f.n = n; f.out = h->Hc; f.out_stride = (long)h->ncols_max * (h->ncols_max + 1);
   f.tol = 1e-13;
-  static bool fattr = false;
-  if (!fattr) {
-    cudaFuncSetAttribute(k_gram_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_gram_factor_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    fattr = true;
-  }
-  const char* ev = getenv("IGV_FACTOR_CFG");      // test knob: 1 forces the column-by-column kernel
+  IGV_SMEM_OPTIN((k_gram_factor), 220 * 1024);
+  IGV_SMEM_OPTIN((k_gram_factor_blocked), 220 * 1024);
+  const int factor_cfg = h->knobs.factor_cfg;     // test knob: 1 forces the column-by-column kernel
   const int lds = n + ((4 - n % 8) + 8) % 8;
   const size_t bsmem = sizeof(double) * ((size_t)n * lds + lds + n);
-  if (bsmem <= 200 * 1024 && !(ev && atoi(ev) == 1)) {
+  if (bsmem <= 200 * 1024 && factor_cfg != 1) {
     k_gram_factor_blocked<<<h->B, 256, bsmem, h->stream>>>(f);
   } else {
     const size_t fsmem = sizeof(double) * ((size_t)n * (n + 3) / 2 + 2 * n);

@@ -156,8 +156,9 @@ void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const
     e.gamma_only = 1; e.gamma_out = gam; e.apply_boxplus = 0;
     igv_launch_ekf(h, e);
   }
-  double thr = INFINITY;
-  if ((int)h->chi2_host.size() >= rows && rows >= 1) thr = chi2_mult * h->chi2_host[rows - 1];  // dof = res.rows() (StateManager.cpp:613-617)
+  // the reference hard-codes the 0.95 quantile at dof = res.rows() here, whatever UpdateBase::_thres the updaters
+  // were built with (StateManager.cpp:613-617)
+  const double thr = (rows >= 1) ? chi2_mult * igv_chi2_quantile(0.95, rows) : INFINITY;
   k_delayed_augment<<<h->B, 128, 0, h->stream>>>(h->Pc(), h->ld, h->N, blk, rows, Hw, rw, rho, gam,
                                                  noise_iso * noise_iso, thr, do_chi2, prior_cov, accepted_dev,
                                                  h->Xc(), h->xsize, -1);

@@ -821,11 +821,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
 
 template <int RHO, bool PS, int QT, bool FUSE>
 void launch_feat_q(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_msckf_features<RHO, PS, QT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_msckf_features<RHO, PS, QT, FUSE>), 224 * 1024);
   k_msckf_features<RHO, PS, QT, FUSE><<<grid, threads, smem, st>>>(a);
 }
 
@@ -869,10 +865,8 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   // ---- fused Gram accumulation: one CTA of up to 16 warps per sequence -----------------------------------------
   h->feat_fused = false;
   {
-    const char* e = getenv("IGV_FUSE");          // test knob: 1 forces the fused kernel, 0 forbids it
-    const int ef = e ? atoi(e) : -1;
-    const char* q = getenv("IGV_QR_CFG");        // a forced compression kernel needs the materialised stack
-    const int qc = q ? atoi(q) : 0;
+    const int ef = h->knobs.fuse;                // test knob: 1 forces the fused kernel, 0 forbids it
+    const int qc = h->knobs.qr_cfg;              // a forced compression kernel needs the materialised stack
     const bool allowed = ps && a.nt <= 9 && ncl <= 32 && l.F >= 1 && h->compress != IGV_COMPRESS_HOUSEHOLDER && qc == 0;
     if (allowed && (ef == 1 || (ef != 0 && h->B >= 296))) {
       const int ntt = a.nt * (a.nt + 1) / 2;

@@ -314,11 +314,7 @@ void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const d
     h->launches++;
   }
   const size_t smem = sizeof(double) * kMaxStrip * h->N;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_propagate), 96 * 1024);   // 20 x 512 x 8 B at the largest max_dim igv_create accepts
   k_propagate<<<h->B, 128, smem, h->stream>>>(a);
   h->launches++;
 }

@@ -465,11 +465,7 @@ void launch_stream(const QrArgs& a, int split, int B, int max_frange, cudaStream
   const int n = a.n;
   const size_t npk = (size_t)n * (n + 3) / 2;
   size_t smem = sizeof(double) * (npk + 2 + 3 * ROWS) + sizeof(int) * (max_frange + 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_qr_stream<NSLOT, ROWS, MINB, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_qr_stream<NSLOT, ROWS, MINB, BF>), 220 * 1024);
   dim3 grid(split, B);
   k_qr_stream<NSLOT, ROWS, MINB, BF><<<grid, 32, smem, st>>>(a);
 }
@@ -479,22 +475,16 @@ void launch_one(const QrArgs& a, int split, int B, int max_frange, cudaStream_t 
   const int n = a.n;
   const size_t npk = (size_t)n * (n + 3) / 2;
   size_t smem = sizeof(double) * (npk + (npk & 1) + 2 * W * ROWS + (size_t)W * 32 * NSLOT) + sizeof(int) * (max_frange + 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_qr_compress<NSLOT, ROWS, W, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_qr_compress<NSLOT, ROWS, W, MINB>), 220 * 1024);
   dim3 grid(split, B);
   k_qr_compress<NSLOT, ROWS, W, MINB><<<grid, W * 32, smem, st>>>(a);
 }
 
-void launch_qr(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st) {
+void launch_qr(const QrArgs& a, int split, int B, int max_frange, cudaStream_t st, int cfg) {
   const int nslot = (a.n + 1 + 31) / 32;   // 32-column register slots (DFMA kernels)
   const int nct = (a.n + 1 + 7) / 8;       // 8-column tiles (DMMA kernel)
   // IGV_QR_CFG: test/tuning knob. 0 = automatic; 20 = force the DMMA panel kernel, 8 = force the single-warp
   // DFMA stream kernel, 9 = force the multi-warp DFMA kernel (5, 1, 3: legacy variants for A/B timing).
-  const char* e = getenv("IGV_QR_CFG");
-  const int cfg = e ? atoi(e) : 0;
   // one independent single-warp stream per CTA when there are enough CTAs to fill the chip
   const bool many = a.src_mode == 0 && (long)B * split >= 1000;
   if (nct <= 9 && (cfg == 20 || (cfg == 0 && many))) {
@@ -533,10 +523,8 @@ void igv_launch_qr_compress(igv_batch* h, int F, int max_valid) {
   int split = 1;
   const int target = 2 * 148;
   if (h->B < target) split = min(h->qr_split_cap, max(1, min((target + h->B - 1) / h->B, (F + 7) / 8)));
-  if (const char* env = getenv("IGV_QR_SPLIT")) {  // test knob: force the row split
-    const int s = atoi(env);
-    if (s >= 1) split = min(h->qr_split_cap, min(s, max(1, F)));
-  }
+  if (h->knobs.qr_split >= 1)   // test knob: force the row split
+    split = min(h->qr_split_cap, min(h->knobs.qr_split, max(1, F)));
   if (h->feat_fused) {   // k_msckf_features<FUSE> already left the Gram matrix of the accepted stack in Gws
     h->feat_fused = false;
     h->last_visual_path = 2;
@@ -545,8 +533,7 @@ void igv_launch_qr_compress(igv_batch* h, int F, int max_valid) {
   }
   {
     // IGV_QR_CFG (test knob) >= 1 forces one of the Householder kernels, 30 forces the Gram path
-    const char* e = getenv("IGV_QR_CFG");
-    const int cfg = e ? atoi(e) : 0;
+    const int cfg = h->knobs.qr_cfg;
     const bool forced_hh = (cfg > 0 && cfg != 30) || h->compress == IGV_COMPRESS_HOUSEHOLDER;
     if (!forced_hh && igv_gram_supported(n)) {
       h->last_visual_path = 1;
@@ -564,16 +551,16 @@ void igv_launch_qr_compress(igv_batch* h, int F, int max_valid) {
   a.hs_seq_stride = (size_t)h->cfg.max_feats * h->qmax * (h->ncols_max + 1);
   if (split == 1) {
     a.out = h->Hc; a.out_stride = (long)h->ncols_max * (h->ncols_max + 1);
-    launch_qr(a, 1, h->B, F, h->stream);
+    launch_qr(a, 1, h->B, F, h->stream, h->knobs.qr_cfg);
     h->launches++;
   } else {
     a.out = h->Rpart; a.out_stride = (long)h->qr_split_cap * h->ncols_max * (h->ncols_max + 1);
-    launch_qr(a, split, h->B, (F + split - 1) / split + 1, h->stream);
+    launch_qr(a, split, h->B, (F + split - 1) / split + 1, h->stream, h->knobs.qr_cfg);
     QrArgs c = a;
     c.src_mode = 1; c.dense = h->Rpart; c.dense_stride = a.out_stride; c.dense_rows = split * n;
     c.n_acc = nullptr;
     c.out = h->Hc; c.out_stride = (long)h->ncols_max * (h->ncols_max + 1);
-    launch_qr(c, 1, h->B, 1, h->stream);
+    launch_qr(c, 1, h->B, 1, h->stream, h->knobs.qr_cfg);
     h->launches += 2;
   }
 }

@@ -306,11 +306,7 @@ void launch_mma(const QrArgs& a, int split, int B, int max_frange, cudaStream_t 
   const int n = a.n;
   const size_t npk = (size_t)n * (n + 3) / 2;
   size_t smem = sizeof(double) * (npk + 2 + 8 * 34 + 64 + 64 + 18) + sizeof(int) * (max_frange + 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_qr_mma<NCT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
-  }
+  IGV_SMEM_OPTIN((k_qr_mma<NCT, MINB>), 220 * 1024);
   dim3 grid(split, B);
   k_qr_mma<NCT, MINB><<<grid, 32, smem, st>>>(a);
 }

@@ -423,11 +423,7 @@ void igv_launch_trk_collect(igv_batch* h, const int* n_meas, int meas_stride, co
   IgvProfScope prof_scope_(h, IGV_K_OTHER);
   const int T = h->trk.T, M = meas_stride;
   const size_t smem = trk_collect_smem(T, M);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(k_trk_collect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
+  if (smem > 48 * 1024) IGV_SMEM_OPTIN((k_trk_collect), 220 * 1024);
   k_trk_collect<<<h->B, 256, smem, h->stream>>>(ptrs(h), igv_trk_cols(h->trk), n_meas, M, ids, uv);
   h->launches++;
 }
@@ -441,11 +437,7 @@ void igv_launch_trk_mark_lost(igv_batch* h) {
 void igv_launch_trk_gather(igv_batch* h, const IgvTrkGatherLaunch& g) {
   IgvProfScope prof_scope_(h, IGV_K_OTHER);
   const size_t smem = trk_gather_smem(h->trk.T, g.F);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(k_trk_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
+  if (smem > 48 * 1024) IGV_SMEM_OPTIN((k_trk_gather), 220 * 1024);
   k_trk_gather<<<h->B, 256, smem, h->stream>>>(ptrs(h), igv_trk_cols(h->trk), g);
   h->launches++;
 }

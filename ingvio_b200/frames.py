@@ -61,6 +61,21 @@ class FramePacket:
     def batch(self):
         return self.gyro.shape[0]
 
+    def tiled(self, B):
+        """The same packet repeated to B sequences (sequence b is a copy of b % batch): a chip-filling batch built
+        from a few distinct streams."""
+        def t(a):
+            reps = -(-B // a.shape[0])
+            return np.ascontiguousarray(np.concatenate([a] * reps, axis=0)[:B])
+        g = None
+        if self.gnss is not None:
+            g = GnssArrays(**{k: t(getattr(self.gnss, k)) for k in self.gnss.__dataclass_fields__})
+        return FramePacket(t=self.t, gyro=t(self.gyro), accel=t(self.accel), dt=t(self.dt), pf_w=t(self.pf_w),
+                           anchor_slot=t(self.anchor_slot), obs=t(self.obs), obs_mask=t(self.obs_mask),
+                           obs_total=t(self.obs_total), visual_mode=self.visual_mode,
+                           selected_slots=list(self.selected_slots), marg_slots=list(self.marg_slots),
+                           max_valid=self.max_valid, gnss=g)
+
     def seq(self, b):
         """Single-sequence view with the attribute names oracle/ingvio_oracle/frame.py reads."""
         g = None

@@ -12,6 +12,7 @@ extern "C" void igv_emul_set_last_error(int e) { g_last = (cudaError_t)e; }
 
 extern "C" {
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

@@ -74,9 +74,6 @@ def test_map_server_mirror_links_against_the_library():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU run (green against the library's own host code on the CPU "
-                                        "model, tests/test_capi_on_cpu_model.py::test_cpp_map_server_mirror); non-strict until it has "
-                                        "run on hardware once")
 def test_map_server_mirror_reference_cases():
     exe = _build_map_server_test(os.path.join(ROOT, "tests", "cpp", "_build", "test_map_server_mirror"), LIBDIR, LIBNAME)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)

@@ -119,9 +119,6 @@ def test_updater_mirror_links_against_the_library():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: green on the CPU model of the library "
-                                        "(tests/test_capi_on_cpu_model.py::test_cpp_estimator_mirror_vs_oracle, all three modes with "
-                                        "IGV_TEST_LIB=emul), not yet run on hardware; non-strict until it has")
 @pytest.mark.parametrize("keyframe,stereo", [(False, False), (True, False), (False, True)])
 def test_updater_mirror_vs_oracle(tmp_path, keyframe, stereo):
     exe = _build(os.path.join(ROOT, "tests", "cpp", "_build", "test_updaters_frames"), LIBDIR, LIBNAME)

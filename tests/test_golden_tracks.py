@@ -55,9 +55,6 @@ def test_emulated_kernels_vs_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU run (same C-ABI call pattern as tests/test_gpu_tracks.py, "
-                                        "which is green on B200; green on the CPU model of the library, "
-                                        "tests/test_capi_on_cpu_model.py::test_golden_replay); non-strict until it has run on hardware once")
 @pytest.mark.parametrize("name", ["mono", "stereo"])
 def test_cuda_vs_golden(name):
     from ingvio_b200.filter import BatchFilter

@@ -1,0 +1,199 @@
+"""GPU parity, round-2 additions: the dispatch paths and branches the first round's cases did not reach.
+
+* the per-track kernel's FUSED instance at its natural dispatch (B >= 296, the benchmarked path) vs the oracle;
+* a 500-frame c2 run at the <= 1e-6 drift bar of SURVEY.md §8d / BASELINE.md §4;
+* SwMarg with stereo observations;
+* the small-angle branches of Gamma / Psi (AuxGammaFunc.cpp:53,119,172) through an IMU propagation with |w dt| below the
+  cut-offs;
+* propagation at the largest state dimension igv_create accepts (k_propagate's strip);
+* two handles on two devices in one process (per-device kernel attributes, device guard on every entry point).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import ingvio_oracle as o
+from ingvio_oracle import StateManager as SM
+
+from helpers import (TiledStream, assert_state_close, block_rel_error, filter_params, gstep, make_gpu, make_oracles,
+                     oracle_blocks)
+from ingvio_b200.synth import WORKLOADS, SyntheticStream
+
+
+def test_fused_natural_dispatch_c2_b296():
+    """c2 at B = 296 (4 distinct streams tiled): the dispatcher picks k_msckf_features<FUSE> on its own
+    (igv_last_visual_path() == 2); the 4 distinct sequences and a tiled copy of each are compared with the oracle."""
+    wl = WORKLOADS["c2"]
+    fp = filter_params(wl)
+    inner = SyntheticStream(wl, 4)
+    orc = make_oracles(wl, inner, fp)
+    st = TiledStream(inner, 296)
+    g = make_gpu(wl, st, fp)
+    saw_fused = False
+    for i in range(13):
+        fr = st.next_frame()
+        out = g.step(fr, noise=fp.visual_noise, want=True)
+        for b, f in enumerate(orc):
+            f.step(fr.seq(b))
+        if "visual" in out:
+            saw_fused = saw_fused or g.last_visual_path() == 2
+            for b, f in enumerate(orc):
+                acc = sum(1 for x in f.last["gammas"] if x[3])
+                assert out["visual"]["accepted"][b] == acc and out["visual"]["accepted"][292 + b] == acc
+    assert saw_fused, "the fused per-track kernel was not dispatched at B = 296"
+    P, X = g.get_full_cov(), g.get_state()
+    for b, f in enumerate(orc):
+        Po = f.cov()
+        for bb in (b, 292 + b):
+            err = np.linalg.norm(P[bb] - Po) / max(1.0, np.linalg.norm(Po))
+            assert err <= 1e-8, (bb, err)
+            berr, where = block_rel_error(P[bb], Po, oracle_blocks(f))
+            assert berr <= 1e-7, (bb, where, berr)
+        assert np.array_equal(P[b], P[292 + b]) and np.array_equal(X[b], X[292 + b])   # schedule independent, bitwise
+
+
+def test_c2_500_frames_drift():
+    """500 full frame cycles of c2 (propagate x10, augment, MSCKF, GNSS, marginalise): the CUDA path stays within
+    1e-6 of the oracle (<= 1e-9 per frame, <= 1e-6 after 500 frames)."""
+    wl = WORKLOADS["c2"]
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 1)
+    orc = make_oracles(wl, st, fp)
+    g = make_gpu(wl, st, fp)
+    worst = 0.0
+    for i in range(500):
+        fr = st.next_frame()
+        gstep(g, fr, fp)
+        orc[0].step(fr.seq(0))
+        if i % 50 == 49 or i == 499:
+            P, Po = g.get_full_cov()[0], orc[0].cov()
+            err = np.linalg.norm(P - Po) / max(1.0, np.linalg.norm(Po))
+            worst = max(worst, err)
+            assert err <= 1e-6, f"frame {i}: |dP| = {err:.3e}"
+    assert_state_close(g, orc, wl.sw, tol_P=1e-6, tol_x=1e-6, tol_block=1e-5, what="c2 after 500 frames")
+    R, p, v = orc[0].pose()
+    x = g.get_state()[0]
+    assert np.max(np.abs(x[9:12] - p)) <= 1e-6
+    tr, tro = g.cov_trace()[0], np.trace(orc[0].cov())
+    assert abs(tr - tro) <= 1e-6 * tro
+    print(f"c2 500 frames: worst |dP|_F/max(1,|P|_F) = {worst:.3e}, |dp| = {np.max(np.abs(x[9:12] - p)):.3e}")
+
+
+def test_sw_marg_stereo():
+    """SwMargUpdate::updateStateStereo (SwMargUpdate.cpp:216-365): selected clones with stereo rows, anchors inside and
+    outside the selection."""
+    wl = WORKLOADS["tiny_stereo"]
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 2)
+    orc = make_oracles(wl, st, fp)
+    g = make_gpu(wl, st, fp)
+    used = False
+    for i in range(8):
+        fr = st.next_frame()
+        if fr.visual_mode is not None and int(fr.obs_mask[0, 0].sum()) == wl.sw:
+            fr.visual_mode = "sw_marg"
+            fr.selected_slots = [0, 1, 3]
+            fr.anchor_slot[:, 0::3] = 0
+            fr.anchor_slot[:, 1::3] = 2          # anchor outside the selection: its column block is appended
+            fr.anchor_slot[:, 2::3] = 3
+            fr.marg_slots = [0]
+            out = g.step(fr, noise=fp.visual_noise, want=True)
+            for b, f in enumerate(orc):
+                f.step(fr.seq(b))
+                for fid, gam, dof, ok in f.last["gammas"]:
+                    assert abs(out["visual"]["gamma"][b, fid] - gam) <= 1e-8 * max(1, abs(gam))
+                assert out["visual"]["accepted"][b] == sum(1 for x in f.last["gammas"] if x[3])
+            st.n_clones = g.num_clones()
+            used = True
+        else:
+            g.step(fr, noise=fp.visual_noise)
+            for b, f in enumerate(orc):
+                f.step(fr.seq(b))
+        assert_state_close(g, orc, wl.sw, what=f"sw_marg stereo frame {i}")
+    assert used
+
+
+@pytest.mark.parametrize("scale", [1e-5, 1e-7, 1e-9, 0.0])
+def test_small_angle_gamma_psi_branches(scale):
+    """|w| dt below the cut-offs of GammaFunc (1e-6), Psi1 (1e-8) and Psi2 (1e-7) (AuxGammaFunc.cpp:53,119,172): the
+    device takes the same series branches as the oracle."""
+    wl = WORKLOADS["tiny"]
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 2)
+    orc = make_oracles(wl, st, fp)
+    g = make_gpu(wl, st, fp)
+    fr = st.next_frame(with_visual=False, with_gnss=False, marg_oldest=False)
+    rng = np.random.default_rng(5)
+    # the biases are subtracted from the raw rate: aim the UNBIASED rate at the wanted magnitude
+    ini = st.initial_state()
+    dirn = rng.standard_normal(fr.gyro.shape)
+    dirn /= np.linalg.norm(dirn, axis=-1, keepdims=True)
+    gyro = ini["bg"][:, None, :] + scale * dirn / fr.dt[..., None]
+    g.propagate_imu(gyro, fr.accel, fr.dt)
+    for b, f in enumerate(orc):
+        f.prop.propagate_steps(f.state, gyro[b], fr.accel[b], fr.dt[b])
+    assert_state_close(g, orc, wl.sw, tol_P=1e-10, what=f"small angle {scale}")
+
+
+def test_propagate_at_max_dim():
+    """k_propagate's strip needs 20 * N * 8 bytes of shared memory: N = 411 (64 clones + 6 GNSS scalars) must work,
+    and the result must equal the oracle's propagateStateCov on the same (random, dense) covariance."""
+    from ingvio_b200.filter import BatchFilter
+    rng = np.random.default_rng(3)
+    B, SW = 2, 64
+    g = BatchFilter(B, SW, 1, 1)
+    eye = np.tile(np.eye(3).reshape(1, 9), (B, 1))
+    z3 = np.zeros((B, 3))
+    g.init_state_and_cov(eye, z3, z3, z3, z3, eye, z3, np.full(21, 1e-2))
+    for gt in range(6):
+        g.add_gnss_variable(gt, 0.0, 1.0)
+    for _ in range(SW):
+        g.augment_sliding_window_pose()
+    N = g.curr_cov_size()
+    assert N == 21 + 6 + 6 * SW
+    A = rng.standard_normal((B, N, N)) * 0.1
+    P0 = A @ A.transpose(0, 2, 1) + np.eye(N)
+    g.set_full_cov(P0)
+    Phi = rng.uniform(-1, 1, (B, 15, 15))
+    G = rng.uniform(-1, 1, (B, 15, 12))
+    dt = np.array([0.7, 0.02])
+    g.propagate_state_cov(Phi, G, dt)
+    P = g.get_full_cov()
+    # oracle: a State with the same variable order
+    fp = o.FilterParams(max_sw_clones=SW, enable_gnss=1)
+    for b in range(B):
+        f = o.OracleFilter(fp, stereo=False, max_valid_ids=1)
+        f.init(0.0, np.eye(3), np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3))
+        for gt in range(6):
+            SM.add_gnss_variable(f.state, gt, 0.0, 1.0)
+        for k in range(SW):
+            f.state.timestamp = 0.05 * (k + 1)
+            SM.augment_sliding_window_pose(f.state)
+        f.state.cov[:, :] = P0[b]
+        SM.propagate_state_cov(f.state, Phi[b], G[b], dt[b])
+        err = np.linalg.norm(P[b] - f.cov()) / max(1.0, np.linalg.norm(f.cov()))
+        assert err <= 1e-10, err
+
+
+def test_two_devices_one_process():
+    """One handle per device in ONE process: kernel attributes are per device and every entry point runs on its handle's
+    device whatever the caller's current device is."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from ingvio_b200.filter import BatchFilter
+    wl = WORKLOADS["tiny"]
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 2)
+    orc = make_oracles(wl, st, fp)
+    gs = [make_gpu(wl, st, fp, device=d) for d in (0, 1)]
+    for i in range(6):
+        fr = st.next_frame()
+        for d, g in enumerate(gs):
+            torch.cuda.set_device(1 - d)       # the caller's current device is the OTHER one
+            gstep(g, fr, fp)
+        for b, f in enumerate(orc):
+            f.step(fr.seq(b))
+    for g in gs:
+        assert_state_close(g, orc, wl.sw, what="two devices")

@@ -1,34 +1,69 @@
-#!/usr/bin/env python
-"""Per-source-line stall-sample histogram from an ncu report captured with --import-source on.
-    python tools/ncu_lines.py gpurun_out/x.ncu-rep [top_n] [file_filter]"""
-import csv, subprocess, sys, collections, io
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-flt = sys.argv[3] if len(sys.argv) > 3 else None
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
-cur_file = None; hdr = None; lines = collections.OrderedDict(); total = 0
-for r in csv.reader(io.StringIO(out)):
-    if not r: continue
-    if r[0] == "File Path": cur_file = r[1]; continue
-    if r[0] == "Function Name": continue
-    if r[0] == "Line No": hdr = r; continue
-    if r[0] and r[0].isdigit() and hdr:
-        try: smp = int(r[4]); ins = int(r[7])
-        except Exception: continue
-        key = (cur_file.split('/')[-1], int(r[0]))
-        if key in lines: lines[key] = (lines[key][0] + smp, lines[key][1] + ins, r[1])
-        else: lines[key] = (smp, ins, r[1])
-        total += smp
-print("total samples", total)
-items = [(k, v) for k, v in lines.items() if not flt or flt in k[0]]
-for k, v in sorted(items, key=lambda kv: -kv[1][0])[:top]:
-    print(f"{k[0]}:{k[1]:4d} {100.0*v[0]/max(total,1):5.1f}%  inst {v[1]:>10d}  {v[2].strip()[:110]}")
-# coarse buckets of 20 lines for the main file
-if len(sys.argv) > 4:
-    # stage buckets "name:lo-hi,name:lo-hi" over the filtered file
-    tot = collections.OrderedDict()
-    for spec in sys.argv[4].split(","):
-        nm, rg = spec.split(":"); lo, hi = map(int, rg.split("-"))
-        s = sum(v[0] for k, v in items if lo <= k[1] <= hi); i = sum(v[1] for k, v in items if lo <= k[1] <= hi)
-        print(f"  {nm:12s} {100.0*s/max(total,1):5.1f}%  inst {i}")
-    other = sum(v[0] for k, v in lines.items() if flt and flt not in k[0])
-    print(f"  other files  {100.0*other/max(total,1):5.1f}%")
+"""Per-CUDA-line summary of an ncu report's source page (stall samples, instructions executed).
+
+usage: python tools/ncu_lines.py report.ncu-rep [--top 40] [--file k_msckf.cu] [--ranges 100-200,201-300]
+Reads `ncu -i report --page source --csv --print-source cuda,sass` (the report must have been captured with
+--import-source on and the library built with -lineinfo)."""
+import argparse
+import csv
+import io
+import subprocess
+import sys
+
+
+def load(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    cur_file, hdr, data = None, None, []
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur_file = r[1]
+            continue
+        if r[0] == "Line No":
+            hdr = r
+            continue
+        if hdr is None or r[0] == "" or not r[0].isdigit():
+            continue
+        d = dict(zip(hdr[4:], r[4:]))
+        try:
+            data.append((cur_file, int(r[0]), r[1], int(d["# Samples"]), int(d["Instructions Executed"]), d))
+        except (KeyError, ValueError):
+            pass
+    return data
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("rep")
+    ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--file", default=None)
+    ap.add_argument("--ranges", default=None)
+    a = ap.parse_args()
+    data = load(a.rep)
+    tot_s = sum(d[3] for d in data) or 1
+    tot_i = sum(d[4] for d in data) or 1
+    print(f"total samples {tot_s}, warp instructions {tot_i}")
+    byfile = {}
+    for f, ln, src, s, i, _ in data:
+        byfile.setdefault(f, [0, 0])
+        byfile[f][0] += s
+        byfile[f][1] += i
+    for f, (s, i) in sorted(byfile.items(), key=lambda kv: -kv[1][0]):
+        print(f"  {f}: samples {100 * s / tot_s:.1f}%  instr {100 * i / tot_i:.1f}%")
+    sel = [d for d in data if a.file is None or d[0].endswith(a.file)]
+    if a.ranges:
+        for rg in a.ranges.split(","):
+            lo, hi = (int(x) for x in rg.split("-"))
+            s = sum(d[3] for d in sel if lo <= d[1] <= hi)
+            i = sum(d[4] for d in sel if lo <= d[1] <= hi)
+            print(f"lines {lo}-{hi}: samples {100 * s / tot_s:.1f}%  instr {100 * i / tot_i:.1f}%")
+    for f, ln, src, s, i, d in sorted(sel, key=lambda d: -d[3])[: a.top]:
+        stalls = {k[6:]: int(v) for k, v in d.items() if k.startswith("stall_") and "(" not in k and v.isdigit() and int(v) > 0}
+        top = ",".join(f"{k}:{v}" for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:3])
+        print(f"{f.split('/')[-1]}:{ln:4d} {100 * s / tot_s:5.1f}% instr {100 * i / tot_i:5.1f}%  [{top}]  {src.strip()[:90]}")
+
+
+if __name__ == "__main__":
+    sys.exit(main())
