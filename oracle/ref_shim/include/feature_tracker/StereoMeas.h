@@ -1,0 +1,15 @@
+// TEST INFRASTRUCTURE: feature_tracker/StereoMeas as the plain struct roscpp generates from
+// feature_tracker/msg/StereoMeas.msg (uint64 id, float64 image coordinates).
+#pragma once
+#include <cstdint>
+#include <map>      // roscpp message headers bring these in; MapServer.h relies on it
+#include <memory>
+#include <string>
+namespace feature_tracker {
+struct StereoMeas {
+  uint64_t id = 0;
+  double u0 = 0, v0 = 0, u1 = 0, v1 = 0;
+  typedef std::shared_ptr<StereoMeas const> ConstPtr;
+  typedef std::shared_ptr<StereoMeas> Ptr;
+};
+}  // namespace feature_tracker

@@ -143,7 +143,8 @@ class TiledStream:
     def initial_state(self):
         ini = self.inner.initial_state()
         reps = -(-self.B // self.inner.B)
-        return {k: np.concatenate([v] * reps, axis=0)[:self.B] for k, v in ini.items()}
+        return {k: (np.concatenate([v] * reps, axis=0)[:self.B] if isinstance(v, np.ndarray) and v.ndim else v)
+                for k, v in ini.items()}
 
     def next_frame(self, **kw):
         return self.inner.next_frame(**kw).tiled(self.B)
