@@ -14,6 +14,8 @@
 #include <iostream>
 #include <limits>
 #include <stdexcept>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace Eigen {
@@ -179,6 +181,12 @@ class MatX {
   MatX col(long j) const { return block(0, j, r_, 1); }
   BlockRef topLeftCorner(long r, long c);
   MatX topLeftCorner(long r, long c) const { return block(0, 0, r, c); }
+  template <int R, int C> BlockRef topLeftCorner();
+  template <int R, int C> MatX topLeftCorner() const { return block(0, 0, R, C); }
+  template <int N> BlockRef topRows();
+  template <int N> MatX topRows() const { return block(0, 0, N, c_); }
+  template <int N> BlockRef bottomRows();
+  template <int N> MatX bottomRows() const { return block(r_ - N, 0, N, c_); }
 
   CommaInit operator<<(double v) { CommaInit ci(*this); ci.push(v); return ci; }
   CommaInit operator<<(const MatX& b) { CommaInit ci(*this); ci.push_block(b); return ci; }
@@ -202,6 +210,7 @@ class MatX {
 class TransposedX : public MatX {
  public:
   TransposedX(long r, long c) : MatX(r, c) {}
+  TransposedX operator-() const { TransposedX t(*this); for (auto& v : t.d_) v = -v; return t; }
 };
 class ScalarProduct : public TransposedX {   // a product with a transposed factor: still "transposed" for the next product
  public:
@@ -344,6 +353,9 @@ inline BlockRef MatX::middleRows(long i, long n) { return BlockRef(*this, i, 0, 
 inline BlockRef MatX::row(long i) { return BlockRef(*this, i, 0, 1, c_); }
 inline BlockRef MatX::col(long j) { return BlockRef(*this, 0, j, r_, 1); }
 inline BlockRef MatX::topLeftCorner(long r, long c) { return BlockRef(*this, 0, 0, r, c); }
+template <int R, int C> inline BlockRef MatX::topLeftCorner() { return BlockRef(*this, 0, 0, R, C); }
+template <int N> inline BlockRef MatX::topRows() { return BlockRef(*this, 0, 0, N, c_); }
+template <int N> inline BlockRef MatX::bottomRows() { return BlockRef(*this, r_ - N, 0, N, c_); }
 
 // a comma initialiser writing into a view goes through a temporary of the view's shape
 struct BlockComma {
@@ -361,17 +373,16 @@ class Matrix : public MatX {
   Matrix(MatX&& o) : MatX(std::move(o)) {}
   Matrix(const BlockRef& b) : MatX(b) {}
   // VectorXd v(n) / MatrixXd m(r, c) / Vector2d(x, y) share these signatures: decide by the static shape
-  explicit Matrix(long n) : MatX(R == Dynamic ? n : R, C == Dynamic ? (R == Dynamic ? 1 : n) : C) {
+  template <typename A, typename = typename std::enable_if<std::is_integral<A>::value>::type>
+  explicit Matrix(A n) : MatX(R == Dynamic ? (long)n : R, C == Dynamic ? (R == Dynamic ? 1 : (long)n) : C) {
     static_assert(R == Dynamic || C == Dynamic, "size constructor on a fixed-size matrix");
   }
-  explicit Matrix(int n) : Matrix((long)n) {}
-  explicit Matrix(size_t n) : Matrix((long)n) {}
-  Matrix(double a, double b) : MatX() { init2(a, b); }
-  Matrix(int a, int b) : MatX() { init2(a, b); }
-  Matrix(long a, long b) : MatX() { init2((double)a, (double)b); }
-  Matrix(size_t a, size_t b) : MatX() { init2((double)a, (double)b); }
-  Matrix(long a, int b) : MatX() { init2((double)a, (double)b); }
-  Matrix(int a, long b) : MatX() { init2((double)a, (double)b); }
+  template <typename A, typename B,
+            typename = typename std::enable_if<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>::type>
+  Matrix(A a, B b) : MatX() { init2((double)a, (double)b); }
+  // from a rotation object (AngleAxisd, Quaterniond)
+  template <typename T, typename = decltype(std::declval<const T&>().toRotationMatrix())>
+  Matrix(const T& rot) : MatX(rot.toRotationMatrix()) {}
   Matrix(double a, double b, double c) : MatX(3, 1) { d_[0] = a; d_[1] = b; d_[2] = c; }
   Matrix(double a, double b, double c, double d) : MatX(4, 1) { d_[0] = a; d_[1] = b; d_[2] = c; d_[3] = d; }
   Matrix& operator=(const MatX& o) { MatX::operator=(o); return *this; }

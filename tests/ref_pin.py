@@ -1,0 +1,52 @@
+"""TEST INFRASTRUCTURE: runs the reference's own code (oracle/_ref/ref_driver: the unmodified translation units of
+/root/reference/ingvio_estimator/src compiled against the stand-in headers of oracle/ref_shim) on a recorded stream and
+reads back state + covariance after every frame.  `oracle/_ref/` is built by `make -C oracle/ref_shim` wherever
+/root/reference exists; elsewhere (the GPU box) the prebuilt binary travels with the snapshot, and the committed outputs
+tests/golden/ref_frames.npz (made by tests/golden/make_golden_ref.py) stand in when even that is missing."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+REF_SRC = "/root/reference/ingvio_estimator/src"
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_frames.npz")
+CONFIGS = [(False, False), (True, False), (False, True), (True, True)]   # (keyframe, stereo) of test_cpp_updaters._stream
+GOLDEN_FRAMES = (0, 4, 8, 13)
+
+
+def build_ref():
+    """Build oracle/_ref if the reference sources are here; returns True when the driver exists afterwards."""
+    if os.path.isdir(REF_SRC):
+        r = subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle", "ref_shim")], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle/_ref build failed:\n" + (r.stdout + r.stderr)[-3000:])
+    return os.path.exists(REF_DRIVER)
+
+
+def config_key(keyframe, stereo):
+    return f"{'kf' if keyframe else 'swmarg'}_{'stereo' if stereo else 'mono'}"
+
+
+def run_ref(keyframe, stereo):
+    """The recorded stream of tests/test_cpp_updaters.py through the reference build; one record per frame."""
+    from test_cpp_updaters import SW, _read_output, _stream, _write_input
+    wl, fp, st, frames = _stream(keyframe, stereo)
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        _write_input(fin, wl, fp, st, frames, keyframe)
+        r = subprocess.run([REF_DRIVER, fin, fout], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0 or "FRAMES DONE" not in r.stdout:
+            raise RuntimeError("ref_driver failed: " + r.stdout[-500:] + r.stderr[-2000:])
+        return _read_output(fout, SW + 1)
+
+
+def load_golden():
+    z = np.load(GOLDEN)
+    out = {}
+    for keyframe, stereo in CONFIGS:
+        k = config_key(keyframe, stereo)
+        out[k] = {int(f): dict(x=z[f"{k}_x{f}"], P=z[f"{k}_P{f}"]) for f in GOLDEN_FRAMES}
+    return out

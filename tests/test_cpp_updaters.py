@@ -142,6 +142,39 @@ def test_updater_mirror_vs_oracle(tmp_path, keyframe, stereo):
         assert ex <= 1e-9, f"frame {k}: state mismatch {ex:.3e}"
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("keyframe,stereo", [(False, False), (True, False), (False, True), (True, True)])
+def test_cuda_path_vs_reference_outputs(tmp_path, keyframe, stereo):
+    """CUDA path (C++ estimator mirror over the C-ABI) vs the REFERENCE's own outputs for the same recorded stream: the
+    committed golden of the reference build (tests/golden/ref_frames.npz, tests/golden/make_golden_ref.py) and, where the
+    prebuilt oracle/_ref/ref_driver travelled with the snapshot, a live run of it for every frame.  No oracle in between."""
+    import ref_pin
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "_build", "test_updaters_frames"), LIBDIR, LIBNAME)
+    wl, fp, st, frames = _stream(keyframe, stereo)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_input(fin, wl, fp, st, frames, keyframe)
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and f"FRAMES DONE {FRAMES}" in r.stdout, r.stdout + r.stderr
+    recs = _read_output(fout, SW + 1)
+
+    def close(rec, ref, what):
+        assert rec["P"].shape == ref["P"].shape, (what, rec["P"].shape, ref["P"].shape)
+        err = np.linalg.norm(rec["P"] - ref["P"]) / max(1.0, np.linalg.norm(ref["P"]))
+        assert err <= 1e-8, f"{what}: |dP|_F/max(1,|P|_F) = {err:.3e}"
+        nu = 39 + 12 * rec["ncl"]
+        ex = np.max(np.abs(rec["x"][:nu] - ref["x"][:nu]) / np.maximum(1.0, np.abs(ref["x"][:nu])))
+        assert ex <= 1e-9, f"{what}: state mismatch {ex:.3e}"
+
+    gold = ref_pin.load_golden()[ref_pin.config_key(keyframe, stereo)]
+    for f, ref in gold.items():
+        close(recs[f], ref, f"frame {f} vs reference golden")
+    if os.path.exists(ref_pin.REF_DRIVER):
+        live = ref_pin.run_ref(keyframe, stereo)
+        for k, ref in enumerate(live):
+            assert recs[k]["ntr"] == ref["ntr"] and recs[k]["N"] == ref["N"], (k, recs[k]["ntr"], ref["ntr"])
+            close(recs[k], ref, f"frame {k} vs reference live")
+
+
 def test_imu_buffer_matches_oracle(tmp_path):
     """ImuPropagator::storeImu / propagateUntil of the C++ mirror vs the oracle restatement of ImuPropagator.cpp:232-292 on
     irregular stamps and awkward end times: the steps handed to the device, the state time and the buffer must agree
