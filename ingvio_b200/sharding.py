@@ -41,3 +41,25 @@ def gather_readouts(local, total, dist=None, device="cpu"):
     out = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)], 0)
+
+
+def gather_readouts_device(local, total, dist=None):
+    """All-gather of per-sequence read-outs that stays on the device: `local` is a (B_local x K) float64 torch tensor on
+    this rank's GPU (or a CPU tensor under gloo), the result is the (total x K) tensor in sequence order on every rank.
+    Shards may differ in size by one (block distribution of shard_range); one collective per call, a few KB."""
+    import torch
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    sizes = [shard_range(total, world, r)[1] - shard_range(total, world, r)[0] for r in range(world)]
+    pad, K = max(sizes), local.shape[1]
+    if local.shape[0] == pad:
+        buf = local.contiguous()
+    else:
+        buf = torch.zeros((pad, K), dtype=local.dtype, device=local.device)
+        buf[:local.shape[0]] = local
+    out = torch.empty((world * pad, K), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf)
+    if all(s == pad for s in sizes):
+        return out
+    return torch.cat([out[r * pad:r * pad + s] for r, s in enumerate(sizes)], 0)

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ingvio_b200.sharding import gather_readouts, max_over_ranks, shard_range
+from ingvio_b200.sharding import gather_readouts, gather_readouts_device, max_over_ranks, shard_range
 from ingvio_b200.synth import WORKLOADS, SyntheticStream
 
 TOTAL = 5
@@ -28,6 +28,8 @@ def _worker(rank, world, port, q):
     lo, hi = shard_range(TOTAL, world, rank)
     local = _readout(lo, hi)
     full = gather_readouts(local, TOTAL, dist)
+    full_dev = gather_readouts_device(torch.from_numpy(local), TOTAL, dist).numpy()   # the tensor path bench.py's c4 leg uses
+    assert np.array_equal(full, full_dev)
     ms = max_over_ranks(10.0 + rank, dist)
     q.put((rank, lo, hi, full, ms))
     dist.barrier()
