@@ -249,6 +249,37 @@ typedef struct {
 } igv_gnss_args;
 igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a);
 
+/* GnssUpdate::addNewTrackedSys (GnssUpdate.cpp:317-476) for ONE newly seen system -- the reference loops over
+ * sys_to_add and ends every iteration in StateManager::addVariableDelayed (StateManager.cpp:547-630). The measurement
+ * rows are built on the device from the same psr_res / dopp_res boundary as igv_gnss_update, evaluated by the caller
+ * with the SPP initial value of the new scalar in the receiver clock vector (GnssUpdate.cpp:351-370):
+ *   clock bias g (IGV_GNSS_GPS..BDS): the satellites with sys == g (getResJacobianOfSys, :478-521),
+ *        H_x = [u^T R_w2e [p]x, -u^T R_w2e, 0 | yof], res = -res_pos, noise = psr_amp sqrt(mean ura psr_std / sin^2 el);
+ *   clock drift (IGV_GNSS_FS): every satellite, H_x = [u^T R_w2e [v]x, 0, -u^T R_w2e | yof], res = -res_vel (:374-425);
+ *   H_f = ones; chi^2 gate at the reference's 0.95 quantile times chi2_mult (0.95 at both call sites).
+ * The yaw-offset column uses R_ecef2enu * dR_z (getRecef2enu(), :403,:464) as the reference does.  Sequences may hold
+ * different numbers of satellites of the system; one with fewer than two is not initialised (StateManager.cpp:574-578).
+ * Rejected sequences keep a decoupled scalar with prior_cov_if_rejected, like igv_add_variable_delayed. */
+typedef struct {
+  int n_sats;                /* S, 2..max_sats                                                     */
+  int gtype;                 /* IGV_GNSS_GPS..IGV_GNSS_BDS or IGV_GNSS_FS: the scalar to add        */
+  const double* value;       /* B          SPP initial value (posSpp(3+i) / velSpp(3), :414,:467)   */
+  const double* unit;        /* B x S x 3  as igv_gnss_args                                         */
+  const double* res_pos;     /* B x S                                                               */
+  const double* res_vel;     /* B x S                                                               */
+  const double* sigma_psr;   /* B x S      psr_amp sqrt(ura psr_std / sin^2 el)                     */
+  const double* sigma_dopp;  /* B x S      dopp_amp sqrt(ura dopp_std c / f / sin^2 el)             */
+  const int* sys;            /* B x S                                                               */
+  const double* R_enu2ecef;  /* B x 9 row-major                                                     */
+  const double* R_ecef2enu;  /* B x 9 row-major, or NULL = transpose of R_enu2ecef                  */
+  int is_adjust_yof;
+  double chi2_mult;          /* 0 = the reference's 0.95                                            */
+  double prior_cov_if_rejected;
+  int* accepted_out;         /* optional B                                                          */
+  double* dx_out;            /* optional B x (N+1)                                                  */
+} igv_gnss_new_sys_args;
+igv_status igv_gnss_add_new_tracked_sys(igv_batch* h, const igv_gnss_new_sys_args* a);
+
 /* ---- GNSS residual generator ("next" row) ------------------------------------------
  * gnss_comm::psr_res (gnss_comm/src/gnss_spp.cpp:99-146) and gnss_comm::dopp_res (:256-282) with sat_azel,
  * ecef2geo, calculate_trop_delay (Saastamoinen + Niell) and calculate_ion_delay (Klobuchar) of

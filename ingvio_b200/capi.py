@@ -59,6 +59,14 @@ class igv_gnss_args(C.Structure):
                 ("strong_reject", C.c_int), ("dx_out", C.c_void_p)]
 
 
+class igv_gnss_new_sys_args(C.Structure):
+    _fields_ = [("n_sats", C.c_int), ("gtype", C.c_int), ("value", C.c_void_p), ("unit", C.c_void_p),
+                ("res_pos", C.c_void_p), ("res_vel", C.c_void_p), ("sigma_psr", C.c_void_p), ("sigma_dopp", C.c_void_p),
+                ("sys", C.c_void_p), ("R_enu2ecef", C.c_void_p), ("R_ecef2enu", C.c_void_p), ("is_adjust_yof", C.c_int),
+                ("chi2_mult", C.c_double), ("prior_cov_if_rejected", C.c_double), ("accepted_out", C.c_void_p),
+                ("dx_out", C.c_void_p)]
+
+
 class igv_gnss_res_args(C.Structure):
     _fields_ = [("n_sats", C.c_int), ("sat_pos", C.c_void_p), ("sat_vel", C.c_void_p), ("sat_clk", C.c_void_p),
                 ("obs", C.c_void_p), ("obs_std", C.c_void_p), ("ttx", C.c_void_p), ("sys", C.c_void_p),
@@ -134,6 +142,7 @@ SIGNATURES = {
     "igv_box_plus": (C.c_int, [_H, _VP]),
     "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
     "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
+    "igv_gnss_add_new_tracked_sys": (C.c_int, [_H, C.POINTER(igv_gnss_new_sys_args)]),
     "igv_gnss_residuals": (C.c_int, [_H, C.POINTER(igv_gnss_res_args)]),
     "igv_sat_states": (C.c_int, [_H, C.POINTER(igv_sat_state_args)]),
     "igv_triangulate": (C.c_int, [_H, C.POINTER(igv_tri_args)]),

@@ -261,6 +261,7 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
     h->knobs.factor_cfg = knob("IGV_FACTOR_CFG", 0);
     h->knobs.tri_cfg = knob("IGV_TRI_CFG", 0);
     h->knobs.graph = knob("IGV_GRAPH", -1);
+    h->knobs.feat_const = knob("IGV_FEAT_CONST", 1);
   }
   if (cfg->stream) {
     h->stream = static_cast<cudaStream_t>(cfg->stream);
@@ -295,6 +296,14 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
   IGV_ALLOC(h->X[1], B * h->xsize);
   IGV_ALLOC(h->flags, B);
   IGV_ALLOC(h->chi2, 1024);
+  IGV_ALLOC(h->chi2_095, 128);
+  {
+    double tab[128];
+    for (int d = 1; d <= 128; ++d) tab[d - 1] = igv_chi2_quantile(0.95, d);
+    e = cudaMemcpyAsync(h->chi2_095, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // `tab` is a stack array
+    if (e != cudaSuccess) return bail("chi2_095", e);
+  }
   const size_t F = std::max(1, cfg->max_feats);
   IGV_ALLOC(h->Hs, B * F * h->qmax * (h->ncols_max + 1));
   IGV_ALLOC(h->f_rows, B * F);
@@ -330,7 +339,7 @@ igv_status igv_destroy(igv_batch* h) {
   IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
+  void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->chi2_095, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
                   h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws};
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -933,6 +942,42 @@ igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
 }
 
 // ---- delayed init / linear replace ------------------------------------------------------------------------
+// Shared tail of igv_add_variable_delayed / igv_gnss_add_new_tracked_sys. All pointers are DEVICE pointers here.
+// noise2_dev / rows_dev (optional, B each): per-sequence measurement variance and true row count (rows beyond it are
+// zero padding: they change neither the Givens split nor the posterior, only the dof of the gate).
+static igv_status delayed_common(igv_batch* h, int gtype, const double* dval, const IgvBlocks& blk, int rows,
+                                 const double* dHo, const double* dHn, const double* dr, double noise_iso,
+                                 const double* noise2_dev, const int* rows_dev, double chi2_mult, int do_chi2,
+                                 double prior_cov_if_rejected, int* accepted_out, double* dx_out) {
+  const size_t B = h->B;
+  int* dacc = h->n_acc;
+  igv_launch_delayed_init(h, blk, rows, dHo, dHn, dr, noise_iso, noise2_dev, rows_dev, chi2_mult, do_chi2,
+                          prior_cov_if_rejected, dacc);
+  IGV_TRY(check_launch(h));
+  h->vars.push_back({gtype >= 0 ? VK_GNSS : VK_OPAQUE, h->N, 1, gtype >= 0 ? gtype : 0});
+  reindex(h);
+  if (gtype >= 0) { igv_launch_set_gnss_value(h, gtype, dval); IGV_TRY(check_launch(h)); }
+  // EKF on the remaining rows (StateManager.cpp:626-627), only where the variable was accepted
+  IgvEkfLaunch e{};
+  e.blk = blk; e.rows = rows - 1;
+  e.H = h->Dws + 1; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
+  e.res = h->Dws + B * rows * blk.n + 1; e.strideRes = rows; e.res_inc = 1;
+  e.R = noise2_dev; e.strideR = noise2_dev ? 1 : 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
+  e.only_if = dacc; e.apply_boxplus = 1;
+  double* ddx = nullptr;
+  IGV_TRY(out_buf(h, dx_out, B * h->N, &ddx));
+  e.dx_out = ddx;
+  igv_launch_ekf(h, e);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, dx_out, ddx, B * h->N));
+  if (accepted_out) {
+    if (h->ptr_mode == IGV_PTR_DEVICE)
+      IGV_CUDA(h, cudaMemcpyAsync(accepted_out, dacc, sizeof(int) * B, cudaMemcpyDeviceToDevice, h->stream));
+    else IGV_TRY(fetch(h, accepted_out, dacc, B));
+  }
+  return IGV_OK;
+}
+
 igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value, int n_blocks, const int* blk_idx,
                                     const int* blk_size, int rows, const double* H_old, const double* H_new,
                                     const double* res, double noise_iso, double chi2_mult, int do_chi2,
@@ -953,31 +998,56 @@ igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value
   IGV_TRY(stage(h, res, B * rows, &dr));
   if (gtype >= 0) IGV_TRY(stage(h, value, B, &dval));
   if (blk.n > 16) return fail(h, IGV_ERR_CAPACITY, "delayed init supports at most 16 measured columns");
-  int* dacc = h->n_acc;
-  igv_launch_delayed_init(h, blk, rows, dHo, dHn, dr, noise_iso, chi2_mult, do_chi2, prior_cov_if_rejected, dacc);
+  return delayed_common(h, gtype, dval, blk, rows, dHo, dHn, dr, noise_iso, nullptr, nullptr, chi2_mult, do_chi2,
+                        prior_cov_if_rejected, accepted_out, dx_out);
+}
+
+// GnssUpdate::addNewTrackedSys for ONE system (GnssUpdate.cpp:317-476; the reference loops over sys_to_add and calls
+// StateManager::addVariableDelayed per system): rows of the satellites of that system (all satellites for the clock
+// drift FS) are built on the device -- H_x = [u^T R_w2e [x]x | -u^T R_w2e on p (clock bias) or v (FS) | yof], H_f = 1,
+// res = -res_pos / -res_vel, noise = sqrt(mean sigma_i^2) -- and handed to the delayed initialisation.
+igv_status igv_gnss_add_new_tracked_sys(igv_batch* h, const igv_gnss_new_sys_args* a) {
+  IgvDeviceGuard dev_guard_(h);
+  if (!h || !a) return IGV_ERR_INVALID;
+  if (a->gtype < 0 || a->gtype > IGV_GNSS_FS) return IGV_ERR_INVALID;
+  if (a->n_sats < 2 || a->n_sats > h->cfg.max_sats) return fail(h, IGV_ERR_CAPACITY, "n_sats outside [2, max_sats]");
+  if (!a->unit || !a->res_pos || !a->res_vel || !a->sigma_psr || !a->sigma_dopp || !a->sys || !a->R_enu2ecef || !a->value)
+    return IGV_ERR_INVALID;
+  IgvLayout L = h->layout();
+  if (L.idx_gnss[IGV_GNSS_YOF] < 0) return IGV_OK;                        // GnssUpdate.cpp:329-330: nothing to do
+  if (L.idx_gnss[a->gtype] >= 0) return fail(h, IGV_ERR_STATE, "New var already in state");
+  if (h->N + 1 > h->cfg.max_dim) return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds max_dim");
+  if (a->n_sats - 1 > h->max_rows || a->n_sats > 128) return fail(h, IGV_ERR_CAPACITY, "rows exceed the EKF workspace");
+  arena_reset(h);
+  const size_t B = h->B, S = a->n_sats;
+  IgvGnssNewRowsLaunch g{};
+  g.S = a->n_sats; g.gtype = a->gtype; g.adjust_yof = a->is_adjust_yof;
+  IGV_TRY(stage(h, a->unit, B * S * 3, &g.unit));
+  IGV_TRY(stage(h, a->res_pos, B * S, &g.res_pos));
+  IGV_TRY(stage(h, a->res_vel, B * S, &g.res_vel));
+  IGV_TRY(stage(h, a->sigma_psr, B * S, &g.sig_psr));
+  IGV_TRY(stage(h, a->sigma_dopp, B * S, &g.sig_dopp));
+  IGV_TRY(stage(h, a->sys, B * S, &g.sys));
+  IGV_TRY(stage(h, a->R_enu2ecef, B * 9, &g.R_enu2ecef));
+  IGV_TRY(stage(h, a->R_ecef2enu, B * 9, &g.R_ecef2enu));
+  const double* dval;
+  IGV_TRY(stage(h, a->value, B, &dval));
+  // workspace in the staging slot: Hx (S x 10 col-major) | Hf (S) | res (S) | noise^2 | count
+  char* mem = nullptr;
+  IGV_TRY(arena_reserve(h, sizeof(double) * B * (S * 12 + 1) + sizeof(int) * B, &mem));
+  g.Hx = reinterpret_cast<double*>(mem);
+  g.Hf = g.Hx + B * S * 10;
+  g.res = g.Hf + B * S;
+  g.noise2 = g.res + B * S;
+  g.count = reinterpret_cast<int*>(g.noise2 + B);
+  igv_launch_gnss_new_rows(h, g);
   IGV_TRY(check_launch(h));
-  h->vars.push_back({gtype >= 0 ? VK_GNSS : VK_OPAQUE, h->N, 1, gtype >= 0 ? gtype : 0});
-  reindex(h);
-  if (gtype >= 0) { igv_launch_set_gnss_value(h, gtype, dval); IGV_TRY(check_launch(h)); }
-  // EKF on the remaining rows (StateManager.cpp:626-627), only where the variable was accepted
-  IgvEkfLaunch e{};
-  e.blk = blk; e.rows = rows - 1;
-  e.H = h->Dws + 1; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
-  e.res = h->Dws + B * rows * blk.n + 1; e.strideRes = rows; e.res_inc = 1;
-  e.R = nullptr; e.strideR = 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
-  e.only_if = dacc; e.apply_boxplus = 1;
-  double* ddx = nullptr;
-  IGV_TRY(out_buf(h, dx_out, B * h->N, &ddx));
-  e.dx_out = ddx;
-  igv_launch_ekf(h, e);
-  IGV_TRY(check_launch(h));
-  IGV_TRY(fetch(h, dx_out, ddx, B * h->N));
-  if (accepted_out) {
-    if (h->ptr_mode == IGV_PTR_DEVICE)
-      IGV_CUDA(h, cudaMemcpyAsync(accepted_out, dacc, sizeof(int) * B, cudaMemcpyDeviceToDevice, h->stream));
-    else IGV_TRY(fetch(h, accepted_out, dacc, B));
-  }
-  return IGV_OK;
+  IgvBlocks blk;
+  blk.n_blocks = 2; blk.n = 10;
+  blk.idx[0] = 0; blk.size[0] = 9;
+  blk.idx[1] = L.idx_gnss[IGV_GNSS_YOF]; blk.size[1] = 1;
+  return delayed_common(h, a->gtype, dval, blk, a->n_sats, g.Hx, g.Hf, g.res, 0.0, g.noise2, g.count,
+                        a->chi2_mult > 0.0 ? a->chi2_mult : 0.95, 1, a->prior_cov_if_rejected, a->accepted_out, a->dx_out);
 }
 
 igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size, int n_blocks, const int* blk_idx,

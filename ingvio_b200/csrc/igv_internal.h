@@ -73,6 +73,7 @@ struct IgvKnobs {
   int factor_cfg = 0;   // IGV_FACTOR_CFG: 1 forces the column-by-column factorisation
   int tri_cfg = 0;      // IGV_TRI_CFG: 1 forces the thread-per-track triangulation kernel
   int graph = -1;       // IGV_GRAPH: 0 disables CUDA-graph replay of igv_frame_step
+  int feat_const = 1;   // IGV_FEAT_CONST: 0 forbids the compile-time-sized instances of the per-track kernel
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: one bit per device ordinal,
@@ -110,6 +111,7 @@ struct igv_batch {
   int* flags = nullptr;                // B
   double* chi2 = nullptr;              // table[d-1]
   int chi2_n = 0;
+  double* chi2_095 = nullptr;          // 0.95 quantiles, dof 1..128 (the delayed initialisation's hard-coded gate)
   // workspaces
   double* Hs = nullptr;                // stacked projected blocks  B x F x qmax x (ncols_max+1) row-major
   int* f_rows = nullptr;               // B x F rows written per feature (0 = rejected)
@@ -283,6 +285,13 @@ void igv_launch_trk_erase_invalid(igv_batch* h, double min_depth);
 void igv_launch_trk_dump(igv_batch* h, const igv_track_dump& d);
 
 void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
-                             const double* res, double noise_iso, double chi2_mult, int do_chi2,
-                             double prior_cov, int* accepted_dev);
+                             const double* res, double noise_iso, const double* noise2_dev, const int* rows_dev,
+                             double chi2_mult, int do_chi2, double prior_cov, int* accepted_dev);
+struct IgvGnssNewRowsLaunch {
+  int S, gtype, adjust_yof;
+  const double* unit; const double* res_pos; const double* res_vel; const double* sig_psr; const double* sig_dopp;
+  const int* sys; const double* R_enu2ecef; const double* R_ecef2enu;
+  double* Hx; double* Hf; double* res; double* noise2; int* count;
+};
+void igv_launch_gnss_new_rows(igv_batch* h, const IgvGnssNewRowsLaunch& g);
 void igv_launch_replace_var_linear(igv_batch* h, int tidx, int tsize, const IgvBlocks& blk, const double* H);

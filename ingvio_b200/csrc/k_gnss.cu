@@ -105,7 +105,82 @@ __global__ void k_gnss_rows(GnssArgs a) {
   if (threadIdx.x == 0) a.cnt[b] = s_cnt;
 }
 
+// Rows of GnssUpdate::addNewTrackedSys for one new system (GnssUpdate.cpp:372-473): the satellites of that
+// constellation (clock bias) or every satellite (clock drift FS), compacted to the front in satellite order; the
+// remaining rows are zero padding. H_x columns: SE23 (9) then the yaw offset.  The yaw-offset column uses
+// getRecef2enu() * dotRw2enu (:403, :464) where updateTrackedSys uses getRenu2ecef() (:166): kept as the reference has it.
+__global__ void k_gnss_new_rows(const double* X, int xsize, IgvGnssNewRowsLaunch g) {
+  const int b = blockIdx.x, S = g.S;
+  const double* Xb = X + (size_t)b * xsize;
+  double* Hx = g.Hx + (size_t)b * S * 10;
+  double* Hf = g.Hf + (size_t)b * S;
+  double* rs = g.res + (size_t)b * S;
+  __shared__ int s_row[128];
+  __shared__ int s_n;
+  __shared__ double s_noise;
+  const bool fs = (g.gtype == IGV_GNSS_FS);
+  if (threadIdx.x == 0) {
+    int n = 0;
+    double acc = 0.0;
+    for (int i = 0; i < S; ++i) {
+      const size_t bi = (size_t)b * S + i;
+      const bool mine = fs || g.sys[bi] == g.gtype;
+      s_row[i] = mine ? n : -1;
+      if (mine) {
+        const double sg = fs ? g.sig_dopp[bi] : g.sig_psr[bi];
+        acc += sg * sg;
+        ++n;
+      }
+    }
+    s_n = n;
+    s_noise = n > 0 ? acc / n : 1.0;     // avg_noise^2 = mean of sigma_i^2 (the amplitude is inside sigma_i)
+    g.count[b] = n;
+    g.noise2[b] = s_noise;
+  }
+  for (int t = threadIdx.x; t < S * 10; t += blockDim.x) Hx[t] = 0.0;
+  for (int t = threadIdx.x; t < S; t += blockDim.x) { Hf[t] = 0.0; rs[t] = 0.0; }
+  __syncthreads();
+  const double yof = Xb[33 + IGV_GNSS_YOF];
+  double sy, cy;
+  sincos(yof, &sy, &cy);
+  const double* Re = g.R_enu2ecef + (size_t)b * 9;
+  const double Rz[9] = {cy, -sy, 0.0, sy, cy, 0.0, 0.0, 0.0, 1.0};
+  const double dRz[9] = {-sy, -cy, 0.0, cy, -sy, 0.0, 0.0, 0.0, 0.0};
+  double Rw[9], dRq[9], Rq[9];
+  mat3_mul(Re, Rz, Rw);
+  if (g.R_ecef2enu) {
+    for (int k = 0; k < 9; ++k) Rq[k] = g.R_ecef2enu[(size_t)b * 9 + k];
+  } else {   // the aligner's R_ecef2enu is the transpose of its R_enu2ecef
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rq[3 * i + j] = Re[3 * j + i];
+  }
+  mat3_mul(Rq, dRz, dRq);
+  const double* x = fs ? (Xb + 12) : (Xb + 9);   // v or p
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const int r = s_row[i];
+    if (r < 0) continue;
+    const size_t bi = (size_t)b * S + i;
+    const double* u = g.unit + bi * 3;
+    double uR[3], udR[3];
+    mat3T_vec(Rw, u, uR);
+    mat3T_vec(dRq, u, udR);
+    Hx[r + 0 * S] = uR[1] * x[2] - uR[2] * x[1];
+    Hx[r + 1 * S] = uR[2] * x[0] - uR[0] * x[2];
+    Hx[r + 2 * S] = uR[0] * x[1] - uR[1] * x[0];
+    const int o = fs ? 6 : 3;
+    Hx[r + (o + 0) * S] = -uR[0]; Hx[r + (o + 1) * S] = -uR[1]; Hx[r + (o + 2) * S] = -uR[2];
+    if (g.adjust_yof) Hx[r + 9 * S] = -(udR[0] * x[0] + udR[1] * x[1] + udR[2] * x[2]);
+    Hf[r] = 1.0;
+    rs[r] = -(fs ? g.res_vel[bi] : g.res_pos[bi]);
+  }
+}
+
 }  // namespace
+
+void igv_launch_gnss_new_rows(igv_batch* h, const IgvGnssNewRowsLaunch& g) {
+  IgvProfScope prof_scope_(h, IGV_K_GNSS_ROWS);
+  k_gnss_new_rows<<<h->B, 64, 0, h->stream>>>(h->Xc(), h->xsize, g);
+  h->launches++;
+}
 
 void igv_launch_gnss_rows(igv_batch* h, const IgvGnssLaunch& l) {
   IgvProfScope prof_scope_(h, IGV_K_GNSS_ROWS);

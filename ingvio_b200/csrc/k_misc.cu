@@ -52,8 +52,9 @@ __global__ void k_delayed_prep(int rows, int n, const double* Hold, const double
 
 // Decide + augment (StateManager.cpp:617-623 + :462-541) for a 1-dim new variable appended at N.
 __global__ void k_delayed_augment(double* P, int ld, int N, IgvBlocks blk, int rows, const double* Hw, const double* rw,
-                                  const double* rho, const double* gamma, double noise2, double thr, int do_chi2,
-                                  double prior_cov, int* accepted, double* X, int xsize, int gslot) {
+                                  const double* rho, const double* gamma, double noise2_all, double thr_all, int do_chi2,
+                                  double prior_cov, int* accepted, double* X, int xsize, int gslot,
+                                  const double* noise2_dev, const int* rows_dev, const double* chi2_095, double chi2_mult) {
   const int b = blockIdx.x;
   double* Pb = P + (size_t)b * ld * ld;
   const double* Hb = Hw + (size_t)b * rows * blk.n;  // row 0 = Hxinit
@@ -63,13 +64,18 @@ __global__ void k_delayed_augment(double* P, int ld, int N, IgvBlocks blk, int r
   if (threadIdx.x == 0) {
     int off = 0;
     for (int q = 0; q < blk.n_blocks; ++q) for (int k = 0; k < blk.size[q]; ++k) cols[off++] = blk.idx[q] + k;
-    const bool rej = do_chi2 && rows > 1 && !(gamma[b] <= thr);   // reject if chi2 > mult*quantile
+    // per-sequence row count (rows beyond it are zero padding): dof = res.rows() of THIS sequence; fewer than two rows:
+    // "H_new rows should be larger than H_new cols" -> not added (StateManager.cpp:574-578)
+    const int rows_b = rows_dev ? rows_dev[b] : rows;
+    const double thr = rows_dev ? ((rows_b >= 1 && rows_b <= 128) ? chi2_mult * chi2_095[rows_b - 1] : 0.0) : thr_all;
+    const bool rej = rows_b < 2 || (do_chi2 && rows > 1 && !(gamma[b] <= thr));   // reject if chi2 > mult*quantile
     s_acc = rej ? 0 : 1;
     accepted[b] = s_acc;
   }
   __syncthreads();
   const int n = blk.n;
-  const double ir = 1.0 / rho[b];
+  const double noise2 = noise2_dev ? noise2_dev[b] : noise2_all;
+  const double ir = s_acc ? 1.0 / rho[b] : 0.0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     double acc = 0.0;
     for (int c = 0; c < n; ++c) acc = fma(Pb[i + (size_t)cols[c] * ld], Hb[(size_t)c * rows], acc);
@@ -137,8 +143,8 @@ __global__ void k_replace_var_linear(double* P, int ld, int N, int t0, int ts, I
 }  // namespace
 
 void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
-                             const double* res, double noise_iso, double chi2_mult, int do_chi2, double prior_cov,
-                             int* accepted_dev) {
+                             const double* res, double noise_iso, const double* noise2_dev, const int* rows_dev,
+                             double chi2_mult, int do_chi2, double prior_cov, int* accepted_dev) {
   igv_commit_copies(h);
   // workspace: Hw (rows x n) | rw (rows) | rho   -- carved from Dws (B x (128*18+2) doubles, n <= 16)
   double* Hw = h->Dws;
@@ -152,7 +158,7 @@ void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const
     e.blk = blk; e.rows = rows - 1;
     e.H = Hw + 1; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
     e.res = rw + 1; e.strideRes = rows; e.res_inc = 1;
-    e.R = nullptr; e.strideR = 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
+    e.R = noise2_dev; e.strideR = noise2_dev ? 1 : 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
     e.gamma_only = 1; e.gamma_out = gam; e.apply_boxplus = 0;
     igv_launch_ekf(h, e);
   }
@@ -161,7 +167,7 @@ void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const
   const double thr = (rows >= 1) ? chi2_mult * igv_chi2_quantile(0.95, rows) : INFINITY;
   k_delayed_augment<<<h->B, 128, 0, h->stream>>>(h->Pc(), h->ld, h->N, blk, rows, Hw, rw, rho, gam,
                                                  noise_iso * noise_iso, thr, do_chi2, prior_cov, accepted_dev,
-                                                 h->Xc(), h->xsize, -1);
+                                                 h->Xc(), h->xsize, -1, noise2_dev, rows_dev, h->chi2_095, chi2_mult);
   h->launches++;
 }
 

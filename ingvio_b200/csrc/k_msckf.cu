@@ -53,6 +53,7 @@ struct FeatArgs {
   int nt, ldz;                       // 8-column tiles of the stack's n+1 columns; row stride of the Z rows
   double* G; long g_seq_stride; int n1p;   // out: upper triangle of [H r]^T [H r], row stride n1p
   int* n_acc; int max_valid;
+  int const_sizes;                   // host: the launch matches the compile-time layout of the NCL > 0 instances
 };
 
 // per-warp scratch layout (doubles): A[M][3] B[M][3] V[M][3] Am[M][3] E[M][3] r[M] qr[M] S[(M+1)][ldm] maps
@@ -62,15 +63,20 @@ __host__ __device__ inline int feat_per_warp(int Mmax, int ssz) {
 
 // QT: largest projected block (rows) whose gate runs in registers, see (5a). FUSE: one CTA of up to 16 warps per
 // sequence; instead of writing the projected blocks to HBM the kernel accumulates their Gram matrix, see (6').
-template <int RHO, bool PS_SMEM, int QT, bool FUSE>
+// NCL > 0: the window size is a compile-time constant (the shipped / benchmarked windows), so every shared-memory array
+// base and stride below folds into immediates instead of integer multiply-adds per access; NCL == 0: any window.
+template <int RHO, bool PS_SMEM, int QT, bool FUSE, int NCL>
 __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ? 1 : 2) k_msckf_features(FeatArgs a) {
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int ncl = a.L.n_clones, n = 6 * ncl, Mmax = a.Mmax, ldm = a.ldm;
+  const int ncl = NCL > 0 ? NCL : a.L.n_clones, n = 6 * ncl, Mmax = NCL > 0 ? RHO * NCL : a.Mmax, ldm = Mmax | 1;
+  const int c_nt = NCL > 0 ? (6 * NCL + 1 + 7) / 8 : a.nt, c_ldz = 8 * c_nt + 4;
+  const int c_ssz = NCL > 0 ? (FUSE ? max((Mmax + 1) * ldm, 3 * c_ldz + NCL * 27) : (Mmax + 1) * ldm) : a.ssz;
+  const int c_per_warp = NCL > 0 ? feat_per_warp(Mmax, c_ssz) : a.per_warp;
   double* sPose = sm;                                   // 12 per clone
   double* sPs = sm + 12 * IGV_MAX_CLONES;               // [n][n] clone block of P (symmetric), if staged
-  double* ws = sPs + (PS_SMEM ? n * n : 0) + (size_t)warp * a.per_warp;
+  double* ws = sPs + (PS_SMEM ? n * n : 0) + (size_t)warp * c_per_warp;
   double* sA = ws;                 // [M][3] rows of A_k (== H_f)
   double* sB = sA + Mmax * 3;      // [M][3] rows of B_k = A_k [pf]x
   double* sV = sB + Mmax * 3;      // [M][3] Householder vectors
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
   double* sr = sE + Mmax * 3;      // [M] residual
   double* sqr = sr + Mmax;         // [M] Q^T r
   double* sS = sqr + Mmax;         // [(M+1)][ldm] : H_x P_s H_x^T, then S and its Cholesky factor (+ rhs row)
-  int* k2slot = reinterpret_cast<int*>(sS + a.ssz);             // [ncl] obs k -> slot
+  int* k2slot = reinterpret_cast<int*>(sS + c_ssz);             // [ncl] obs k -> slot
   int* slot2k = k2slot + ncl;                                    // [ncl] slot -> obs k or -1
   const double* Xb = a.X + (size_t)b * a.xsize;
   for (int t = threadIdx.x; t < 12 * ncl; t += blockDim.x) sPose[t] = Xb[IGV_X_CORE + t];
@@ -95,20 +101,20 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
   // FUSE: CTA-level accumulators behind the per-warp regions
   double* wsbase = sPs + (PS_SMEM ? n * n : 0);                  // per-warp regions start here
   const int zoff = Mmax * 15 + 2 * Mmax;                         // offset of sS inside a per-warp region
-  const int ntt = a.nt * (a.nt + 1) / 2;
-  double* S_acc = wsbase + (size_t)nwarps * a.per_warp;          // [(ncl+1) anchors][ncl][27]
+  const int ntt = c_nt * (c_nt + 1) / 2;
+  double* S_acc = wsbase + (size_t)nwarps * c_per_warp;          // [(ncl+1) anchors][ncl][27]
   double2* Gt = reinterpret_cast<double2*>(                                                     // [ntt][32], 16-byte aligned
       (reinterpret_cast<uintptr_t>(S_acc + (size_t)(ncl + 1) * ncl * 27) + 15) & ~static_cast<uintptr_t>(15));
   double* zero_row = reinterpret_cast<double*>(Gt + (size_t)ntt * 32);   // [ldz] zeros (masked rows of the Z fold)
-  int* flag_s = reinterpret_cast<int*>(zero_row + a.ldz);        // [16]
+  int* flag_s = reinterpret_cast<int*>(zero_row + c_ldz);        // [16]
   int* tile_cc = flag_s + 16;                                    // [ntt] tile -> (column tile i) | (column tile j) << 8
   if (FUSE) {
     for (int t = threadIdx.x; t < (ncl + 1) * ncl * 27; t += blockDim.x) S_acc[t] = 0.0;
     for (int t = threadIdx.x; t < ntt * 32; t += blockDim.x) Gt[t] = make_double2(0.0, 0.0);
-    for (int t = threadIdx.x; t < a.ldz; t += blockDim.x) zero_row[t] = 0.0;
+    for (int t = threadIdx.x; t < c_ldz; t += blockDim.x) zero_row[t] = 0.0;
     for (int t = threadIdx.x; t < ntt; t += blockDim.x) {
       int ci = 0, rem = t;
-      while (rem >= a.nt - ci) { rem -= a.nt - ci; ++ci; }
+      while (rem >= c_nt - ci) { rem -= c_nt - ci; ++ci; }
       tile_cc[t] = ci | ((ci + rem) << 8);
     }
   }
@@ -552,8 +558,8 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
     // order, so the sum is independent of the schedule (bitwise reproducible).
     if (accept && FUSE) {
       double* zrow = sS;                      // [3][ldz]
-      double* dblk = sS + 3 * a.ldz;          // [ncl][27]
-      const int ncolp = 8 * a.nt;
+      double* dblk = sS + 3 * c_ldz;          // [ncl][27]
+      const int ncolp = 8 * c_nt;
       // V^T (rows of the anchor's rotation columns): lanes 0..8 hold entry (q = lane / 3, comp = lane % 3) of
       // -sum_{rows not at the anchor} V[row][q] B[row][comp]
       double yanc = 0.0;
@@ -599,7 +605,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
         } else if (j == n) {
           zr[0] = sqr[0]; zr[1] = sqr[1]; zr[2] = sqr[2];
         }
-        if (j < ncolp) { zrow[j] = zr[0]; zrow[a.ldz + j] = zr[1]; zrow[2 * a.ldz + j] = zr[2]; }
+        if (j < ncolp) { zrow[j] = zr[0]; zrow[c_ldz + j] = zr[1]; zrow[2 * c_ldz + j] = zr[2]; }
       }
       for (int sl = lane; sl < ncl; sl += 32) {
         double* dd = dblk + sl * 27;
@@ -738,7 +744,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
           const bool on = r < nrows && ((onmask >> w) & 1u);
           if (!__any_sync(0xffffffffu, on)) continue;
           // masked rows read a row of zeros instead of being selected away after the load
-          const double* zp = on ? wsbase + (size_t)w * a.per_warp + zoff + p * a.ldz : zero_row;
+          const double* zp = on ? wsbase + (size_t)w * c_per_warp + zoff + p * c_ldz : zero_row;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (warp + u * nwarps < ntt) mma884(g[u].x, g[u].y, zp[ci8[u]], zp[cj8[u]]);
@@ -749,7 +755,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
         for (int idx = threadIdx.x; idx < ncl * 27; idx += blockDim.x)
           for (unsigned mm = onmask; mm; mm &= mm - 1) {
             const int w = __ffs(mm) - 1;
-            S_acc[(size_t)(flag_s[w] - 1) * ncl * 27 + idx] += (wsbase + (size_t)w * a.per_warp + zoff + 3 * a.ldz)[idx];
+            S_acc[(size_t)(flag_s[w] - 1) * ncl * 27 + idx] += (wsbase + (size_t)w * c_per_warp + zoff + 3 * c_ldz)[idx];
           }
       }
       __syncthreads();
@@ -819,20 +825,26 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
   }
 }
 
-template <int RHO, bool PS, int QT, bool FUSE>
+template <int RHO, bool PS, int QT, bool FUSE, int NCL>
 void launch_feat_q(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-  IGV_SMEM_OPTIN((k_msckf_features<RHO, PS, QT, FUSE>), 224 * 1024);
-  k_msckf_features<RHO, PS, QT, FUSE><<<grid, threads, smem, st>>>(a);
+  IGV_SMEM_OPTIN((k_msckf_features<RHO, PS, QT, FUSE, NCL>), 224 * 1024);
+  k_msckf_features<RHO, PS, QT, FUSE, NCL><<<grid, threads, smem, st>>>(a);
 }
 
 template <int RHO, bool PS, bool FUSE>
 void launch_feat(const FeatArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   // register-resident gate sized to the largest block this window can produce (rho * clones - 3 rows)
   const int qmax = a.Mmax - 3;
-  if (qmax <= 9) launch_feat_q<RHO, PS, 9, FUSE>(a, grid, threads, smem, st);
-  else if (qmax <= 17) launch_feat_q<RHO, PS, 17, FUSE>(a, grid, threads, smem, st);
-  else if (qmax <= 21) launch_feat_q<RHO, PS, 21, FUSE>(a, grid, threads, smem, st);
-  else launch_feat_q<RHO, PS, 25, FUSE>(a, grid, threads, smem, st);
+  // the benchmarked window (SW = 11, BASELINE configs c2 / c3 / c4) gets an instance with compile-time sizes
+  if (PS && a.L.n_clones == 11 && a.const_sizes) {
+    if (RHO == 2) launch_feat_q<RHO, PS, 21, FUSE, 11>(a, grid, threads, smem, st);
+    else launch_feat_q<RHO, PS, 25, FUSE, 11>(a, grid, threads, smem, st);
+    return;
+  }
+  if (qmax <= 9) launch_feat_q<RHO, PS, 9, FUSE, 0>(a, grid, threads, smem, st);
+  else if (qmax <= 17) launch_feat_q<RHO, PS, 17, FUSE, 0>(a, grid, threads, smem, st);
+  else if (qmax <= 21) launch_feat_q<RHO, PS, 21, FUSE, 0>(a, grid, threads, smem, st);
+  else launch_feat_q<RHO, PS, 25, FUSE, 0>(a, grid, threads, smem, st);
 }
 
 }  // namespace
@@ -860,6 +872,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   a.nt = (n + 1 + 7) / 8; a.ldz = 8 * a.nt + 4;
   a.G = h->Gws; a.g_seq_stride = (long)h->qr_split_cap * h->gram_n1p * h->gram_n1p; a.n1p = 24 * ((n + 1 + 23) / 24) + 8;
   a.n_acc = h->n_acc; a.max_valid = l.max_valid;
+  a.const_sizes = (h->knobs.feat_const != 0) ? 1 : 0;
   const bool ps = ((size_t)n * n * sizeof(double) <= 72 * 1024);
   const size_t fixed = 12 * IGV_MAX_CLONES + (ps ? (size_t)n * n : 0);
   // ---- fused Gram accumulation: one CTA of up to 16 warps per sequence -----------------------------------------

@@ -403,6 +403,30 @@ class BatchFilter:
         self._ck(self.lib.igv_gnss_update(self.h, C.byref(args)))
         return dx
 
+    def gnss_add_new_tracked_sys(self, gtype, value, unit, res_pos, res_vel, sigma_psr, sigma_dopp, sys, R_enu2ecef,
+                                 R_ecef2enu=None, is_adjust_yof=0, chi2_mult=0.95, prior_cov_if_rejected=1.0):
+        """GnssUpdate::addNewTrackedSys for one system (GnssUpdate.cpp:317-476): rows built on the device, then
+        StateManager::addVariableDelayed. Returns accepted (B,) bool (None in device-pointer mode)."""
+        if np.isscalar(value):
+            value = np.full(self.B, float(value))
+        a = [_Arg(value, np.float64), _Arg(unit, np.float64), _Arg(res_pos, np.float64), _Arg(res_vel, np.float64),
+             _Arg(sigma_psr, np.float64), _Arg(sigma_dopp, np.float64), _Arg(sys, np.int32), _Arg(R_enu2ecef, np.float64)]
+        if R_ecef2enu is not None:
+            a.append(_Arg(R_ecef2enu, np.float64))
+        mode = self._set_mode(a)
+        args = capi.igv_gnss_new_sys_args()
+        args.n_sats, args.gtype = int(a[2].keep.shape[1]), int(gtype)
+        (args.value, args.unit, args.res_pos, args.res_vel, args.sigma_psr, args.sigma_dopp, args.sys,
+         args.R_enu2ecef) = [x.ptr for x in a[:8]]
+        args.R_ecef2enu = a[8].ptr if R_ecef2enu is not None else None
+        args.is_adjust_yof, args.chi2_mult, args.prior_cov_if_rejected = int(is_adjust_yof), float(chi2_mult), float(prior_cov_if_rejected)
+        acc = None
+        if mode == capi.IGV_PTR_HOST:
+            acc = np.zeros(self.B, dtype=np.int32)
+            args.accepted_out = C.c_void_p(acc.ctypes.data)
+        self._ck(self.lib.igv_gnss_add_new_tracked_sys(self.h, C.byref(args)))
+        return None if acc is None else acc.astype(bool)
+
     def sat_states(self, eph, t_obs_rel, psr, sys, out=None):
         """gnss_comm::sat_states: ephemeris records (B,S,24) + observation time relative to toe + L1 pseudo-range ->
         dict(sat_pos, sat_vel, sat_clk, ttx_rel). Host arrays in, numpy out; device tensors need `out`."""
