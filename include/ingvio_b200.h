@@ -308,6 +308,9 @@ typedef struct {
   double* sigma_dopp;        /* out B x S                                                                       */
   double* azel;              /* out B x S x 2, optional                                                         */
   double* atmos;             /* out B x S x 2 (ionosphere, troposphere delay [m]), optional                     */
+  const double* clock_init;  /* optional B x 5 (GPS, GLO, GAL, BDS clock bias [m], clock drift): receiver clock entries
+                                that override the state's (NaN = keep the state's), the SPP initial values
+                                addNewTrackedSys writes into xyzt / dopp (GnssUpdate.cpp:351-370); NULL = none     */
 } igv_gnss_res_args;
 igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a);
 

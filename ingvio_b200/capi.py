@@ -72,7 +72,8 @@ class igv_gnss_res_args(C.Structure):
                 ("obs", C.c_void_p), ("obs_std", C.c_void_p), ("ttx", C.c_void_p), ("sys", C.c_void_p),
                 ("T_enu2ecef", C.c_void_p), ("iono", C.c_void_p), ("psr_noise_amp", C.c_double),
                 ("dopp_noise_amp", C.c_double), ("unit", C.c_void_p), ("res_pos", C.c_void_p), ("res_vel", C.c_void_p),
-                ("sigma_psr", C.c_void_p), ("sigma_dopp", C.c_void_p), ("azel", C.c_void_p), ("atmos", C.c_void_p)]
+                ("sigma_psr", C.c_void_p), ("sigma_dopp", C.c_void_p), ("azel", C.c_void_p), ("atmos", C.c_void_p),
+                ("clock_init", C.c_void_p)]
 
 
 class igv_sat_state_args(C.Structure):

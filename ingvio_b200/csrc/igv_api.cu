@@ -831,6 +831,7 @@ igv_status igv_gnss_residuals(igv_batch* h, const igv_gnss_res_args* a) {
   IGV_TRY(stage(h, a->sys, B * S, &g.sys));
   IGV_TRY(stage(h, a->T_enu2ecef, B * 12, &g.T));
   IGV_TRY(stage(h, a->iono, B * 8, &g.iono));
+  IGV_TRY(stage(h, a->clock_init, B * 5, &g.clock_init));
   IGV_TRY(out_buf(h, a->unit, B * S * 3, &g.unit));
   IGV_TRY(out_buf(h, a->res_pos, B * S, &g.res_pos));
   IGV_TRY(out_buf(h, a->res_vel, B * S, &g.res_vel));

@@ -255,6 +255,7 @@ struct IgvGnssResLaunch {
   const double* ttx; const int* sys; const double* T; const double* iono;
   double psr_amp, dopp_amp;
   double* unit; double* res_pos; double* res_vel; double* sig_psr; double* sig_dopp; double* azel; double* atmos;
+  const double* clock_init;
 };
 void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l);
 void igv_launch_sat_states(igv_batch* h, int S, const double* eph, const double* t_obs, const double* psr, const int* sys,

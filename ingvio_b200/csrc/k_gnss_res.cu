@@ -33,6 +33,7 @@ struct ResArgs {
   const double* ttx; const int* sys; const double* T; const double* iono;
   double psr_amp, dopp_amp;
   double* unit; double* res_pos; double* res_vel; double* sig_psr; double* sig_dopp; double* azel; double* atmos;
+  const double* clock_init;
 };
 
 __device__ void ecef2geo(const double* xyz, double* lla) {   // gnss_utility.cpp:347-387
@@ -133,7 +134,10 @@ __global__ void __launch_bounds__(128) k_gnss_residuals(ResArgs a) {
   mat3_vec(T, pe, rp);
   mat3_vec(T, ve, rv);
   for (int i = 0; i < 3; ++i) rp[i] += T[9 + i];
-  const double fs = (a.idx_gnss[IGV_GNSS_FS] >= 0) ? Xb[33 + IGV_GNSS_FS] : 0.0;
+  // clock_init (optional, B x 5): initial values of receiver clock entries not yet in the state, as addNewTrackedSys
+  // writes them into xyzt / dopp from the SPP solution (GnssUpdate.cpp:351-370); NaN = take the entry from the state
+  const double* ci = a.clock_init ? a.clock_init + (size_t)b * 5 : nullptr;
+  const double fs = (ci && !isnan(ci[4])) ? ci[4] : ((a.idx_gnss[IGV_GNSS_FS] >= 0) ? Xb[33 + IGV_GNSS_FS] : 0.0);
   const double* sp = a.sat_pos + gid * 3;
   const double* sv = a.sat_vel + gid * 3;
   const double sdt = a.sat_clk[gid * 3], sddt = a.sat_clk[gid * 3 + 1], tgd = a.sat_clk[gid * 3 + 2];
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(128) k_gnss_residuals(ResArgs a) {
       tro_d = trop_delay(a.ttx[gid * 2], lla, azel);
       ion_d = ion_delay(a.ttx[gid * 2 + 1], a.iono ? a.iono + (size_t)b * 8 : nullptr, lla, azel);
     }
-    const double cb = (a.idx_gnss[k] >= 0) ? Xb[33 + k] : 0.0;   // GnssManager::getClockbiasVec
+    const double cb = (ci && !isnan(ci[k])) ? ci[k] : ((a.idx_gnss[k] >= 0) ? Xb[33 + k] : 0.0);   // GnssManager::getClockbiasVec
     const double sagnac = kOmg * (sp[0] * rp[1] - sp[1] * rp[0]) / kC;
     const double est = rng + sagnac + cb - sdt * kC + tro_d + ion_d + tgd * kC;
     res_p = est - psr;
@@ -342,7 +346,7 @@ void igv_launch_gnss_residuals(igv_batch* h, const IgvGnssResLaunch& l) {
   a.sat_pos = l.sat_pos; a.sat_vel = l.sat_vel; a.sat_clk = l.sat_clk; a.obs = l.obs; a.obs_std = l.obs_std;
   a.ttx = l.ttx; a.sys = l.sys; a.T = l.T; a.iono = l.iono; a.psr_amp = l.psr_amp; a.dopp_amp = l.dopp_amp;
   a.unit = l.unit; a.res_pos = l.res_pos; a.res_vel = l.res_vel; a.sig_psr = l.sig_psr; a.sig_dopp = l.sig_dopp;
-  a.azel = l.azel; a.atmos = l.atmos;
+  a.azel = l.azel; a.atmos = l.atmos; a.clock_init = l.clock_init;
   const long n = (long)h->B * l.S;
   k_gnss_residuals<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(a);
   h->launches++;

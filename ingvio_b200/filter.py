@@ -448,14 +448,15 @@ class BatchFilter:
         return out
 
     def gnss_residuals(self, sat_pos, sat_vel, sat_clk, obs, obs_std, ttx, sys, T_enu2ecef, iono=None, psr_amp=1.0,
-                       dopp_amp=1.0, out=None):
+                       dopp_amp=1.0, out=None, clock_init=None):
         """gnss_comm::psr_res / dopp_res (+ az/el, delays, sigmas) at the filter's receiver state; returns a dict
         with unit, res_pos, res_vel, sigma_psr, sigma_dopp, azel, atmos -- the inputs of gnss_update. Host arrays in,
         numpy arrays out; device tensors in, `out` must hold preallocated device tensors under the same keys."""
         a = [_Arg(sat_pos, np.float64), _Arg(sat_vel, np.float64), _Arg(sat_clk, np.float64), _Arg(obs, np.float64),
              _Arg(obs_std, np.float64), _Arg(ttx, np.float64), _Arg(sys, np.int32), _Arg(T_enu2ecef, np.float64),
              _Arg(iono, np.float64)]
-        mode = self._set_mode(a)
+        ci = _Arg(clock_init, np.float64) if clock_init is not None else None
+        mode = self._set_mode(a + ([ci] if ci is not None else []))
         S = int(a[6].keep.shape[1])
         shapes = dict(unit=(self.B, S, 3), res_pos=(self.B, S), res_vel=(self.B, S), sigma_psr=(self.B, S),
                       sigma_dopp=(self.B, S), azel=(self.B, S, 2), atmos=(self.B, S, 2))
@@ -469,6 +470,7 @@ class BatchFilter:
         (args.sat_pos, args.sat_vel, args.sat_clk, args.obs, args.obs_std, args.ttx, args.sys, args.T_enu2ecef,
          args.iono) = [x.ptr for x in a]
         args.psr_noise_amp, args.dopp_noise_amp = float(psr_amp), float(dopp_amp)
+        args.clock_init = ci.ptr if ci is not None else None
         for k in shapes:
             setattr(args, k, o[k].ptr)
         self._ck(self.lib.igv_gnss_residuals(self.h, C.byref(args)))

@@ -340,6 +340,32 @@ class StateManager {
     marg->set_cov_idx(-1);
     state->_err_variables = rem;
   }
+  // StateManager.cpp:194-214: a new variable with its own covariance block, decoupled from the rest
+  static void addVariableIndependent(std::shared_ptr<State> state, std::shared_ptr<Type> new_state, const Matrix& new_state_cov_block) {
+    if (std::find(state->_err_variables.begin(), state->_err_variables.end(), new_state) != state->_err_variables.end()) {
+      std::printf("[StateManager]: Variable already in the state, cannot be added!\n");
+      return;
+    }
+    new_state->set_cov_idx(state->curr_cov_size());
+    check(state, igv_add_variable_independent(state->_gpu, new_state->size(), new_state_cov_block.data()));
+    state->_err_variables.push_back(new_state);
+  }
+  // StateManager.cpp:632-693: target_var becomes a linear function H of the variables in dependence_order
+  static void replaceVarLinear(std::shared_ptr<State> state, const std::shared_ptr<Type> target_var,
+                               const std::vector<std::shared_ptr<Type>>& dependence_order, const Matrix& H) {
+    if (std::find(state->_err_variables.begin(), state->_err_variables.end(), target_var) == state->_err_variables.end()) {
+      std::printf("[StateManager]: Target var not in state, cannot linearly replace!\n");
+      return;
+    }
+    std::vector<int> idx, size;
+    for (auto& v : dependence_order) { idx.push_back(v->idx()); size.push_back(v->size()); }
+    check(state, igv_replace_var_linear(state->_gpu, target_var->idx(), target_var->size(), (int)idx.size(), idx.data(), size.data(), H.data()));
+  }
+  // a variable the device already appended at covariance index `idx` (fused device-side additions)
+  static void registerVariable(std::shared_ptr<State> state, std::shared_ptr<Type> var, int idx) {
+    var->set_cov_idx(idx);
+    state->_err_variables.push_back(var);
+  }
   static void addGNSSVariable(std::shared_ptr<State> state, int gtype, double value, double cov) {  // :216-231
     if (state->_gnss.count(gtype)) std::printf("[StateManager]: GNSS variable already in the state, adding operation will rewrite such var!\n");
     auto s = std::make_shared<Scalar>();

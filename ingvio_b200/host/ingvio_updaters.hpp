@@ -25,6 +25,9 @@ struct IngvioParams {
   double _trans_thres = 0.1, _huber_epsilon = 0.01, _conv_precision = 5e-7, _init_damping = 1e-3;
   int _outer_loop_max_iter = 10, _inner_loop_max_iter = 10;
   double _max_depth = 60.0, _min_depth = 0.2;
+  // GNSS (IngvioParams.h:86-113)
+  double _psr_noise_amp = 1.0, _dopp_noise_amp = 1.0, _init_cov_yof = 0.015;
+  int _is_adjust_yof = 0, _is_gnss_chi2_test = 0, _is_gnss_strong_reject = 0;
 };
 
 class Triangulator {   // Triangulator.h:35-60

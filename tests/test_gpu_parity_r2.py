@@ -197,3 +197,50 @@ def test_two_devices_one_process():
             f.step(fr.seq(b))
     for g in gs:
         assert_state_close(g, orc, wl.sw, what="two devices")
+
+
+@pytest.mark.parametrize("adjust_yof", [0, 1])
+def test_gnss_add_new_tracked_sys(adjust_yof):
+    """GnssUpdate::addNewTrackedSys (GnssUpdate.cpp:317-476): a clock bias of a constellation seen for the first time and
+    the clock drift FS are added through the device-built rows + delayed initialisation; ragged satellite counts per
+    sequence, an outlier epoch that the 0.95 gate rejects, and the reference's R_ecef2enu quirk in the yaw-offset column."""
+    from ingvio_oracle import BDS, FS, GAL, GLO, GPS, YOF
+    from ingvio_oracle.gnss_update import GnssEpoch
+    wl = WORKLOADS["tiny"]
+    fp = filter_params(wl, is_adjust_yof=adjust_yof)
+    st = SyntheticStream(wl, 3)
+    orc = make_oracles(wl, st, fp, with_gnss=False)
+    g = make_gpu(wl, st, fp, with_gnss=False)
+    for gt, val, cov in ((YOF, 0.3, 0.015 ** 2), (GPS, 1.0, 4.0)):
+        g.add_gnss_variable(gt, val, cov)
+        for f in orc:
+            SM.add_gnss_variable(f.state, gt, val, cov)
+    for _ in range(5):                       # realistic cross-covariances first
+        fr = st.next_frame(with_gnss=False)
+        gstep(g, fr, fp)
+        for b, f in enumerate(orc):
+            f.step(fr.seq(b))
+    fr = st.next_frame(with_visual=False)
+    G = fr.gnss
+    S = G.unit.shape[1]
+    G.sys[:, :] = np.array([GPS, GAL, GAL, GLO, GAL] + [GLO] * (S - 5))[None, :S]
+    G.sys[1, 1] = GLO                        # sequence 1 sees one GAL satellite fewer (ragged rows)
+    G.res_pos[2] += 3000.0                   # sequence 2: inconsistent epoch, the 0.95 gate must reject GAL
+    R_e2n = np.transpose(G.R_enu2ecef, (0, 2, 1)).copy()
+    R_e2n[:, 0, 1] += 1e-3                   # make the reference's getRecef2enu() quirk observable
+    spp = {GAL: 0.7, FS: 0.05}
+    for gt in (GAL, FS):
+        acc = g.gnss_add_new_tracked_sys(gt, spp[gt], G.unit, G.res_pos, G.res_vel, G.sigma_psr(fp.psr_noise_amp),
+                                         G.sigma_dopp(fp.dopp_noise_amp), G.sys, G.R_enu2ecef.reshape(-1, 9),
+                                         R_ecef2enu=R_e2n.reshape(-1, 9), is_adjust_yof=adjust_yof,
+                                         prior_cov_if_rejected=1.0)
+        for b, f in enumerate(orc):
+            ep = GnssEpoch(unit=G.unit[b], res_pos=G.res_pos[b], res_vel=G.res_vel[b], sys=G.sys[b], ura=G.ura[b],
+                           psr_std=G.psr_std[b], dopp_std_mps=G.dopp_std_mps[b], el=G.el[b])
+            out = f.gnss.add_new_tracked_sys(f.state, ep, G.R_enu2ecef[b], [gt], spp, R_ecef2enu=R_e2n[b])
+            assert bool(acc[b]) == bool(out[gt]), (gt, b, acc[b], out)
+            if not out[gt]:
+                # batch semantics: a rejected sequence keeps a decoupled scalar (documented deviation); mirror it
+                SM.add_gnss_variable(f.state, gt, spp[gt], 1.0)
+        assert_state_close(g, orc, wl.sw, what=f"add new sys {gt}")
+    assert not acc is None
