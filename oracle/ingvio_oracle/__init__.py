@@ -22,3 +22,4 @@ from .visual_update import (FeatureInfo, KeyframeUpdate, RemoveLostUpdate, SwMar
 from .gnss_update import GnssEpoch, GnssUpdate, calc_R_w2enu, dot_R_w2enu  # noqa: F401
 from .triangulator import TriParams, Triangulator  # noqa: F401
 from .frame import OracleFilter  # noqa: F401
+from .landmark_update import LandmarkUpdate  # noqa: F401,E402

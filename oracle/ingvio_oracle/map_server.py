@@ -10,14 +10,16 @@ TEST INFRASTRUCTURE (oracle). CPU restatement of
   /root/reference/ingvio_estimator/src/KeyframeUpdate.cpp:251-327,455-480                      (same, two marginalised keyframes)
 and of the wire format feature_tracker/msg/{MonoMeas,StereoMeas}.msg (uint64 id, float64 u0 v0 [u1 v1]).
 SURVEY.md section 8f rank 4 ("next" row). `MapServer` is `std::map<int, shared_ptr<FeatureInfo>>`: a dict here, iterated
-in ascending key order wherever the reference iterates the map. SLAM-type features (section 8f rank 3) are not restated.
+in ascending key order wherever the reference iterates the map. SLAM-type features (section 8f rank 3): the branches of
+collect*Meas (:136, :178), markMarg*Features (:231, :259) and eraseInvalidFeatures (:485) are restated; the landmark algebra
+itself lives in landmark_update.py.
 
 Pinned by the reference's own test: tests/test_oracle_map_server.py restates
 test/TestMapServer.cpp:184-308 (collectFeatureAndMarg, mono and stereo).
 """
 import numpy as np
 
-from .visual_update import MSCKF, FeatureInfo
+from .visual_update import MSCKF, SLAM, FeatureInfo
 
 
 def msg_id_to_key(msg_id):
@@ -60,17 +62,26 @@ def collect_meas(map_server, state, ids, uv, stereo=False):
         else:
             if t in obs:  # "Meas timestamp already in mono obs, skip adding!" (:126-130)
                 continue
+            if f.ftype == SLAM:   # a landmark in the state only keeps its current observation (:136-137, :178-179)
+                obs.clear()
             obs[t] = np.array(z, dtype=np.float64)
             f.is_to_marg = False
 
 
 def mark_marg_features(map_server, state, stereo=False):
     """MapServerManager::markMarg{Mono,Stereo}Features (:221-273), MSCKF part."""
+    from .landmark_update import marg_anchored_landmark_in_state
     t = state.timestamp
+    marg_ids = []
     for key in map_server.ids():
         f = map_server[key]
         if t not in _obs_of(f, stereo):
             f.is_to_marg = True
+            if f.ftype == SLAM:       # a lost landmark leaves the state and the map at once (:231-246)
+                marg_ids.append(key)
+    for key in marg_ids:
+        marg_anchored_landmark_in_state(state, key)
+        del map_server[key]
 
 
 def triangulate_feature_info(feat, tri, state, stereo=False):
@@ -168,13 +179,15 @@ def change_msckf_anchor(map_server, state, marg_times, min_depth):
         del map_server[key]
 
 
-def erase_invalid_features(map_server, min_depth=0.2):
-    """MapServerManager::eraseInvalidFeatures (:454-490)."""
+def erase_invalid_features(map_server, min_depth=0.2, state=None):
+    """MapServerManager::eraseInvalidFeatures (:454-490); `state` is needed once SLAM features exist (:485-486)."""
+    from .landmark_update import marg_anchored_landmark_in_state, sync_feat
     rm = []
     for key in map_server.ids():
         f = map_server[key]
         if not f.is_tri:
             continue
+        sync_feat(f)
         if f.anchor is None:
             rm.append(key)
             continue
@@ -182,6 +195,8 @@ def erase_invalid_features(map_server, min_depth=0.2):
         if body[2] <= min_depth:
             rm.append(key)
     for key in rm:
+        if map_server[key].ftype == SLAM and state is not None:
+            marg_anchored_landmark_in_state(state, key)
         del map_server[key]
 
 

@@ -68,6 +68,7 @@ class StateParams:
         self.noise_cb_rw = 0.2
         self.cam_nums = 2
         self.max_sw_poses = 20
+        self.max_landmarks = 25
         self.enable_gnss = True
         self.T_cl2cr_R, self.T_cl2cr_p = np.eye(3), np.zeros(3)
         self.T_cl2i_R, self.T_cl2i_p = np.eye(3), np.zeros(3)
@@ -80,6 +81,7 @@ class StateParams:
             return
         self.cam_nums = fp.cam_nums
         self.max_sw_poses = fp.max_sw_clones
+        self.max_landmarks = fp.max_lm_feats          # State.cpp:29
         self.T_cl2cr_R, self.T_cl2cr_p = np.array(fp.T_cl2cr_R, float), np.array(fp.T_cl2cr_p, float)
         self.T_cl2i_R, self.T_cl2i_p = np.array(fp.T_cl2i_R, float), np.array(fp.T_cl2i_p, float)
         self.enable_gnss = bool(fp.enable_gnss)

@@ -582,9 +582,8 @@ inline MatX MatX::inverse() const {
   return x;
 }
 
-// Givens rotation with Eigen's conventions: makeGivens(p, q) gives G = [c s; -s c] with G^T [p; q] = [r; 0], and
-// applyOnTheLeft(i, j, G) does rows (x_i, x_j) <- (c x_i - s x_j, s x_i + c x_j)  (real case: [c -s; s c] [x_i; x_j]
-// with Eigen's storage m_c, m_s, where adjoint() flips the sign of s).
+// Givens rotation with Eigen's conventions: makeGivens(p, q) gives G = [c s; -s c] with G^T [p; q] = [r; 0];
+// applyOnTheLeft(i, j, G.adjoint()) therefore maps rows (p, q) to (r, 0): x <- c x - s y, y <- s x + c y.
 template <typename S> class JacobiRotation {
  public:
   JacobiRotation() : c_(1), s_(0) {}
@@ -608,8 +607,9 @@ template <typename S> class JacobiRotation {
   S c_, s_;
 };
 template <typename S> inline void BlockRef::applyOnTheLeft(long p, long q, const JacobiRotation<S>& g) const {
-  // rows x = row p, y = row q:  x <- c x + s y,  y <- -s x + c y   (Eigen's apply_rotation_in_the_plane with j.transpose())
-  const double c = g.c(), s = -g.s();   // applyOnTheLeft(p, q, j) rotates with j.transpose()
+  // Eigen: applyOnTheLeft(p, q, j) hands j itself to apply_rotation_in_the_plane(x = row p, y = row q, j), which does
+  // x <- c x + s y, y <- -s x + c y with j's own (c, s); the reference passes tmpG.adjoint() = (c, -s).
+  const double c = g.c(), s = g.s();
   for (long k = 0; k < c_; ++k) {
     const double xi = (*this)(p, k), yi = (*this)(q, k);
     (*this)(p, k) = c * xi + s * yi;

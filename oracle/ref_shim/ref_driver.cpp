@@ -7,6 +7,7 @@
 //   usage: ref_driver <input.bin> <output.bin>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -59,7 +60,10 @@ int main(int argc, char** argv) {
   fp._cam_nums = rho == 4 ? 2 : 1;
   fp._max_sw_clones = SW;
   fp._is_key_frame = keyframe;
-  fp._max_lm_feats = 0;
+  // SLAM landmarks (LandmarkUpdate, mono): off in the recorded format; IGV_REF_MAX_LM > 0 switches the branch of
+  // IngvioFilter.cpp:155-173 / :181-194 on
+  const char* lm_env = std::getenv("IGV_REF_MAX_LM");
+  fp._max_lm_feats = lm_env ? std::atoi(lm_env) : 0;
   fp._enable_gnss = 0;
   fp._noise_g = in.next(); fp._noise_a = in.next(); fp._noise_bg = in.next(); fp._noise_ba = in.next();
   fp._noise_clockbias = in.next(); fp._noise_cb_rw = in.next();
@@ -93,6 +97,8 @@ int main(int argc, char** argv) {
   auto remove_lost = std::make_shared<RemoveLostUpdate>(fp);
   auto sw_marg = std::make_shared<SwMargUpdate>(fp);
   auto kf_update = std::make_shared<KeyframeUpdate>(fp);
+  auto lm_update = std::make_shared<LandmarkUpdate>(fp);
+  const bool use_lm = fp._max_lm_feats > 0 && rho == 2;
   state->initStateAndCov(0.0, Eigen::Quaterniond(R0), p0, v0, bg0, ba0);
   // the quaternion round trip must not perturb the attitude the other implementations start from
   state->_extended_pose->setValueLinearByMat(R0);
@@ -134,13 +140,27 @@ int main(int argc, char** argv) {
       remove_lost->updateStateMono(state, map_server, tri);           // :149
       if (keyframe) {
         kf_update->updateStateMono(state, map_server, tri);           // :153
+        if (use_lm) {
+          lm_update->updateLandmarkMono(state, map_server);           // :157
+          lm_update->initNewLandmarkMono(state, map_server, tri, fp._max_sw_clones);   // :159-160
+        }
         kf_update->cleanMonoObsAtMargTime(state, map_server);         // :163
         kf_update->changeMSCKFAnchor(state, map_server);              // :165
+        if (use_lm) {
+          std::vector<double> marg_kfs;
+          kf_update->getMargKfs(state, marg_kfs);                     // :169-170
+          lm_update->changeLandmarkAnchor(state, map_server, marg_kfs);   // :172
+        }
         kf_update->margSwPose(state);                                 // :175
       } else {
         sw_marg->updateStateMono(state, map_server, tri);             // :179
+        if (use_lm) {
+          lm_update->updateLandmarkMono(state, map_server);           // :183
+          lm_update->initNewLandmarkMono(state, map_server, tri, fp._max_sw_clones);   // :185-186
+        }
         sw_marg->cleanMonoObsAtMargTime(state, map_server);           // :189
         sw_marg->changeMSCKFAnchor(state, map_server);                // :191
+        if (use_lm) lm_update->changeLandmarkAnchor(state, map_server);   // :193-194
         sw_marg->margSwPose(state);                                   // :196
       }
     } else {
@@ -189,6 +209,15 @@ int main(int argc, char** argv) {
     std::fwrite(hdr, sizeof(double), 3, out);
     std::fwrite(x.data(), sizeof(double), x.size(), out);
     std::fwrite(P.data(), sizeof(double), (std::size_t)(P.rows() * P.cols()), out);   // column-major
+    if (use_lm) {   // landmarks in the state: count, then (id, covariance index, world xyz) in ascending id
+      std::map<int, std::shared_ptr<AnchoredLandmark>> lms(state->_anchored_landmarks.begin(), state->_anchored_landmarks.end());
+      const double nl = (double)lms.size();
+      std::fwrite(&nl, sizeof(double), 1, out);
+      for (const auto& it : lms) {
+        const double rec[5] = {(double)it.first, (double)it.second->idx(), it.second->valuePosXyz()(0), it.second->valuePosXyz()(1), it.second->valuePosXyz()(2)};
+        std::fwrite(rec, sizeof(double), 5, out);
+      }
+    }
   }
   std::fclose(out);
   std::printf("FRAMES DONE %d\n", n_frames);

@@ -26,6 +26,13 @@ def main():
         for f in ref_pin.GOLDEN_FRAMES:
             out[f"{k}_x{f}"] = recs[f]["x"]
             out[f"{k}_P{f}"] = recs[f]["P"]
+    for keyframe, max_lm in ref_pin.LM_CONFIGS:
+        recs = ref_pin.run_ref(keyframe, False, max_lm)
+        k = ref_pin.config_key(keyframe, False, max_lm)
+        for f in ref_pin.GOLDEN_FRAMES:
+            out[f"{k}_x{f}"] = recs[f]["x"]
+            out[f"{k}_P{f}"] = recs[f]["P"]
+            out[f"{k}_lms{f}"] = recs[f]["lms"]
     np.savez_compressed(ref_pin.GOLDEN, **out)
     print("wrote", ref_pin.GOLDEN, os.path.getsize(ref_pin.GOLDEN), "bytes")
 

@@ -24,14 +24,16 @@ from track_frames import OracleFrontEnd
 TOL_P, TOL_X, TOL_BLOCK = 1e-10, 1e-10, 1e-9     # the reference's own unit bars are 1e-8 / 1e-10 (TestStateManager.cpp)
 
 
-def _oracle_records(keyframe, stereo):
+def _oracle_records(keyframe, stereo, max_lm=0):
     wl, fp, st, frames = _stream(keyframe, stereo)
-    fe = OracleFrontEnd(make_oracles(wl, st, fp, with_gnss=False)[0], keyframe)
+    fe = OracleFrontEnd(make_oracles(wl, st, fp, with_gnss=False)[0], keyframe, max_lm_feats=max_lm)
     recs = []
     for fr, n, ids, uv in frames:
         fe.frame(fr.seq(0), int(n[0]), ids[0], uv[0])
+        lms = np.array([[lid, lm.idx()] + list(lm.value_pos_xyz()) for lid, lm in sorted(fe.f.state.anchored_landmarks.items())],
+                       dtype=np.float64).reshape(-1, 5)
         recs.append(dict(P=fe.f.cov().copy(), x=oracle_packed_state(fe.f, SW + 1), blocks=oracle_blocks(fe.f),
-                         ntr=len(fe.ms.ids())))
+                         ntr=len(fe.ms.ids()), lms=lms))
     return recs
 
 
@@ -69,3 +71,41 @@ def test_oracle_matches_reference_live(keyframe, stereo):
     for f, rec in gold.items():
         assert np.allclose(ref[f]["P"], rec["P"], rtol=0, atol=1e-13 * max(1.0, np.abs(rec["P"]).max()))
         assert np.allclose(ref[f]["x"], rec["x"], rtol=0, atol=1e-12)
+
+
+# ---- SLAM landmarks in the state: LandmarkUpdate::updateLandmarkMono / initNewLandmarkMono (delayed
+# initialisation of a 3-dim anchored variable through the Givens sweep of StateManager::addVariableDelayed) /
+# changeLandmarkAnchor (replaceVarLinear) / margAnchoredLandmarkInState, AnchoredLandmark::update -- the unmodified
+# LandmarkUpdate.cpp / AnchoredLandmark.cpp of the reference against oracle/ingvio_oracle/landmark_update.py.
+# Landmark covariances are large right after initialisation (depth is weakly observed), hence the looser covariance bar.
+def _compare_lm(ref, orc, what):
+    assert ref["P"].shape == orc["P"].shape, (what, ref["P"].shape, orc["P"].shape)
+    assert ref["lms"].shape == orc["lms"].shape and np.array_equal(ref["lms"][:, :2], orc["lms"][:, :2]), (what, ref["lms"][:, :2], orc["lms"][:, :2])
+    eP = np.linalg.norm(ref["P"] - orc["P"]) / max(1.0, np.linalg.norm(orc["P"]))
+    assert eP <= 1e-9, f"{what}: |dP|_F = {eP:.3e}"
+    ex = np.max(np.abs(ref["x"] - orc["x"]) / np.maximum(1.0, np.abs(orc["x"])))
+    assert ex <= 1e-10, f"{what}: state {ex:.3e}"
+    if len(ref["lms"]):
+        el = np.max(np.abs(ref["lms"][:, 2:] - orc["lms"][:, 2:]))
+        assert el <= 1e-8, f"{what}: landmark positions {el:.3e}"
+
+
+@pytest.mark.parametrize("keyframe,max_lm", ref_pin.LM_CONFIGS)
+def test_oracle_landmarks_match_reference_golden(keyframe, max_lm):
+    gold = ref_pin.load_golden()[ref_pin.config_key(keyframe, False, max_lm)]
+    orc = _oracle_records(keyframe, False, max_lm)
+    assert max(len(r["lms"]) for r in orc) == max_lm      # the scenario does fill the landmark slots
+    for f, rec in gold.items():
+        _compare_lm(rec, orc[f], f"{ref_pin.config_key(keyframe, False, max_lm)} frame {f} (golden)")
+
+
+@pytest.mark.parametrize("keyframe,max_lm", ref_pin.LM_CONFIGS)
+def test_oracle_landmarks_match_reference_live(keyframe, max_lm):
+    if not ref_pin.build_ref():
+        pytest.skip("oracle/_ref/ref_driver not built and /root/reference absent: the golden test above is the pin")
+    ref = ref_pin.run_ref(keyframe, False, max_lm)
+    orc = _oracle_records(keyframe, False, max_lm)
+    assert len(ref) == len(orc)
+    for k, (r, o_) in enumerate(zip(ref, orc)):
+        assert r["ntr"] == o_["ntr"], (k, r["ntr"], o_["ntr"])
+        _compare_lm(r, o_, f"{ref_pin.config_key(keyframe, False, max_lm)} frame {k} (live)")

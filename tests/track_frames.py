@@ -11,8 +11,12 @@ from ingvio_oracle import map_server as oms
 class OracleFrontEnd:
     """One sequence: OracleFilter + MapServer + Triangulator, non-keyframe (SwMargUpdate) or keyframe mode."""
 
-    def __init__(self, oracle_filter, keyframe=False, max_valid=20):
+    def __init__(self, oracle_filter, keyframe=False, max_valid=20, max_lm_feats=0):
         self.f = oracle_filter
+        self.max_lm = max_lm_feats
+        self.lm = o.LandmarkUpdate(oracle_filter.fp) if max_lm_feats > 0 else None
+        if max_lm_feats > 0:
+            oracle_filter.state.state_params.max_landmarks = max_lm_feats
         self.ms = oms.MapServer()
         self.tri = o.Triangulator(o.TriParams())
         self.keyframe = keyframe
@@ -52,9 +56,20 @@ class OracleFrontEnd:
             upd = oms.select_seen_at(ms, self.tri, st, sel_ts, stereo)
             self.counts["sel"] += len(upd)
             updater._update_selected(st, ms, sel_ts, dof, stereo)
+        if self.lm is not None:      # IngvioFilter.cpp:155-161 / :181-187 (the reference runs these every frame)
+            self.lm.update_landmark_mono(st, ms)
+            self.lm.init_new_landmark_mono(st, ms, lambda ft: oms.triangulate_feature_info(ft, self.tri, st, stereo),
+                                           f.fp.max_sw_clones)
+        if marg_ts:
             oms.clean_obs_at(ms, marg_ts, stereo)
             oms.change_msckf_anchor(ms, st, marg_ts, thr)
+        if self.lm is not None:      # :167-173 (keyframes: the clones about to leave) / :193-194 (next marg time)
+            if self.keyframe:
+                self.lm.change_landmark_anchor(st, ms, list(marg_ts))
+            else:
+                self.lm.change_landmark_anchor(st, ms)
+        if marg_ts:
             for t in marg_ts:
                 SM.marg_sliding_window_pose(st, t)
-        oms.erase_invalid_features(ms, 0.2)
+        oms.erase_invalid_features(ms, 0.2, state=st)
         return info
