@@ -78,6 +78,8 @@ typedef struct {
   int stereo;       /* 0: 2 rows per observation, 1: 4 rows (left + right camera)                */
   int device;       /* CUDA device ordinal                                                       */
   void* stream;     /* cudaStream_t to enqueue on, or NULL for a stream owned by the handle      */
+  int max_landmarks;/* SLAM landmarks kept in the state (StateParams::_max_landmarks), 0..32; 0 = none;
+                       max_dim must leave room for 3 per landmark                                  */
 } igv_config;
 
 /* StateParams (State.h:36-70) + gravity (ImuPropagator.h) */
@@ -426,6 +428,51 @@ igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value
                                     const double* H_new, const double* res, double noise_iso,
                                     double chi2_mult, int do_chi2, double prior_cov_if_rejected,
                                     int* accepted_out, double* dx_out);
+/* ---- SLAM landmarks in the state (mono) ------------------------------------------
+ * An anchored landmark is a 3-dim variable holding the world position p_f, tied to an anchor clone
+ * (AnchoredLandmark.h:27-108); its retraction is p_f <- Gamma0(dtheta_anchor) p_f + Gamma1(dtheta_anchor) dp
+ * (AnchoredLandmark.cpp:227-243), applied by every update once landmarks exist. The packed mean gains 3 doubles per
+ * landmark slot after the clones (igv_state_size). Landmark slots are in order of insertion. */
+int igv_num_landmarks(const igv_batch* h);
+int igv_landmark_idx(const igv_batch* h, int lm_slot);           /* Type::idx(), -1 if absent            */
+int igv_landmark_anchor(const igv_batch* h, int lm_slot);        /* anchor clone slot                    */
+/* LandmarkUpdate::initNewLandmarkMono, the body of its loop for ONE track (LandmarkUpdate.cpp:395-421 with
+ * calcResJacobianSingleFeatAllMonoObs :426-500): rows over every clone of the window that observed the track,
+ * H_x on the clones, H_f (rows x 3) on the landmark, then StateManager::addVariableDelayed (Givens split of H_f, 0.95
+ * chi^2 gate times chi2_mult on the remaining rows, invertible 3 x 3 initialisation, EKF on the remaining rows).
+ * Sequences that fail the gate (or have fewer than two observations) keep a decoupled landmark with
+ * prior_cov_if_rejected on its diagonal, so that the batch keeps one layout (B = 1: marginalise it again = the
+ * reference's `continue`). */
+typedef struct {
+  int obs_slots;             /* SW' >= number of clones                                            */
+  int anchor_slot;           /* anchor clone slot of the new landmark (shared by the batch)         */
+  const double* pf_w;        /* B x 3      triangulated world position                              */
+  const double* obs;         /* B x SW' x 2 normalised image coordinates per clone slot             */
+  const unsigned char* obs_mask; /* B x SW'                                                         */
+  double noise;              /* _noise = visual_noise                                               */
+  double chi2_mult;          /* 0 = the reference's 0.95                                            */
+  double prior_cov_if_rejected;
+  int* accepted_out;         /* optional B                                                          */
+} igv_lm_init_args;
+igv_status igv_landmark_init(igv_batch* h, const igv_lm_init_args* a);
+/* LandmarkUpdate::updateLandmarkMono (LandmarkUpdate.cpp:32-149 with calcResJacobianSingleLandmarkMono :521-572):
+ * every landmark of the state observed in the current image contributes 2 rows on [SE23 | cam-IMU extrinsics | anchor
+ * clone | landmark], gated by the chi^2 test (dof 2) and stacked into one EKF update with R = noise^2 I. */
+typedef struct {
+  const double* uv;          /* B x L x 2  current observation of landmark slot l (L = igv_num_landmarks) */
+  const unsigned char* valid;/* B x L      0: skip this landmark in this sequence                   */
+  double noise;
+  int* n_accepted_out;       /* optional B                                                          */
+  double* gamma_out;         /* optional B x L gate statistic (NaN where skipped)                   */
+} igv_lm_update_args;
+igv_status igv_landmark_update(igv_batch* h, const igv_lm_update_args* a);
+/* FeatureInfoManager::changeAnchoredPose (MapServerManager.cpp:343-378): the landmark becomes a linear function of
+ * (old anchor, new anchor, itself) through StateManager::replaceVarLinear with H = [-[p_f]x 0 | [p_f]x 0 | I]; the world
+ * position is unchanged. */
+igv_status igv_landmark_change_anchor(igv_batch* h, int lm_slot, int new_clone_slot);
+/* StateManager::margAnchoredLandmarkInState (StateManager.cpp:340-353). */
+igv_status igv_landmark_marginalize(igv_batch* h, int lm_slot);
+
 /* StateManager::replaceVarLinear (StateManager.cpp:632-693). H: size(target) x n, col-major, B x ... */
 igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size, int n_blocks,
                                   const int* blk_idx, const int* blk_size, const double* H);

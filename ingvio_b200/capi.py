@@ -25,7 +25,8 @@ c_ucp = C.POINTER(C.c_ubyte)
 
 class igv_config(C.Structure):
     _fields_ = [("batch", C.c_int), ("max_dim", C.c_int), ("max_clones", C.c_int), ("max_feats", C.c_int),
-                ("max_sats", C.c_int), ("stereo", C.c_int), ("device", C.c_int), ("stream", C.c_void_p)]
+                ("max_sats", C.c_int), ("stereo", C.c_int), ("device", C.c_int), ("stream", C.c_void_p),
+                ("max_landmarks", C.c_int)]
 
 
 class igv_params(C.Structure):
@@ -65,6 +66,17 @@ class igv_gnss_new_sys_args(C.Structure):
                 ("sys", C.c_void_p), ("R_enu2ecef", C.c_void_p), ("R_ecef2enu", C.c_void_p), ("is_adjust_yof", C.c_int),
                 ("chi2_mult", C.c_double), ("prior_cov_if_rejected", C.c_double), ("accepted_out", C.c_void_p),
                 ("dx_out", C.c_void_p)]
+
+
+class igv_lm_init_args(C.Structure):
+    _fields_ = [("obs_slots", C.c_int), ("anchor_slot", C.c_int), ("pf_w", C.c_void_p), ("obs", C.c_void_p),
+                ("obs_mask", C.c_void_p), ("noise", C.c_double), ("chi2_mult", C.c_double),
+                ("prior_cov_if_rejected", C.c_double), ("accepted_out", C.c_void_p)]
+
+
+class igv_lm_update_args(C.Structure):
+    _fields_ = [("uv", C.c_void_p), ("valid", C.c_void_p), ("noise", C.c_double), ("n_accepted_out", C.c_void_p),
+                ("gamma_out", C.c_void_p)]
 
 
 class igv_gnss_res_args(C.Structure):
@@ -144,6 +156,13 @@ SIGNATURES = {
     "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
     "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
     "igv_gnss_add_new_tracked_sys": (C.c_int, [_H, C.POINTER(igv_gnss_new_sys_args)]),
+    "igv_num_landmarks": (C.c_int, [_H]),
+    "igv_landmark_idx": (C.c_int, [_H, C.c_int]),
+    "igv_landmark_anchor": (C.c_int, [_H, C.c_int]),
+    "igv_landmark_init": (C.c_int, [_H, C.POINTER(igv_lm_init_args)]),
+    "igv_landmark_update": (C.c_int, [_H, C.POINTER(igv_lm_update_args)]),
+    "igv_landmark_change_anchor": (C.c_int, [_H, C.c_int, C.c_int]),
+    "igv_landmark_marginalize": (C.c_int, [_H, C.c_int]),
     "igv_gnss_residuals": (C.c_int, [_H, C.POINTER(igv_gnss_res_args)]),
     "igv_sat_states": (C.c_int, [_H, C.POINTER(igv_sat_state_args)]),
     "igv_triangulate": (C.c_int, [_H, C.POINTER(igv_tri_args)]),

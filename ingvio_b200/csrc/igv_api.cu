@@ -216,11 +216,14 @@ double reg_gamma_p(double a, double x) {
 IgvLayout igv_batch::layout() const {
   IgvLayout L;
   L.N = N; L.ld = ld; L.xsize = xsize; L.n_clones = 0;
+  L.n_lm = 0; L.lm_off = IGV_X_CORE + 12 * cfg.max_clones;
   for (int i = 0; i < 6; ++i) L.idx_gnss[i] = -1;
   for (int i = 0; i < IGV_MAX_CLONES; ++i) L.idx_clone[i] = -1;
+  for (int i = 0; i < IGV_MAX_LM; ++i) { L.idx_lm[i] = -1; L.lm_anchor[i] = -1; }
   for (const auto& v : vars) {
     if (v.kind == VK_GNSS) L.idx_gnss[v.tag] = v.idx;
     if (v.kind == VK_CLONE && L.n_clones < IGV_MAX_CLONES) L.idx_clone[L.n_clones++] = v.idx;
+    if (v.kind == VK_LANDMARK && L.n_lm < IGV_MAX_LM) { L.idx_lm[L.n_lm] = v.idx; L.lm_anchor[L.n_lm] = v.tag; ++L.n_lm; }
   }
   return L;
 }
@@ -231,13 +234,14 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
   if (!cfg || !out) return IGV_ERR_INVALID;
   *out = nullptr;
   if (cfg->batch < 1 || cfg->max_dim < 21 || cfg->max_dim > 512 || cfg->max_clones < 0 ||
-      cfg->max_clones > IGV_MAX_CLONES || cfg->max_feats < 0 || cfg->max_sats < 0 || cfg->max_sats > 64)
+      cfg->max_clones > IGV_MAX_CLONES || cfg->max_feats < 0 || cfg->max_sats < 0 || cfg->max_sats > 64 ||
+      cfg->max_landmarks < 0 || cfg->max_landmarks > IGV_MAX_LM)
     return IGV_ERR_INVALID;
   igv_batch* h = new igv_batch();
   h->cfg = *cfg;
   h->B = cfg->batch;
   h->ld = (cfg->max_dim + 1) & ~1;
-  h->xsize = IGV_X_CORE + 12 * cfg->max_clones;
+  h->xsize = IGV_X_CORE + 12 * cfg->max_clones + 3 * cfg->max_landmarks;
   h->rho = cfg->stereo ? 4 : 2;
   h->ncols_max = 6 * std::max(1, cfg->max_clones);
   h->qmax = std::max(1, h->rho * cfg->max_clones - 3);
@@ -323,7 +327,14 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
   IGV_ALLOC(h->Rg, B * S2);
   IGV_ALLOC(h->cnt_g, B);
   IGV_ALLOC(h->gam_ws, B);
-  IGV_ALLOC(h->Dws, B * (128 * 18 + 2));
+  if (cfg->max_landmarks > 0) {   // landmark initialisation measures every clone: rows rho * clones, columns 6 * clones
+    h->dws_rows = std::max(128, h->rho * cfg->max_clones);
+    h->dws_cols = std::max(16, 6 * cfg->max_clones);
+  }
+  h->dws_stride = (size_t)h->dws_rows * (h->dws_cols + 2) + 16;
+  IGV_ALLOC(h->Dws, B * h->dws_stride);
+  if (cfg->max_landmarks > 0)
+    IGV_ALLOC(h->Lws, B * (size_t)(2 * cfg->max_landmarks) * (15 + 6 * cfg->max_clones + 3 * cfg->max_landmarks + 2));
 #undef IGV_ALLOC
   // defaults of StateParams (State.h:48-53)
   h->params.noise_g = 0.005; h->params.noise_a = 0.05; h->params.noise_bg = 0.001; h->params.noise_ba = 0.01;
@@ -340,7 +351,7 @@ igv_status igv_destroy(igv_batch* h) {
   if (!h) return IGV_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->chi2_095, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
-                  h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->pre_ws};
+                  h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->Lws, h->pre_ws};
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   for (void* p : ptrs) if (p) cudaFree(p);
   void* tptrs[] = {h->trk.id, h->trk.mask, h->trk.st, h->trk.anchor, h->trk.pf, h->trk.pf_fej, h->trk.obs};
@@ -569,13 +580,24 @@ static igv_status marginalize_var(igv_batch* h, size_t vi) {
   const IgvVar v = h->vars[vi];
   if (v.kind == VK_SE23 || v.kind == VK_BG || v.kind == VK_BA || v.kind == VK_EXT)
     return fail(h, IGV_ERR_STATE, "core variables cannot be marginalised");
-  int clone_slot = -1;
+  int clone_slot = -1, lm_slot = -1;
   if (v.kind == VK_CLONE) {
     clone_slot = 0;
     for (size_t k = 0; k < vi; ++k) if (h->vars[k].kind == VK_CLONE) ++clone_slot;
+    // a landmark must have left its anchor before the clone goes (LandmarkUpdate::changeLandmarkAnchor precedes margSwPose,
+    // IngvioFilter.cpp:167-175, :193-196)
+    for (const auto& w : h->vars)
+      if (w.kind == VK_LANDMARK && w.tag == clone_slot) return fail(h, IGV_ERR_STATE, "a landmark is still anchored at this clone");
   }
-  igv_launch_marginalize(h, v.idx, v.size, clone_slot);
-  if (clone_slot >= 0) trk_on_marg_clone(h, clone_slot);
+  if (v.kind == VK_LANDMARK) {
+    lm_slot = 0;
+    for (size_t k = 0; k < vi; ++k) if (h->vars[k].kind == VK_LANDMARK) ++lm_slot;
+  }
+  igv_launch_marginalize(h, v.idx, v.size, clone_slot, lm_slot);
+  if (clone_slot >= 0) {
+    trk_on_marg_clone(h, clone_slot);
+    for (auto& w : h->vars) if (w.kind == VK_LANDMARK && w.tag > clone_slot) --w.tag;   // later clones move down one slot
+  }
   h->vars.erase(h->vars.begin() + vi);
   reindex(h);
   return check_launch(h);
@@ -946,23 +968,33 @@ igv_status igv_gnss_update(igv_batch* h, const igv_gnss_args* a) {
 // Shared tail of igv_add_variable_delayed / igv_gnss_add_new_tracked_sys. All pointers are DEVICE pointers here.
 // noise2_dev / rows_dev (optional, B each): per-sequence measurement variance and true row count (rows beyond it are
 // zero padding: they change neither the Givens split nor the posterior, only the dof of the gate).
-static igv_status delayed_common(igv_batch* h, int gtype, const double* dval, const IgvBlocks& blk, int rows,
-                                 const double* dHo, const double* dHn, const double* dr, double noise_iso,
+static igv_status delayed_common(igv_batch* h, int gtype, const double* dval, const IgvBlocks& blk, int rows, int k,
+                                 int lm_anchor, const double* dHo, const double* dHn, const double* dr, double noise_iso,
                                  const double* noise2_dev, const int* rows_dev, double chi2_mult, int do_chi2,
                                  double prior_cov_if_rejected, int* accepted_out, double* dx_out) {
   const size_t B = h->B;
   int* dacc = h->n_acc;
-  igv_launch_delayed_init(h, blk, rows, dHo, dHn, dr, noise_iso, noise2_dev, rows_dev, chi2_mult, do_chi2,
+  if ((size_t)rows * (blk.n + 2) + 16 > h->dws_stride) return fail(h, IGV_ERR_CAPACITY, "delayed-init workspace too small");
+  igv_launch_delayed_init(h, blk, rows, k, dHo, dHn, dr, noise_iso, noise2_dev, rows_dev, chi2_mult, do_chi2,
                           prior_cov_if_rejected, dacc);
   IGV_TRY(check_launch(h));
-  h->vars.push_back({gtype >= 0 ? VK_GNSS : VK_OPAQUE, h->N, 1, gtype >= 0 ? gtype : 0});
-  reindex(h);
-  if (gtype >= 0) { igv_launch_set_gnss_value(h, gtype, dval); IGV_TRY(check_launch(h)); }
+  if (lm_anchor >= 0) {   // a landmark: value = the triangulated world position, tied to its anchor clone
+    int lm_slot = 0;
+    for (const auto& v : h->vars) if (v.kind == VK_LANDMARK) ++lm_slot;
+    h->vars.push_back({VK_LANDMARK, h->N, 3, lm_anchor});
+    reindex(h);
+    igv_launch_set_lm_value(h, lm_slot, dval);
+    IGV_TRY(check_launch(h));
+  } else {
+    h->vars.push_back({gtype >= 0 ? VK_GNSS : VK_OPAQUE, h->N, 1, gtype >= 0 ? gtype : 0});
+    reindex(h);
+    if (gtype >= 0) { igv_launch_set_gnss_value(h, gtype, dval); IGV_TRY(check_launch(h)); }
+  }
   // EKF on the remaining rows (StateManager.cpp:626-627), only where the variable was accepted
   IgvEkfLaunch e{};
-  e.blk = blk; e.rows = rows - 1;
-  e.H = h->Dws + 1; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
-  e.res = h->Dws + B * rows * blk.n + 1; e.strideRes = rows; e.res_inc = 1;
+  e.blk = blk; e.rows = rows - k;
+  e.H = h->Dws + k; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
+  e.res = h->Dws + B * rows * blk.n + k; e.strideRes = rows; e.res_inc = 1;
   e.R = noise2_dev; e.strideR = noise2_dev ? 1 : 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
   e.only_if = dacc; e.apply_boxplus = 1;
   double* ddx = nullptr;
@@ -998,8 +1030,8 @@ igv_status igv_add_variable_delayed(igv_batch* h, int gtype, const double* value
   IGV_TRY(stage(h, H_new, B * rows, &dHn));
   IGV_TRY(stage(h, res, B * rows, &dr));
   if (gtype >= 0) IGV_TRY(stage(h, value, B, &dval));
-  if (blk.n > 16) return fail(h, IGV_ERR_CAPACITY, "delayed init supports at most 16 measured columns");
-  return delayed_common(h, gtype, dval, blk, rows, dHo, dHn, dr, noise_iso, nullptr, nullptr, chi2_mult, do_chi2,
+  if (blk.n > h->dws_cols) return fail(h, IGV_ERR_CAPACITY, "too many measured columns for the delayed-init workspace");
+  return delayed_common(h, gtype, dval, blk, rows, 1, -1, dHo, dHn, dr, noise_iso, nullptr, nullptr, chi2_mult, do_chi2,
                         prior_cov_if_rejected, accepted_out, dx_out);
 }
 
@@ -1047,8 +1079,138 @@ igv_status igv_gnss_add_new_tracked_sys(igv_batch* h, const igv_gnss_new_sys_arg
   blk.n_blocks = 2; blk.n = 10;
   blk.idx[0] = 0; blk.size[0] = 9;
   blk.idx[1] = L.idx_gnss[IGV_GNSS_YOF]; blk.size[1] = 1;
-  return delayed_common(h, a->gtype, dval, blk, a->n_sats, g.Hx, g.Hf, g.res, 0.0, g.noise2, g.count,
+  return delayed_common(h, a->gtype, dval, blk, a->n_sats, 1, -1, g.Hx, g.Hf, g.res, 0.0, g.noise2, g.count,
                         a->chi2_mult > 0.0 ? a->chi2_mult : 0.95, 1, a->prior_cov_if_rejected, a->accepted_out, a->dx_out);
+}
+
+// ---- SLAM landmarks ----------------------------------------------------------------------------------------------
+int igv_num_landmarks(const igv_batch* h) { return h ? h->layout().n_lm : -1; }
+int igv_landmark_idx(const igv_batch* h, int lm_slot) {
+  if (!h) return -1;
+  IgvLayout L = h->layout();
+  return (lm_slot >= 0 && lm_slot < L.n_lm) ? L.idx_lm[lm_slot] : -1;
+}
+int igv_landmark_anchor(const igv_batch* h, int lm_slot) {
+  if (!h) return -1;
+  IgvLayout L = h->layout();
+  return (lm_slot >= 0 && lm_slot < L.n_lm) ? L.lm_anchor[lm_slot] : -1;
+}
+
+igv_status igv_landmark_init(igv_batch* h, const igv_lm_init_args* a) {
+  IgvDeviceGuard dev_guard_(h);
+  if (!h || !a || !a->pf_w || !a->obs || !a->obs_mask) return IGV_ERR_INVALID;
+  if (h->rho != 2) return fail(h, IGV_ERR_STATE, "landmarks: mono handles only");
+  IgvLayout L = h->layout();
+  if (L.n_lm >= h->cfg.max_landmarks) return fail(h, IGV_ERR_CAPACITY, "no vacant landmark slot (max_landmarks)");
+  if (a->obs_slots < L.n_clones || L.n_clones < 2) return fail(h, IGV_ERR_INVALID, "obs_slots smaller than the clone count");
+  if (a->anchor_slot < 0 || a->anchor_slot >= L.n_clones) return fail(h, IGV_ERR_INVALID, "anchor clone not in the window");
+  if (h->N + 3 > h->cfg.max_dim) return fail(h, IGV_ERR_CAPACITY, "state dimension exceeds max_dim");
+  const int rows = 2 * L.n_clones, n = 6 * L.n_clones;
+  if (rows > 128 || rows - 3 > h->max_rows || n > h->dws_cols) return fail(h, IGV_ERR_CAPACITY, "window too large for the delayed-init workspace");
+  arena_reset(h);
+  const size_t B = h->B, SW = a->obs_slots;
+  IgvLmInitLaunch g{};
+  g.SW = a->obs_slots; g.anchor_slot = a->anchor_slot; g.rows_max = rows;
+  IGV_TRY(stage(h, a->pf_w, B * 3, &g.pf));
+  IGV_TRY(stage(h, a->obs, B * SW * 2, &g.obs));
+  IGV_TRY(stage(h, a->obs_mask, B * SW, &g.mask));
+  char* mem = nullptr;
+  IGV_TRY(arena_reserve(h, sizeof(double) * B * ((size_t)rows * (n + 4)) + sizeof(int) * B, &mem));
+  g.Hx = reinterpret_cast<double*>(mem);
+  g.Hf = g.Hx + B * rows * n;
+  g.res = g.Hf + B * rows * 3;
+  g.count = reinterpret_cast<int*>(g.res + B * rows);
+  igv_launch_lm_init_rows(h, g);
+  IGV_TRY(check_launch(h));
+  IgvBlocks blk;
+  blk.n_blocks = L.n_clones; blk.n = n;
+  for (int s = 0; s < L.n_clones; ++s) { blk.idx[s] = L.idx_clone[s]; blk.size[s] = 6; }
+  return delayed_common(h, -1, g.pf, blk, rows, 3, a->anchor_slot, g.Hx, g.Hf, g.res, a->noise, nullptr, g.count,
+                        a->chi2_mult > 0.0 ? a->chi2_mult : 0.95, 1, a->prior_cov_if_rejected, a->accepted_out, nullptr);
+}
+
+igv_status igv_landmark_update(igv_batch* h, const igv_lm_update_args* a) {
+  IgvDeviceGuard dev_guard_(h);
+  if (!h || !a) return IGV_ERR_INVALID;
+  IgvLayout L = h->layout();
+  if (L.n_lm == 0) return IGV_OK;                                   // LandmarkUpdate.cpp:35
+  if (!a->uv || !a->valid) return IGV_ERR_INVALID;
+  if (h->chi2_n < 2) return fail(h, IGV_ERR_STATE, "chi^2 table not set (igv_set_chi2_table)");
+  const int rows = 2 * L.n_lm, ncols = 15 + 6 * L.n_clones + 3 * L.n_lm;
+  if (rows > h->max_rows) return fail(h, IGV_ERR_CAPACITY, "rows exceed the EKF workspace (max_rows)");
+  arena_reset(h);
+  const size_t B = h->B, nl = L.n_lm;
+  IgvLmUpdateLaunch g{};
+  IGV_TRY(stage(h, a->uv, B * nl * 2, &g.uv));
+  IGV_TRY(stage(h, a->valid, B * nl, &g.valid));
+  g.noise2 = a->noise * a->noise;
+  g.H = h->Lws; g.ldh = rows; g.ncols = ncols;
+  g.res = h->Lws + B * (size_t)rows * ncols;
+  double* dgam = nullptr;
+  IGV_TRY(out_buf(h, a->gamma_out, B * nl, &dgam));
+  g.gamma = dgam; g.n_acc = h->n_acc;
+  igv_launch_lm_update_rows(h, g);
+  IGV_TRY(check_launch(h));
+  IgvEkfLaunch e{};
+  IgvBlocks& blk = e.blk;
+  blk.n_blocks = 0; blk.n = 0;
+  auto push = [&](int idx, int size) { blk.idx[blk.n_blocks] = idx; blk.size[blk.n_blocks] = size; blk.n_blocks++; blk.n += size; };
+  push(0, 9); push(15, 6);
+  for (int s = 0; s < L.n_clones; ++s) push(L.idx_clone[s], 6);
+  for (int l = 0; l < L.n_lm; ++l) push(L.idx_lm[l], 3);
+  e.rows = rows; e.H = g.H; e.strideH = (long)rows * ncols; e.h_ld = rows; e.h_rowmajor = 0;
+  e.res = g.res; e.strideRes = rows; e.res_inc = 1;
+  e.R = nullptr; e.strideR = 0; e.r_kind = IGV_R_ISO; e.r_iso_value = g.noise2;
+  e.only_if = h->n_acc; e.apply_boxplus = 1;
+  igv_launch_ekf(h, e);
+  IGV_TRY(check_launch(h));
+  IGV_TRY(fetch(h, a->gamma_out, dgam, B * nl));
+  if (a->n_accepted_out) {
+    if (h->ptr_mode == IGV_PTR_DEVICE)
+      IGV_CUDA(h, cudaMemcpyAsync(a->n_accepted_out, h->n_acc, sizeof(int) * B, cudaMemcpyDeviceToDevice, h->stream));
+    else IGV_TRY(fetch(h, a->n_accepted_out, h->n_acc, B));
+  }
+  return IGV_OK;
+}
+
+igv_status igv_landmark_change_anchor(igv_batch* h, int lm_slot, int new_clone_slot) {
+  IgvDeviceGuard dev_guard_(h);
+  if (!h) return IGV_ERR_INVALID;
+  IgvLayout L = h->layout();
+  if (lm_slot < 0 || lm_slot >= L.n_lm) return fail(h, IGV_ERR_STATE, "landmark slot not in the state");
+  if (new_clone_slot < 0 || new_clone_slot >= L.n_clones) return fail(h, IGV_ERR_STATE, "clone slot not in the sliding window");
+  if (L.n_clones < 2) return IGV_OK;                                 // MapServerManager.cpp:347
+  const int old = L.lm_anchor[lm_slot];
+  if (old == new_clone_slot) return IGV_OK;
+  arena_reset(h);
+  char* mem = nullptr;
+  IGV_TRY(arena_reserve(h, sizeof(double) * (size_t)h->B * 45, &mem));
+  double* H = reinterpret_cast<double*>(mem);
+  igv_launch_lm_anchor_H(h, lm_slot, H);
+  IGV_TRY(check_launch(h));
+  IgvBlocks blk;
+  blk.n_blocks = 3; blk.n = 15;
+  blk.idx[0] = L.idx_clone[old]; blk.size[0] = 6;
+  blk.idx[1] = L.idx_clone[new_clone_slot]; blk.size[1] = 6;
+  blk.idx[2] = L.idx_lm[lm_slot]; blk.size[2] = 3;
+  igv_launch_replace_var_linear(h, L.idx_lm[lm_slot], 3, blk, H);
+  IGV_TRY(check_launch(h));
+  int l = 0;
+  for (auto& v : h->vars)
+    if (v.kind == VK_LANDMARK) { if (l == lm_slot) v.tag = new_clone_slot; ++l; }
+  return IGV_OK;
+}
+
+igv_status igv_landmark_marginalize(igv_batch* h, int lm_slot) {
+  IgvDeviceGuard dev_guard_(h);
+  if (!h) return IGV_ERR_INVALID;
+  int l = 0;
+  for (size_t i = 0; i < h->vars.size(); ++i)
+    if (h->vars[i].kind == VK_LANDMARK) {
+      if (l == lm_slot) return marginalize_var(h, i);
+      ++l;
+    }
+  return fail(h, IGV_ERR_STATE, "[StateManager]: Landmark id not exists in state! Cannot marg!");   // StateManager.cpp:342-346
 }
 
 igv_status igv_replace_var_linear(igv_batch* h, int target_idx, int target_size, int n_blocks, const int* blk_idx,

@@ -144,17 +144,34 @@ __device__ inline void boxplus_var(double* X, const double* dx, const IgvLayout&
   } else if (v < 10) {
     const int g = v - 4;
     if (L.idx_gnss[g] >= 0) X[33 + g] += dx[L.idx_gnss[g]];
-  } else {
+  } else if (v < 10 + L.n_clones) {
     const int s = v - 10;
-    if (s < L.n_clones) {
-      double* c = X + IGV_X_CORE + 12 * s;
-      const double* d = dx + L.idx_clone[s];
-      retract_pose(c, c + 9, nullptr, d, d + 3, nullptr);
+    double* c = X + IGV_X_CORE + 12 * s;
+    const double* d = dx + L.idx_clone[s];
+    retract_pose(c, c + 9, nullptr, d, d + 3, nullptr);
+  } else {
+    // AnchoredLandmark::update (AnchoredLandmark.cpp:227-243): p_f <- Gamma0(dtheta_anchor) p_f + Gamma1(dtheta_anchor) dp
+    const int l = v - 10 - L.n_clones;
+    if (l < L.n_lm) {
+      double* pf = X + L.lm_off + 3 * l;
+      const double* dp = dx + L.idx_lm[l];
+      const int a = L.lm_anchor[l];
+      if (a >= 0 && a < L.n_clones) {
+        const double* dth = dx + L.idx_clone[a];
+        double G0[9], G1[9], t[3], u[3];
+        gamma_func(dth, 0, G0);
+        gamma_func(dth, 1, G1);
+        mat3_vec(G0, pf, t);
+        mat3_vec(G1, dp, u);
+        for (int i = 0; i < 3; ++i) pf[i] = t[i] + u[i];
+      } else {
+        for (int i = 0; i < 3; ++i) pf[i] += dp[i];
+      }
     }
   }
 }
 __device__ inline void boxplus_all(double* X, const double* dx, const IgvLayout& L) {
-  for (int v = threadIdx.x; v < 10 + L.n_clones; v += blockDim.x) boxplus_var(X, dx, L, v);
+  for (int v = threadIdx.x; v < 10 + L.n_clones + L.n_lm; v += blockDim.x) boxplus_var(X, dx, L, v);
 }
 
 // ---------------------------------------------------------------------------------------------

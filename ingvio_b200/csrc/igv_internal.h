@@ -9,7 +9,8 @@
 #include "../../include/ingvio_b200.h"
 
 #define IGV_MAX_CLONES 64
-#define IGV_MAX_BLOCKS 80
+#define IGV_MAX_BLOCKS 100
+#define IGV_MAX_LM 32
 #define IGV_X_CORE 39          // packed mean: 33 core doubles + 6 GNSS scalars, then 12 per clone
 
 // Variable layout of the batch, passed BY VALUE to kernels (all sequences share it).
@@ -20,6 +21,10 @@ struct IgvLayout {
   int n_clones;
   int idx_clone[IGV_MAX_CLONES]; // Type::idx() of clone slot s (0 = oldest)
   int idx_gnss[6];               // Type::idx() of GPS,GLO,GAL,BDS,FS,YOF or -1
+  int n_lm;                      // SLAM landmarks in the state
+  int lm_off;                    // offset of the landmark values (3 each) in the packed mean
+  int idx_lm[IGV_MAX_LM];        // Type::idx() of landmark slot l
+  int lm_anchor[IGV_MAX_LM];     // anchor clone slot of landmark slot l
 };
 
 struct IgvBlocks {               // a var_order as (idx,size) blocks
@@ -57,11 +62,11 @@ struct IgvTrkCols {                        // by-value kernel argument
   signed char slot_of_col[IGV_MAX_CLONES];
 };
 
-enum IgvVarKind { VK_SE23, VK_BG, VK_BA, VK_EXT, VK_GNSS, VK_CLONE, VK_OPAQUE };
+enum IgvVarKind { VK_SE23, VK_BG, VK_BA, VK_EXT, VK_GNSS, VK_CLONE, VK_OPAQUE, VK_LANDMARK };
 struct IgvVar {
   IgvVarKind kind;
   int idx, size;
-  int tag;                       // gnss type for VK_GNSS
+  int tag;                       // gnss type for VK_GNSS, anchor clone slot for VK_LANDMARK
 };
 
 // Test / tuning knobs, read from the environment ONCE per handle (igv_create), never on the launch path.
@@ -133,7 +138,10 @@ struct igv_batch {
   double* Rg = nullptr;                // B x 2*max_sats
   int* cnt_g = nullptr;                // B accepted GNSS rows
   double* gam_ws = nullptr;            // B
-  double* Dws = nullptr;               // delayed-init workspace: B x (128*18 + 2)
+  double* Dws = nullptr;               // delayed-init workspace: B x dws_stride
+  size_t dws_stride = 0;
+  int dws_rows = 128, dws_cols = 16;   // most rows / measured columns of a delayed initialisation
+  double* Lws = nullptr;               // landmark-update rows: B x (2 L) x (lm_cols + 2)
   double* pre_ws = nullptr;            // per (sequence, IMU step) Phi (225) + G*sigma (180), row-major
   size_t pre_cap = 0;
   std::vector<double> chi2_host;
@@ -202,7 +210,7 @@ void igv_launch_state_init(igv_batch* h, const double* R, const double* p, const
 void igv_launch_cov_copy(igv_batch* h, double* user, int ld_user, bool to_user);
 void igv_launch_cov_blocks(igv_batch* h, const IgvBlocks& blk, double* dst);
 void igv_launch_add_variable(igv_batch* h, int size, const double* cov_block_dev);
-void igv_launch_marginalize(igv_batch* h, int start, int size, int clone_slot);
+void igv_launch_marginalize(igv_batch* h, int start, int size, int clone_slot, int lm_slot = -1);
 void igv_launch_set_gnss_value(igv_batch* h, int gtype, const double* value_dev);
 void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const double* accel, const double* dt,
                           const double* Phi, const double* G);
@@ -285,9 +293,22 @@ void igv_launch_trk_change_anchor(igv_batch* h, unsigned long long old_cols, dou
 void igv_launch_trk_erase_invalid(igv_batch* h, double min_depth);
 void igv_launch_trk_dump(igv_batch* h, const igv_track_dump& d);
 
-void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
+void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, int k, const double* Hold, const double* Hnew,
                              const double* res, double noise_iso, const double* noise2_dev, const int* rows_dev,
                              double chi2_mult, int do_chi2, double prior_cov, int* accepted_dev);
+struct IgvLmInitLaunch {
+  int SW, anchor_slot, rows_max;
+  const double* pf; const double* obs; const unsigned char* mask;
+  double* Hx; double* Hf; double* res; int* count;
+};
+void igv_launch_lm_init_rows(igv_batch* h, const IgvLmInitLaunch& l);
+struct IgvLmUpdateLaunch {
+  const double* uv; const unsigned char* valid; double noise2;
+  double* H; int ldh; int ncols; double* res; double* gamma; int* n_acc;
+};
+void igv_launch_lm_update_rows(igv_batch* h, const IgvLmUpdateLaunch& l);
+void igv_launch_lm_anchor_H(igv_batch* h, int lm_slot, double* H);
+void igv_launch_set_lm_value(igv_batch* h, int lm_slot, const double* pf_dev);
 struct IgvGnssNewRowsLaunch {
   int S, gtype, adjust_yof;
   const double* unit; const double* res_pos; const double* res_vel; const double* sig_psr; const double* sig_dopp;

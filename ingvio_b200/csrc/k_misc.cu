@@ -12,92 +12,143 @@ using namespace igv;
 
 namespace {
 
-// Householder on H_new (rows x 1) applied to H_old (rows x n, col-major ld=rows) and res. Output in
-// the workspace: Hw (rows x n), rw (rows), rho (first entry of Q^T H_new).
-__global__ void k_delayed_prep(int rows, int n, const double* Hold, const double* Hnew, const double* res, double* Hw,
-                               double* rw, double* rho_out) {
+// k Householder reflectors (k = size of the new variable, 1 or 3) on H_new (rows x k, col-major, ld = rows), applied to
+// H_old (rows x n, col-major, ld = rows) and res. Outputs in the workspace: Hw (rows x n), rw (rows) and Rf, the k x k
+// upper triangle of Q^T H_new (row-major, stride 3).
+__global__ void k_delayed_prep(int rows, int n, int k, const double* Hold, const double* Hnew, const double* res, double* Hw,
+                               double* rw, double* Rf_out) {
   const int b = blockIdx.x;
   const double* Ho = Hold + (size_t)b * rows * n;
-  const double* hn = Hnew + (size_t)b * rows;
+  const double* hn = Hnew + (size_t)b * rows * k;
   const double* rr = res + (size_t)b * rows;
   double* Hb = Hw + (size_t)b * rows * n;
   double* rb = rw + (size_t)b * rows;
+  __shared__ double hf[3 * 128];   // working copy of H_new
   __shared__ double v[128];
-  __shared__ double s_tau, s_beta;
-  if (threadIdx.x == 0) {
-    double ss = 0.0;
-    for (int i = 1; i < rows; ++i) ss += hn[i] * hn[i];
-    const double alpha = hn[0];
-    double beta = alpha, tau = 0.0, scale = 0.0;
-    if (ss > 0.0) {
-      beta = -copysign(sqrt(alpha * alpha + ss), alpha);
-      tau = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
-    }
-    v[0] = 1.0;
-    for (int i = 1; i < rows; ++i) v[i] = hn[i] * scale;
-    s_tau = tau; s_beta = beta;
-    rho_out[b] = beta;
-  }
+  __shared__ double s_tau;
+  for (int t = threadIdx.x; t < rows * k; t += blockDim.x) hf[t] = hn[t];
+  for (int t = threadIdx.x; t < rows * n; t += blockDim.x) Hb[t] = Ho[t];
+  for (int t = threadIdx.x; t < rows; t += blockDim.x) rb[t] = rr[t];
+  if (threadIdx.x < 9) Rf_out[(size_t)b * 9 + threadIdx.x] = 0.0;
   __syncthreads();
-  for (int c = threadIdx.x; c <= n; c += blockDim.x) {
-    const double* src = (c < n) ? Ho + (size_t)c * rows : rr;
-    double* dst = (c < n) ? Hb + (size_t)c * rows : rb;
-    double w = 0.0;
-    for (int i = 0; i < rows; ++i) w += v[i] * src[i];
-    w *= s_tau;
-    for (int i = 0; i < rows; ++i) dst[i] = src[i] - w * v[i];
+  for (int j = 0; j < k; ++j) {
+    if (threadIdx.x == 0) {
+      double* col = hf + j * rows;
+      double ss = 0.0;
+      for (int i = j + 1; i < rows; ++i) ss += col[i] * col[i];
+      const double alpha = col[j];
+      double beta = alpha, tau = 0.0, scale = 0.0;
+      if (ss > 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      for (int i = 0; i < j; ++i) v[i] = 0.0;
+      v[j] = 1.0;
+      for (int i = j + 1; i < rows; ++i) v[i] = col[i] * scale;
+      s_tau = tau;
+      Rf_out[(size_t)b * 9 + 3 * j + j] = beta;
+      for (int c = j + 1; c < k; ++c) {          // the remaining columns of H_new
+        double* cc = hf + c * rows;
+        double w = 0.0;
+        for (int i = j; i < rows; ++i) w += v[i] * cc[i];
+        w *= tau;
+        for (int i = j; i < rows; ++i) cc[i] -= w * v[i];
+        Rf_out[(size_t)b * 9 + 3 * j + c] = cc[j];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c <= n; c += blockDim.x) {
+      double* x = (c < n) ? Hb + (size_t)c * rows : rb;
+      double w = 0.0;
+      for (int i = j; i < rows; ++i) w += v[i] * x[i];
+      w *= s_tau;
+      for (int i = j; i < rows; ++i) x[i] -= w * v[i];
+    }
+    __syncthreads();
   }
 }
 
-// Decide + augment (StateManager.cpp:617-623 + :462-541) for a 1-dim new variable appended at N.
-__global__ void k_delayed_augment(double* P, int ld, int N, IgvBlocks blk, int rows, const double* Hw, const double* rw,
-                                  const double* rho, const double* gamma, double noise2_all, double thr_all, int do_chi2,
-                                  double prior_cov, int* accepted, double* X, int xsize, int gslot,
-                                  const double* noise2_dev, const int* rows_dev, const double* chi2_095, double chi2_mult) {
+// Decide + augment (StateManager.cpp:617-623 + :462-541) for a k-dim new variable appended at N:
+//   P[:, new] = -(P H_x^T) H_f^-T,  P[new, new] = H_f^-1 (H_x P_s H_x^T + sigma^2 I) H_f^-T   with H_f = Rf (upper triangular).
+__global__ void k_delayed_augment(double* P, int ld, int N, IgvBlocks blk, int rows, int k, const double* Hw, const double* Rf,
+                                  const double* gamma, double noise2_all, double thr_all, int do_chi2,
+                                  double prior_cov, int* accepted, const double* noise2_dev, const int* rows_dev,
+                                  const double* chi2_095, double chi2_mult) {
+  extern __shared__ double sPH[];                       // N x k, column a at sPH + a * N
   const int b = blockIdx.x;
   double* Pb = P + (size_t)b * ld * ld;
-  const double* Hb = Hw + (size_t)b * rows * blk.n;  // row 0 = Hxinit
+  const double* Hb = Hw + (size_t)b * rows * blk.n;    // rows 0..k-1 = Hxinit
   __shared__ int cols[6 * IGV_MAX_BLOCKS];
-  __shared__ double sPH[512];
   __shared__ int s_acc;
+  __shared__ double s_Rinv[9], s_S[9];
   if (threadIdx.x == 0) {
     int off = 0;
-    for (int q = 0; q < blk.n_blocks; ++q) for (int k = 0; k < blk.size[q]; ++k) cols[off++] = blk.idx[q] + k;
-    // per-sequence row count (rows beyond it are zero padding): dof = res.rows() of THIS sequence; fewer than two rows:
-    // "H_new rows should be larger than H_new cols" -> not added (StateManager.cpp:574-578)
+    for (int q = 0; q < blk.n_blocks; ++q) for (int c = 0; c < blk.size[q]; ++c) cols[off++] = blk.idx[q] + c;
+    // per-sequence row count (rows beyond it are zero padding): dof = res.rows() of THIS sequence; no more rows than
+    // columns: "H_new rows should be larger than H_new cols" -> not added (StateManager.cpp:574-578)
     const int rows_b = rows_dev ? rows_dev[b] : rows;
     const double thr = rows_dev ? ((rows_b >= 1 && rows_b <= 128) ? chi2_mult * chi2_095[rows_b - 1] : 0.0) : thr_all;
-    const bool rej = rows_b < 2 || (do_chi2 && rows > 1 && !(gamma[b] <= thr));   // reject if chi2 > mult*quantile
+    bool rej = rows_b <= k || (do_chi2 && rows > k && !(gamma[b] <= thr));   // reject if chi2 > mult * quantile
+    const double* R = Rf + (size_t)b * 9;
+    for (int a = 0; a < k; ++a) if (!(fabs(R[3 * a + a]) > 0.0)) rej = true;   // H_f not invertible
+    if (!rej) {   // inverse of the upper triangle by back substitution
+      for (int e = 0; e < 9; ++e) s_Rinv[e] = 0.0;
+      for (int c = 0; c < k; ++c) {
+        s_Rinv[3 * c + c] = 1.0 / R[3 * c + c];
+        for (int a = c - 1; a >= 0; --a) {
+          double acc = 0.0;
+          for (int d = a + 1; d <= c; ++d) acc += R[3 * a + d] * s_Rinv[3 * d + c];
+          s_Rinv[3 * a + c] = -acc / R[3 * a + a];
+        }
+      }
+    }
     s_acc = rej ? 0 : 1;
     accepted[b] = s_acc;
   }
   __syncthreads();
   const int n = blk.n;
   const double noise2 = noise2_dev ? noise2_dev[b] : noise2_all;
-  const double ir = s_acc ? 1.0 / rho[b] : 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  for (int t = threadIdx.x; t < N * k; t += blockDim.x) {
+    const int i = t % N, a = t / N;
     double acc = 0.0;
-    for (int c = 0; c < n; ++c) acc = fma(Pb[i + (size_t)cols[c] * ld], Hb[(size_t)c * rows], acc);
-    sPH[i] = acc;   // (P H^T)[i]
+    for (int c = 0; c < n; ++c) acc = fma(Pb[i + (size_t)cols[c] * ld], Hb[a + (size_t)c * rows], acc);
+    sPH[t] = acc;   // (P H_x^T)[i][a]
   }
   __syncthreads();
   if (s_acc) {
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      const double val = -sPH[i] * ir;
-      Pb[i + (size_t)N * ld] = val;
-      Pb[N + (size_t)i * ld] = val;
+    if (threadIdx.x < k * k) {
+      const int a = threadIdx.x / k, d = threadIdx.x % k;
+      double acc = (a == d) ? noise2 : 0.0;
+      for (int c = 0; c < n; ++c) acc = fma(Hb[a + (size_t)c * rows], sPH[cols[c] + d * N], acc);
+      s_S[3 * a + d] = acc;
     }
-    if (threadIdx.x == 0) {
-      double s = noise2;
-      for (int c = 0; c < n; ++c) s = fma(Hb[(size_t)c * rows], sPH[cols[c]], s);
-      Pb[N + (size_t)N * ld] = s * ir * ir;
+    for (int t = threadIdx.x; t < N * k; t += blockDim.x) {
+      const int i = t % N, a = t / N;
+      double val = 0.0;
+      for (int c = 0; c < k; ++c) val = fma(sPH[i + c * N], s_Rinv[3 * a + c], val);   // (P H^T R^-T)[i][a]
+      Pb[i + (size_t)(N + a) * ld] = -val;
+      Pb[(N + a) + (size_t)i * ld] = -val;
+    }
+    __syncthreads();
+    if (threadIdx.x < k * k) {
+      const int a = threadIdx.x / k, d = threadIdx.x % k;
+      double acc = 0.0;
+      for (int c = 0; c < k; ++c)
+        for (int e = 0; e < k; ++e) acc += s_Rinv[3 * a + c] * 0.5 * (s_S[3 * c + e] + s_S[3 * e + c]) * s_Rinv[3 * d + e];
+      Pb[(N + a) + (size_t)(N + d) * ld] = acc;
     }
   } else {
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { Pb[i + (size_t)N * ld] = 0.0; Pb[N + (size_t)i * ld] = 0.0; }
-    if (threadIdx.x == 0) Pb[N + (size_t)N * ld] = prior_cov;
+    for (int t = threadIdx.x; t < N * k; t += blockDim.x) {
+      const int i = t % N, a = t / N;
+      Pb[i + (size_t)(N + a) * ld] = 0.0;
+      Pb[(N + a) + (size_t)i * ld] = 0.0;
+    }
+    if (threadIdx.x < k * k) {
+      const int a = threadIdx.x / k, d = threadIdx.x % k;
+      Pb[(N + a) + (size_t)(N + d) * ld] = (a == d) ? prior_cov : 0.0;
+    }
   }
-  (void)rw; (void)X; (void)xsize; (void)gslot;
 }
 
 __global__ void k_replace_var_linear(double* P, int ld, int N, int t0, int ts, IgvBlocks blk, const double* H) {
@@ -142,22 +193,22 @@ __global__ void k_replace_var_linear(double* P, int ld, int N, int t0, int ts, I
 
 }  // namespace
 
-void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const double* Hold, const double* Hnew,
+void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, int k, const double* Hold, const double* Hnew,
                              const double* res, double noise_iso, const double* noise2_dev, const int* rows_dev,
                              double chi2_mult, int do_chi2, double prior_cov, int* accepted_dev) {
   igv_commit_copies(h);
-  // workspace: Hw (rows x n) | rw (rows) | rho   -- carved from Dws (B x (128*18+2) doubles, n <= 16)
+  // workspace: Hw (rows x n) | rw (rows) | Rf (9)  -- carved from Dws (B x dws_stride doubles)
   double* Hw = h->Dws;
   double* rw = Hw + (size_t)h->B * rows * blk.n;
-  double* rho = rw + (size_t)h->B * rows;
+  double* Rf = rw + (size_t)h->B * rows;
   double* gam = h->gam_ws;
-  k_delayed_prep<<<h->B, 64, 0, h->stream>>>(rows, blk.n, Hold, Hnew, res, Hw, rw, rho);
+  k_delayed_prep<<<h->B, 64, 0, h->stream>>>(rows, blk.n, k, Hold, Hnew, res, Hw, rw, Rf);
   h->launches++;
-  if (rows > 1) {  // chi^2 of the remaining rows against the prior (StateManager.cpp:604-611)
+  if (rows > k) {  // chi^2 of the remaining rows against the prior (StateManager.cpp:604-611)
     IgvEkfLaunch e{};
-    e.blk = blk; e.rows = rows - 1;
-    e.H = Hw + 1; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
-    e.res = rw + 1; e.strideRes = rows; e.res_inc = 1;
+    e.blk = blk; e.rows = rows - k;
+    e.H = Hw + k; e.strideH = (long)rows * blk.n; e.h_ld = rows; e.h_rowmajor = 0;
+    e.res = rw + k; e.strideRes = rows; e.res_inc = 1;
     e.R = noise2_dev; e.strideR = noise2_dev ? 1 : 0; e.r_kind = IGV_R_ISO; e.r_iso_value = noise_iso * noise_iso;
     e.gamma_only = 1; e.gamma_out = gam; e.apply_boxplus = 0;
     igv_launch_ekf(h, e);
@@ -165,9 +216,10 @@ void igv_launch_delayed_init(igv_batch* h, const IgvBlocks& blk, int rows, const
   // the reference hard-codes the 0.95 quantile at dof = res.rows() here, whatever UpdateBase::_thres the updaters
   // were built with (StateManager.cpp:613-617)
   const double thr = (rows >= 1) ? chi2_mult * igv_chi2_quantile(0.95, rows) : INFINITY;
-  k_delayed_augment<<<h->B, 128, 0, h->stream>>>(h->Pc(), h->ld, h->N, blk, rows, Hw, rw, rho, gam,
-                                                 noise_iso * noise_iso, thr, do_chi2, prior_cov, accepted_dev,
-                                                 h->Xc(), h->xsize, -1, noise2_dev, rows_dev, h->chi2_095, chi2_mult);
+  const size_t smem = sizeof(double) * (size_t)h->N * k;
+  k_delayed_augment<<<h->B, 128, smem, h->stream>>>(h->Pc(), h->ld, h->N, blk, rows, k, Hw, Rf, gam,
+                                                    noise_iso * noise_iso, thr, do_chi2, prior_cov, accepted_dev,
+                                                    noise2_dev, rows_dev, h->chi2_095, chi2_mult);
   h->launches++;
 }
 

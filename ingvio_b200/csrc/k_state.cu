@@ -73,7 +73,7 @@ __global__ void k_add_variable(double* P, int ld, int N, int size, const double*
 
 // out-of-place deletion of rows/cols [s, s+sz) (StateManager.cpp:167-177) + mean compaction
 __global__ void k_marginalize(const double* Pin, double* Pout, int ld, int N, int s, int sz, const double* Xin,
-                              double* Xout, int xsize, int clone_slot, int n_clones) {
+                              double* Xout, int xsize, int clone_slot, int n_clones, int lm_slot, int lm_off, int n_lm) {
   const int b = blockIdx.y;
   const double* A = Pin + (size_t)b * ld * ld;
   double* O = Pout + (size_t)b * ld * ld;
@@ -88,9 +88,13 @@ __global__ void k_marginalize(const double* Pin, double* Pout, int ld, int N, in
     double* xo = Xout + (size_t)b * xsize;
     for (int t = threadIdx.x; t < xsize; t += blockDim.x) {
       double val = xi[t];
-      if (clone_slot >= 0 && t >= IGV_X_CORE + 12 * clone_slot) {
+      if (clone_slot >= 0 && t >= IGV_X_CORE + 12 * clone_slot && (lm_off <= 0 || t < lm_off)) {
         const int src = t + 12;
         val = (src < IGV_X_CORE + 12 * n_clones && src < xsize) ? xi[src] : 0.0;
+      }
+      if (lm_slot >= 0 && t >= lm_off + 3 * lm_slot) {   // landmark values close the gap
+        const int src = t + 3;
+        val = (src < lm_off + 3 * n_lm && src < xsize) ? xi[src] : 0.0;
       }
       xo[t] = val;
     }
@@ -197,13 +201,14 @@ void igv_launch_add_variable(igv_batch* h, int size, const double* cov_block_dev
   k_add_variable<<<h->B, 128, 0, h->stream>>>(h->Pc(), h->ld, h->N, size, cov_block_dev);
   h->launches++;
 }
-void igv_launch_marginalize(igv_batch* h, int start, int size, int clone_slot) {
+void igv_launch_marginalize(igv_batch* h, int start, int size, int clone_slot, int lm_slot) {
   IgvProfScope prof_scope_(h, IGV_K_MARG);
   const int Nn = h->N - size;
   dim3 grid(max(1, min(32, (Nn * Nn + 255) / 256)), h->B);
   IgvLayout L = h->layout();
   k_marginalize<<<grid, 256, 0, h->stream>>>(h->P[h->cur], h->P[h->cur ^ 1], h->ld, h->N, start, size,
-                                             h->X[h->xcur], h->X[h->xcur ^ 1], h->xsize, clone_slot, L.n_clones);
+                                             h->X[h->xcur], h->X[h->xcur ^ 1], h->xsize, clone_slot, L.n_clones,
+                                             lm_slot, L.lm_off, L.n_lm);
   h->cur ^= 1;
   h->xcur ^= 1;
   h->launches++;

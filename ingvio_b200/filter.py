@@ -55,14 +55,15 @@ class BatchFilter:
 
     def __init__(self, batch, max_clones, max_feats, max_sats, stereo=False, device=0, stream=None,
                  max_dim=None, noise=None, gravity=(0.0, 0.0, -9.8), T_cl2cr=None, chi2_max_dof=150,
-                 chi2_thres=0.95):
+                 chi2_thres=0.95, max_landmarks=0):
         self.lib = capi.load()
         self.B = batch
         self.stereo = bool(stereo)
         self.rho = 4 if stereo else 2
-        max_dim = max_dim or (21 + 6 + 6 * max_clones)
+        max_dim = max_dim or (21 + 6 + 6 * max_clones + 3 * max_landmarks)
         cfg = capi.igv_config(batch, max_dim, max_clones, max_feats, max_sats, int(self.stereo), device,
-                              C.c_void_p(stream) if stream else None)
+                              C.c_void_p(stream) if stream else None, int(max_landmarks))
+        self.max_landmarks = int(max_landmarks)
         self.h = C.c_void_p()
         st = self.lib.igv_create(C.byref(cfg), C.byref(self.h))
         if st != capi.IGV_OK:
@@ -426,6 +427,58 @@ class BatchFilter:
             args.accepted_out = C.c_void_p(acc.ctypes.data)
         self._ck(self.lib.igv_gnss_add_new_tracked_sys(self.h, C.byref(args)))
         return None if acc is None else acc.astype(bool)
+
+    # ---- SLAM landmarks in the state (LandmarkUpdate, mono) -------------------------------------------
+    def num_landmarks(self):
+        return int(self.lib.igv_num_landmarks(self.h))
+
+    def landmark_idx(self, lm_slot):
+        return int(self.lib.igv_landmark_idx(self.h, int(lm_slot)))
+
+    def landmark_anchor(self, lm_slot):
+        return int(self.lib.igv_landmark_anchor(self.h, int(lm_slot)))
+
+    def landmark_values(self):
+        """World positions (B, L, 3) of the landmarks in the state, in slot order."""
+        x = self.get_state()
+        off = 39 + 12 * self.max_clones
+        L = self.num_landmarks()
+        return x[:, off:off + 3 * L].reshape(self.B, L, 3)
+
+    def landmark_init(self, pf_w, anchor_slot, obs, obs_mask, noise, chi2_mult=0.95, prior_cov_if_rejected=1.0):
+        """LandmarkUpdate::initNewLandmarkMono for one track (delayed initialisation of a 3-dim anchored variable)."""
+        a = [_Arg(pf_w, np.float64), _Arg(obs, np.float64), _Arg(obs_mask, np.uint8)]
+        mode = self._set_mode(a)
+        args = capi.igv_lm_init_args()
+        args.obs_slots, args.anchor_slot = int(a[2].keep.shape[1]), int(anchor_slot)
+        args.pf_w, args.obs, args.obs_mask = [x.ptr for x in a]
+        args.noise, args.chi2_mult, args.prior_cov_if_rejected = float(noise), float(chi2_mult), float(prior_cov_if_rejected)
+        acc = None
+        if mode == capi.IGV_PTR_HOST:
+            acc = np.zeros(self.B, dtype=np.int32)
+            args.accepted_out = C.c_void_p(acc.ctypes.data)
+        self._ck(self.lib.igv_landmark_init(self.h, C.byref(args)))
+        return None if acc is None else acc.astype(bool)
+
+    def landmark_update(self, uv, valid, noise):
+        """LandmarkUpdate::updateLandmarkMono; returns dict(accepted (B,), gamma (B, L)) in host mode."""
+        a = [_Arg(uv, np.float64), _Arg(valid, np.uint8)]
+        mode = self._set_mode(a)
+        args = capi.igv_lm_update_args()
+        args.uv, args.valid, args.noise = a[0].ptr, a[1].ptr, float(noise)
+        out = None
+        if mode == capi.IGV_PTR_HOST:
+            out = dict(accepted=np.zeros(self.B, dtype=np.int32), gamma=np.zeros((self.B, max(1, self.num_landmarks()))))
+            args.n_accepted_out = C.c_void_p(out["accepted"].ctypes.data)
+            args.gamma_out = C.c_void_p(out["gamma"].ctypes.data)
+        self._ck(self.lib.igv_landmark_update(self.h, C.byref(args)))
+        return out
+
+    def landmark_change_anchor(self, lm_slot, new_clone_slot):
+        self._ck(self.lib.igv_landmark_change_anchor(self.h, int(lm_slot), int(new_clone_slot)))
+
+    def landmark_marginalize(self, lm_slot):
+        self._ck(self.lib.igv_landmark_marginalize(self.h, int(lm_slot)))
 
     def sat_states(self, eph, t_obs_rel, psr, sys, out=None):
         """gnss_comm::sat_states: ephemeris records (B,S,24) + observation time relative to toe + L1 pseudo-range ->

@@ -49,7 +49,7 @@ def cov_diag21(fp):
                     [sp.init_cov_ba] * 3 + [sp.init_cov_ext_rot] * 3 + [sp.init_cov_ext_pos] * 3) ** 2.0
 
 
-def make_gpu(wl, stream, fp, with_gnss=True, max_feats=None, max_clones=None, max_sats=None, device=0):
+def make_gpu(wl, stream, fp, with_gnss=True, max_feats=None, max_clones=None, max_sats=None, device=0, max_landmarks=0):
     from ingvio_b200.filter import BatchFilter
     sp = o.StateParams(fp)
     B = stream.B
@@ -57,7 +57,7 @@ def make_gpu(wl, stream, fp, with_gnss=True, max_feats=None, max_clones=None, ma
                     noise=dict(noise_g=sp.noise_g, noise_a=sp.noise_a, noise_bg=sp.noise_bg, noise_ba=sp.noise_ba,
                                noise_clockbias=sp.noise_clockbias, noise_cb_rw=sp.noise_cb_rw),
                     gravity=(0.0, 0.0, -fp.gravity_norm), T_cl2cr=(fp.T_cl2cr_R, fp.T_cl2cr_p),
-                    chi2_max_dof=max(fp.chi2_max_dof, 160), chi2_thres=fp.chi2_thres)
+                    chi2_max_dof=max(fp.chi2_max_dof, 160), chi2_thres=fp.chi2_thres, max_landmarks=max_landmarks)
     ini = stream.initial_state()
     g.init_state_and_cov(ini["R"].reshape(B, 9), ini["p"], ini["v"], ini["bg"], ini["ba"],
                          np.tile(fp.T_cl2i_R.reshape(1, 9), (B, 1)), np.tile(fp.T_cl2i_p, (B, 1)), cov_diag21(fp))
