@@ -98,6 +98,15 @@ const char* igv_last_error(const igv_batch* h);
 igv_status igv_set_pointer_mode(igv_batch* h, int mode);
 igv_status igv_synchronize(igv_batch* h);
 igv_status igv_set_compression(igv_batch* h, int kind);   /* IGV_COMPRESS_* (default AUTO) */
+/* Arithmetic mode of the visual update (BASELINE configs[4], "FP32 vs FP64").
+ *   IGV_PREC_FP64       everything in double (the parity path, default);
+ *   IGV_PREC_FP32_STACK the projected per-track blocks [H | r] are STORED in single precision (half the HBM traffic of
+ *                       the stack: the bound of wide windows / stereo / small batches, where the stack is materialised);
+ *                       Jacobians, null-space projection and the chi^2 gate are still evaluated in double (no gate
+ *                       decision can flip), the Gram matrix is accumulated in double and the whole EKF update is
+ *                       double. Measured tolerance: tests/test_gpu_precision.py, profiles/r02_precision_sweep.md. */
+enum { IGV_PREC_FP64 = 0, IGV_PREC_FP32_STACK = 1 };
+igv_status igv_set_precision(igv_batch* h, int mode);
 /* which kernels the last igv_msckf_update used: 0 Householder QR of the materialised stack, 1 Gram matrix of the
  * materialised stack, 2 Gram matrix accumulated inside the per-track kernel (no stack in HBM); -1 before any update */
 int igv_last_visual_path(const igv_batch* h);

@@ -382,6 +382,12 @@ igv_status igv_set_compression(igv_batch* h, int kind) {
   return IGV_OK;
 }
 
+igv_status igv_set_precision(igv_batch* h, int mode) {
+  if (!h || (mode != IGV_PREC_FP64 && mode != IGV_PREC_FP32_STACK)) return IGV_ERR_INVALID;
+  h->stack_f32 = (mode == IGV_PREC_FP32_STACK) ? 1 : 0;
+  return IGV_OK;
+}
+
 int igv_last_visual_path(const igv_batch* h) { return h ? h->last_visual_path : -1; }
 
 igv_status igv_synchronize(igv_batch* h) {

@@ -38,6 +38,7 @@ struct GramArgs {
   const double* Hs; int F; int qmax; int ldo; const int* f_rows; int max_valid;
   int n;                      // columns of H; the stack has n + 1 columns
   int F_alloc; size_t hs_seq_stride;
+  int hs_f32;                    // the stack holds floats (IGV_PREC_FP32_STACK)
   double* G; long g_seq_stride; int n1p;     // partial Gram matrices [b][part][n1p x n1p], row-major
   int lds;                    // shared-memory row stride of a chunk
   int nsb;                    // 24-column super-blocks per side
@@ -115,8 +116,14 @@ __global__ void __launch_bounds__(SPW == 1 ? 256 : 288) k_gram_accum(GramArgs a)
           const int mid = (lo + hi) >> 1;
           if (rowstart[mid] <= v) lo = mid; else hi = mid;
         }
-        const double* srow = src + ((size_t)(f0 + lo) * a.qmax + (v - rowstart[lo])) * a.ldo;
-        for (int c = lane; c < n1; c += 32) trow[c] = __ldg(srow + c);
+        const size_t off = ((size_t)(f0 + lo) * a.qmax + (v - rowstart[lo])) * a.ldo;
+        if (a.hs_f32) {
+          const float* srow = reinterpret_cast<const float*>(src) + off;
+          for (int c = lane; c < n1; c += 32) trow[c] = (double)__ldg(srow + c);
+        } else {
+          const double* srow = src + off;
+          for (int c = lane; c < n1; c += 32) trow[c] = __ldg(srow + c);
+        }
       } else {
         for (int c = lane; c < n1; c += 32) trow[c] = 0.0;
       }
@@ -411,7 +418,7 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
   const int n = 6 * L.n_clones;
   GramArgs a;
   a.Hs = h->Hs; a.F = F; a.qmax = h->qmax; a.ldo = n + 1; a.f_rows = h->f_rows; a.max_valid = max_valid;
-  a.n = n; a.F_alloc = h->cfg.max_feats;
+  a.n = n; a.F_alloc = h->cfg.max_feats; a.hs_f32 = h->stack_f32;
   a.hs_seq_stride = (size_t)h->cfg.max_feats * h->qmax * (h->ncols_max + 1);
   a.nsb = (n + 1 + 23) / 24;
   a.n1p = 24 * a.nsb + 8;
@@ -425,7 +432,7 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
   const int nt = (n + 1 + 7) / 8;
   const int frange = (F + split - 1) / split;
   const int gram_cfg = h->knobs.gram_cfg;            // test knob: 1 forces the super-block kernel
-  const bool wide = gram_cfg == 1 || nt > 9;
+  const bool wide = gram_cfg == 1 || nt > 9 || h->stack_f32;   // the stream kernel copies doubles asynchronously
   if (!wide) {
     if (nt <= 4) launch_stream_gram<4, 6>(a, split, h->B, frange, h->stream);
     else if (nt <= 6) launch_stream_gram<6, 4>(a, split, h->B, frange, h->stream);

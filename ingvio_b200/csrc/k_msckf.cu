@@ -54,6 +54,7 @@ struct FeatArgs {
   double* G; long g_seq_stride; int n1p;   // out: upper triangle of [H r]^T [H r], row stride n1p
   int* n_acc; int max_valid;
   int const_sizes;                   // host: the launch matches the compile-time layout of the NCL > 0 instances
+  int hs_f32;                        // IGV_PREC_FP32_STACK: the projected block is stored as float (same element strides)
 };
 
 // per-warp scratch layout (doubles): A[M][3] B[M][3] V[M][3] Am[M][3] E[M][3] r[M] qr[M] S[(M+1)][ldm] maps
@@ -703,7 +704,11 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
             for (int tt = 0; tt < RHO; ++tt) if (tt == t) v += ownv[gq][tt];
             if (acomp[gq] >= 0 && not_anchor_row) v -= sB[i * 3 + acomp[gq]];
             if (isres[gq]) v = qri;
-            if (live[gq]) orow[32 * gq] = v;
+            if (live[gq]) {
+              if (a.hs_f32)   // float elements with the SAME element strides, counted from the sequence's base
+                reinterpret_cast<float*>(a.Hs + (size_t)b * a.hs_seq_stride)[((size_t)f * a.qmax + (i - 3)) * a.ldo + j0 + lane + 32 * gq] = (float)v;
+              else orow[32 * gq] = v;
+            }
           }
         }
       }
@@ -873,6 +878,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   a.G = h->Gws; a.g_seq_stride = (long)h->qr_split_cap * h->gram_n1p * h->gram_n1p; a.n1p = 24 * ((n + 1 + 23) / 24) + 8;
   a.n_acc = h->n_acc; a.max_valid = l.max_valid;
   a.const_sizes = (h->knobs.feat_const != 0) ? 1 : 0;
+  a.hs_f32 = h->stack_f32;
   const bool ps = ((size_t)n * n * sizeof(double) <= 72 * 1024);
   const size_t fixed = 12 * IGV_MAX_CLONES + (ps ? (size_t)n * n : 0);
   // ---- fused Gram accumulation: one CTA of up to 16 warps per sequence -----------------------------------------
@@ -880,7 +886,8 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   {
     const int ef = h->knobs.fuse;                // test knob: 1 forces the fused kernel, 0 forbids it
     const int qc = h->knobs.qr_cfg;              // a forced compression kernel needs the materialised stack
-    const bool allowed = ps && a.nt <= 9 && ncl <= 32 && l.F >= 1 && h->compress != IGV_COMPRESS_HOUSEHOLDER && qc == 0;
+    const bool allowed = ps && a.nt <= 9 && ncl <= 32 && l.F >= 1 && h->compress != IGV_COMPRESS_HOUSEHOLDER && qc == 0 &&
+                         !h->stack_f32;   // the FP32-stack mode is about the materialised stack
     if (allowed && (ef == 1 || (ef != 0 && h->B >= 296))) {
       const int ntt = a.nt * (a.nt + 1) / 2;
       const int ssz = max(a.ssz, 3 * a.ldz + ncl * 27);

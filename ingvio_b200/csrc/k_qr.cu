@@ -534,7 +534,7 @@ void igv_launch_qr_compress(igv_batch* h, int F, int max_valid) {
   {
     // IGV_QR_CFG (test knob) >= 1 forces one of the Householder kernels, 30 forces the Gram path
     const int cfg = h->knobs.qr_cfg;
-    const bool forced_hh = (cfg > 0 && cfg != 30) || h->compress == IGV_COMPRESS_HOUSEHOLDER;
+    const bool forced_hh = ((cfg > 0 && cfg != 30) || h->compress == IGV_COMPRESS_HOUSEHOLDER) && !h->stack_f32;
     if (!forced_hh && igv_gram_supported(n)) {
       h->last_visual_path = 1;
       igv_launch_gram_compress(h, F, max_valid, split);

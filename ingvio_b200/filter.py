@@ -114,6 +114,10 @@ class BatchFilter:
         """capi.COMPRESS_AUTO | COMPRESS_HOUSEHOLDER | COMPRESS_GRAM: how msckf_update forms [R | Q^T r]."""
         self._ck(self.lib.igv_set_compression(self.h, int(kind)))
 
+    def set_precision(self, mode):
+        """capi.PREC_FP64 (default) | capi.PREC_FP32_STACK: projected per-track blocks stored in single precision."""
+        self._ck(self.lib.igv_set_precision(self.h, int(mode)))
+
     def last_visual_path(self):
         """0 Householder QR, 1 Gram of the materialised stack, 2 Gram fused into the per-track kernel."""
         return int(self.lib.igv_last_visual_path(self.h))

@@ -23,6 +23,7 @@ void emu_gnss_residuals(int B, int S, const double* X, int xsize, const int* idx
   a.sat_pos = sat_pos; a.sat_vel = sat_vel; a.sat_clk = sat_clk; a.obs = obs; a.obs_std = obs_std; a.ttx = ttx; a.sys = sys; a.T = T;
   a.iono = iono; a.psr_amp = psr_amp; a.dopp_amp = dopp_amp;
   a.unit = unit; a.res_pos = res_pos; a.res_vel = res_vel; a.sig_psr = sig_psr; a.sig_dopp = sig_dopp; a.azel = azel; a.atmos = atmos;
+  a.clock_init = nullptr;
   const long n = (long)B * S;
   emul::launch((unsigned)((n + 127) / 128), 128, 0, [&] { k_gnss_residuals(a); });
 }
