@@ -244,3 +244,41 @@ def test_gnss_add_new_tracked_sys(adjust_yof):
                 SM.add_gnss_variable(f.state, gt, spp[gt], 1.0)
         assert_state_close(g, orc, wl.sw, what=f"add new sys {gt}")
     assert not acc is None
+
+
+@pytest.mark.parametrize("wname", ["c2", "c3", "c5"])
+def test_triangulate_group_kernel_vs_thread_kernel(wname, monkeypatch):
+    """k_triangulate_grp (a group of lanes per track, the default) against k_triangulate (one thread per track,
+    IGV_TRI_CFG=1) at the BASELINE window sizes -- 16-lane groups at c2 (11 views), 32-lane groups at c3 (22 stereo
+    views) and at c5 (30 views): identical accept / reject decisions and the same positions to 1e-9 m, including ragged
+    tracks, tracks with too few views and garbage tracks that fail the depth gates; the thread kernel itself is held to
+    the oracle by test_gpu_parity.py::test_triangulate_matches_oracle."""
+    wl = WORKLOADS[wname]
+    fp = filter_params(wl)
+    B = 2
+    st = SyntheticStream(wl, B)
+    frames = []
+    for _ in range(wl.sw + 1):
+        frames.append(st.next_frame())
+    fr = frames[-1]
+    rng = np.random.default_rng(9)
+    mask = fr.obs_mask.copy()
+    mask[:, 0::7, :3] = 0                    # ragged
+    mask[:, 1, :] = 0
+    mask[:, 1, :2] = 1                       # too few views
+    obs = fr.obs.copy()
+    obs[:, 2::11] += rng.normal(0, 0.3, obs[:, 2::11].shape)   # garbage tracks
+    res = {}
+    for cfg in ("0", "1"):
+        monkeypatch.setenv("IGV_TRI_CFG", cfg)
+        g = make_gpu(wl, SyntheticStream(wl, B), fp)
+        s2 = SyntheticStream(wl, B)
+        for _ in range(wl.sw + 1):
+            gstep(g, s2.next_frame(), fp)
+        g.augment_sliding_window_pose() if g.num_clones() < wl.sw else None
+        res[cfg] = g.triangulate(obs, mask, fr.anchor_slot, trans_thres=0.1, conv_precision=5e-7, max_depth=60.0)
+        g.close()
+    (pf0, ok0), (pf1, ok1) = res["0"], res["1"]
+    assert np.array_equal(ok0, ok1)
+    assert ok0.sum() > 0.5 * ok0.size and not ok0[:, 1].any()
+    assert np.abs(pf0 - pf1)[ok0].max() <= 1e-9
