@@ -89,6 +89,31 @@ def run_step(g, t, meta):
         g.gnss_update(t["unit"], t["res_pos"], t["res_vel"], t["sig_psr"], t["sig_dopp"], t["sys"], t["Renu"], 0, 0, 1)
 
 
+class FixedFrame:
+    """Device-resident argument buffers at FIXED addresses, refilled every frame, and the frame handed to the library as
+    ONE call (igv_frame_step): from the third frame of a steady window the kernel sequence is a CUDA-graph replay."""
+
+    def __init__(self, torch, dev, example):
+        self.buf = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in example.items()}
+
+    def load(self, src):
+        for k, v in src.items():
+            self.buf[k].copy_(v, non_blocking=True)
+
+    def step(self, g, meta):
+        from ingvio_b200 import capi
+        b = self.buf
+        vis = None
+        if meta["visual"]:
+            vis = dict(mode=capi.VIS_ALL_OBS, pf_w=b["pf"], anchor_slot=b["anchor"], obs=b["obs"], obs_mask=b["mask"],
+                       chi2_dof=b["dof"], noise=VISUAL_NOISE, max_valid=meta["max_valid"])
+        gn = None
+        if meta["gnss"]:
+            gn = dict(unit=b["unit"], res_pos=b["res_pos"], res_vel=b["res_vel"], sigma_psr=b["sig_psr"], sigma_dopp=b["sig_dopp"],
+                      sys=b["sys"], R_enu2ecef=b["Renu"], is_adjust_yof=0, chi2_test=0, strong_reject=1)
+        g.frame_step(b["gyro"], b["accel"], b["dt"], visual=vis, marg_slots=sorted(meta["marg"], reverse=True), gnss=gn)
+
+
 def make_filter(wl, B, stream_obj, torch_stream, device):
     from ingvio_b200.filter import BatchFilter
     g = BatchFilter(B, wl.sw, max(wl.feats, 1), max(wl.sats, 1), stereo=wl.stereo, device=device,
@@ -370,9 +395,12 @@ def c4_sharded(args, wl_name, world, rank, local, dev, ts, dist, torch, total=64
         host = torch.zeros((total, 14), dtype=torch.float64).pin_memory()
         checks = {"sum": 0.0}
 
+        ff = FixedFrame(torch, dev, pin[prefill][0])
+
         def frame(a, m):
-            run_step(g, a, m)                       # host-pointer mode: H2D inside the calls
-            g.get_state_async(xdev)                 # device-pointer mode for the read-out: stays in HBM
+            ff.load(a)                              # H2D of this frame's inputs from pinned memory, on the filter's stream
+            ff.step(g, m)                           # ONE C-ABI call; a CUDA-graph replay in the steady state
+            g.get_state_async(xdev)                 # the read-out stays in HBM
             g.cov_trace_async(tdev)
             ro = torch.cat([xdev[:, 0:12], tdev[:, None], torch.zeros((Bl, 1), dtype=torch.float64, device=dev)], 1)
             full = gather_readouts_device(ro, total, dist if world > 1 else None)
@@ -408,6 +436,7 @@ def c4_sharded(args, wl_name, world, rank, local, dev, ts, dist, torch, total=64
         tr = g.cov_trace()
         assert np.all(np.isfinite(tr)) and np.all(tr > 0), "c4: filter diverged"
         h2d = sum(v.numel() * v.element_size() for v in pin[prefill][0].values())
+        g_replays = g.graph_replays
         g.close()
     return {"workload": f"c4: {total} independent c2 sequences (mono SW={wl.sw} F={wl.feats} S={wl.sats}) block-sharded over "
                         f"{world} GPU(s) = {Bl} per GPU; per-frame NCCL all-gather of pose + trace(P) + flags inside the timed region",
@@ -415,7 +444,8 @@ def c4_sharded(args, wl_name, world, rank, local, dev, ts, dist, torch, total=64
             "ms_per_frame": ms / K, "wall_ms_per_frame": wall_ms / K, "frames": K, "warmup": W,
             "sequences_per_gpu": Bl, "gather": "all_gather_into_tensor, 14 doubles per sequence, every frame" if world > 1 else
             "single rank: no collective", "h2d_bytes_per_frame": int(h2d), "d2h_bytes_per_frame": total * 14 * 8,
-            "gpu_launches_per_frame": launches / K, "visual_path": None, "timing": "CUDA events on the filter's stream, max over ranks"}
+            "gpu_launches_per_frame": launches / K, "graph_replays": g_replays, "submit": "igv_frame_step: one call per frame, CUDA-graph replay",
+            "timing": "CUDA events on the filter's stream, max over ranks"}
 
 
 def main():
@@ -749,16 +779,25 @@ def main():
             g1 = make_filter(wl, 1, st1, ts, local)
             fr1 = [frame_arrays(st1.next_frame()) for _ in range(prefill + W + K)]
             t1 = [({k: torch.from_numpy(v).to(dev) for k, v in f[0].items()}, f[1]) for f in fr1]
-            for a, mta in t1[:prefill + W]:
+            for a, mta in t1[:prefill]:
                 run_step(g1, a, mta)
+            ff1 = FixedFrame(torch, dev, t1[prefill][0])
+            for a, mta in t1[prefill:prefill + W]:
+                ff1.load(a)
+                ff1.step(g1, mta)
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_host = time.perf_counter()
             e0.record(ts)
             for a, mta in t1[prefill + W:]:
-                run_step(g1, a, mta)
+                ff1.load(a)          # device -> device refill of the fixed argument buffers
+                ff1.step(g1, mta)    # one igv_frame_step call: graph replay
             e1.record(ts)
+            host_ms = (time.perf_counter() - t_host) * 1e3 / K
             torch.cuda.synchronize(dev)
-            line["single_sequence"] = {"ms_per_update": e0.elapsed_time(e1) / K, "updates_per_sec": K / (e0.elapsed_time(e1) * 1e-3)}
+            line["single_sequence"] = {"ms_per_update": e0.elapsed_time(e1) / K, "updates_per_sec": K / (e0.elapsed_time(e1) * 1e-3),
+                                       "host_submit_ms_per_update": host_ms, "graph_replays": g1.graph_replays,
+                                       "submit": "igv_frame_step (one call per frame, CUDA-graph replay)"}
             g1.close()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "ingvio_b200", "csrc")
 OUT = os.path.join(ROOT, "ingvio_b200", "lib")
 LIB = os.path.join(OUT, "libingvio_b200.so")
-SOURCES = ["igv_api.cu", "k_peak.cu", "k_tri.cu", "k_state.cu", "k_propagate.cu", "k_ekf.cu", "k_msckf.cu", "k_qr.cu", "k_gram.cu", "k_gnss.cu", "k_gnss_res.cu", "k_misc.cu", "k_tracks.cu", "k_landmark.cu"]
+SOURCES = ["igv_api.cu", "igv_frame.cu", "k_peak.cu", "k_tri.cu", "k_state.cu", "k_propagate.cu", "k_ekf.cu", "k_msckf.cu", "k_qr.cu", "k_gram.cu", "k_gnss.cu", "k_gnss_res.cu", "k_misc.cu", "k_tracks.cu", "k_landmark.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

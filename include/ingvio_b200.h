@@ -425,6 +425,28 @@ typedef struct {
 igv_status igv_tracks_get(igv_batch* h, const igv_track_dump* d);
 int igv_tracks_capacity(const igv_batch* h);   /* max_tracks, 0 before igv_tracks_create */
 
+/* ---- one whole frame cycle -------------------------------------------------------------------
+ * IngvioFilter::callbackMonoFrame / callbackStereoFrame (IngvioFilter.cpp:143-231) behind one call:
+ *   propagateAugmentAtEnd (n_imu IMU samples, then the clone) -> visual update (igv_msckf_update arguments, or NULL)
+ *   -> marginalisation of the listed clone slots (in the given order; slots refer to the window at that moment)
+ *   -> GNSS update (igv_gnss_update arguments, or NULL).
+ * DEVICE pointer mode: the kernel sequence is captured into a CUDA graph the second time the same frame shape occurs
+ * (variable layout, argument pointers and sizes) and replayed afterwards -- keep the argument buffers at fixed
+ * addresses and refill them between frames. dx_out / n_accepted_out / gamma_out of the nested arguments are honoured
+ * (device pointers). HOST pointer mode: the calls run one after the other (no graph). IGV_GRAPH=0 disables replay. */
+typedef struct {
+  int n_imu;                     /* K IMU samples of the frame interval (0: none)                    */
+  const double* gyro;            /* B x K x 3                                                         */
+  const double* accel;           /* B x K x 3                                                         */
+  const double* dt;              /* B x K                                                             */
+  const igv_msckf_args* visual;  /* or NULL                                                           */
+  int n_marg;                    /* clones leaving the window after the visual update                 */
+  const int* marg_slots;         /* n_marg slots (host array)                                         */
+  const igv_gnss_args* gnss;     /* or NULL                                                           */
+} igv_frame_args;
+igv_status igv_frame_step(igv_batch* h, const igv_frame_args* a);
+long long igv_graph_replays(const igv_batch* h);   /* frames served by a graph launch so far           */
+
 /* ---- delayed initialisation / linear replacement ------------------------------------------------
  * StateManager::addVariableDelayed (StateManager.cpp:547-630, with :462-541): new 1-dim variable.
  * H_old: B x (rows x n_old) col-major (ld = rows), H_new: B x rows, res: B x rows.

@@ -61,6 +61,11 @@ class igv_gnss_args(C.Structure):
                 ("strong_reject", C.c_int), ("dx_out", C.c_void_p)]
 
 
+class igv_frame_args(C.Structure):
+    _fields_ = [("n_imu", C.c_int), ("gyro", C.c_void_p), ("accel", C.c_void_p), ("dt", C.c_void_p),
+                ("visual", C.c_void_p), ("n_marg", C.c_int), ("marg_slots", c_ip), ("gnss", C.c_void_p)]
+
+
 class igv_gnss_new_sys_args(C.Structure):
     _fields_ = [("n_sats", C.c_int), ("gtype", C.c_int), ("value", C.c_void_p), ("unit", C.c_void_p),
                 ("res_pos", C.c_void_p), ("res_vel", C.c_void_p), ("sigma_psr", C.c_void_p), ("sigma_dopp", C.c_void_p),
@@ -158,6 +163,8 @@ SIGNATURES = {
     "igv_msckf_update": (C.c_int, [_H, C.POINTER(igv_msckf_args)]),
     "igv_gnss_update": (C.c_int, [_H, C.POINTER(igv_gnss_args)]),
     "igv_gnss_add_new_tracked_sys": (C.c_int, [_H, C.POINTER(igv_gnss_new_sys_args)]),
+    "igv_frame_step": (C.c_int, [_H, C.POINTER(igv_frame_args)]),
+    "igv_graph_replays": (C.c_longlong, [_H]),
     "igv_num_landmarks": (C.c_int, [_H]),
     "igv_landmark_idx": (C.c_int, [_H, C.c_int]),
     "igv_landmark_anchor": (C.c_int, [_H, C.c_int]),

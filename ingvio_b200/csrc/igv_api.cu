@@ -350,6 +350,7 @@ igv_status igv_destroy(igv_batch* h) {
   IgvDeviceGuard dev_guard_(h);
   if (!h) return IGV_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
+  igv_frame_graphs_destroy(h);
   void* ptrs[] = {h->P[0], h->P[1], h->X[0], h->X[1], h->flags, h->chi2, h->chi2_095, h->Hs, h->f_rows, h->f_gamma, h->n_acc,
                   h->Hc, h->Rpart, h->Gws, h->Zws, h->Sws, h->dxws, h->Hg, h->rg, h->Rg, h->cnt_g, h->gam_ws, h->Dws, h->Lws, h->pre_ws};
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
@@ -370,6 +371,7 @@ const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "nu
 
 igv_status igv_set_pointer_mode(igv_batch* h, int mode) {
   IgvDeviceGuard dev_guard_(h);
+  if (h) h->cfg_version++;
   if (!h || (mode != IGV_PTR_HOST && mode != IGV_PTR_DEVICE)) return IGV_ERR_INVALID;
   h->ptr_mode = mode;
   return IGV_OK;
@@ -377,12 +379,14 @@ igv_status igv_set_pointer_mode(igv_batch* h, int mode) {
 
 igv_status igv_set_compression(igv_batch* h, int kind) {
   IgvDeviceGuard dev_guard_(h);
+  if (h) h->cfg_version++;
   if (!h || kind < IGV_COMPRESS_AUTO || kind > IGV_COMPRESS_GRAM) return IGV_ERR_INVALID;
   h->compress = kind;
   return IGV_OK;
 }
 
 igv_status igv_set_precision(igv_batch* h, int mode) {
+  if (h) h->cfg_version++;
   if (!h || (mode != IGV_PREC_FP64 && mode != IGV_PREC_FP32_STACK)) return IGV_ERR_INVALID;
   h->stack_f32 = (mode == IGV_PREC_FP32_STACK) ? 1 : 0;
   return IGV_OK;
@@ -401,6 +405,7 @@ long long igv_launch_count(const igv_batch* h) { return h ? h->launches : 0; }
 
 igv_status igv_set_params(igv_batch* h, const igv_params* p) {
   IgvDeviceGuard dev_guard_(h);
+  if (h) h->cfg_version++;
   if (!h || !p) return IGV_ERR_INVALID;
   h->params.noise_g = p->noise_g; h->params.noise_a = p->noise_a;
   h->params.noise_bg = p->noise_bg; h->params.noise_ba = p->noise_ba;
@@ -440,6 +445,7 @@ double igv_chi2_quantile(double p, int dof) {
 
 igv_status igv_set_chi2_table(igv_batch* h, const double* table, int max_dof) {
   IgvDeviceGuard dev_guard_(h);
+  if (h) h->cfg_version++;
   if (!h || !table || max_dof < 1 || max_dof > 1024) return IGV_ERR_INVALID;
   IGV_CUDA(h, cudaMemcpyAsync(h->chi2, table, sizeof(double) * max_dof, cudaMemcpyHostToDevice, h->stream));
   IGV_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -96,9 +96,23 @@ struct IgvKnobs {
     }                                                                                                 \
   } while (0)
 
+// One captured frame of igv_frame_step (igv_frame.cu): the key it was captured for, the instantiated graph and the
+// host-side bookkeeping the frame leaves behind.
+struct IgvFrameGraph {
+  std::vector<unsigned long long> key;
+  void* exec = nullptr;                  // cudaGraphExec_t
+  std::vector<IgvVar> vars_after;
+  int N_after = 0, cur_after = 0, xcur_after = 0, last_visual_path = -1;
+  std::vector<int> col_of_slot_after;
+  long long launch_delta = 0, uses = 0;
+};
+
 struct igv_batch {
   igv_config cfg{};
   IgvKnobs knobs;
+  unsigned long long cfg_version = 0;    // bumped by every setter whose values kernels receive by value
+  std::vector<IgvFrameGraph> frame_graphs;
+  long long graph_replays = 0;
   int B = 0, ld = 0, xsize = 0, max_rows = 0, qmax = 0, ncols_max = 0, rho = 2;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -317,4 +331,5 @@ struct IgvGnssNewRowsLaunch {
   double* Hx; double* Hf; double* res; double* noise2; int* count;
 };
 void igv_launch_gnss_new_rows(igv_batch* h, const IgvGnssNewRowsLaunch& g);
+void igv_frame_graphs_destroy(igv_batch* h);
 void igv_launch_replace_var_linear(igv_batch* h, int tidx, int tsize, const IgvBlocks& blk, const double* H);

@@ -533,6 +533,48 @@ class BatchFilter:
         self._ck(self.lib.igv_gnss_residuals(self.h, C.byref(args)))
         return out
 
+    def frame_step(self, gyro, accel, dt, visual=None, marg_slots=(), gnss=None):
+        """One whole frame cycle behind ONE C-ABI call (igv_frame_step): propagate + augment, the visual update
+        (`visual`: dict with the arguments of msckf_update: mode, pf_w, anchor_slot, obs, obs_mask, chi2_dof, noise,
+        max_valid, optional feat_ok / n_accepted_out / gamma_out), marginalisation of `marg_slots`, the GNSS update
+        (`gnss`: dict with the arguments of gnss_update). With device tensors at fixed addresses the frame is replayed as a
+        CUDA graph from its third occurrence on (graph_replays counts them)."""
+        a = [_Arg(gyro, np.float64), _Arg(accel, np.float64), _Arg(dt, np.float64)]
+        keep = list(a)
+        fa = capi.igv_frame_args()
+        fa.n_imu = int(a[2].keep.shape[1]) if a[2].keep is not None else 0
+        fa.gyro, fa.accel, fa.dt = a[0].ptr, a[1].ptr, a[2].ptr
+        va = ga = None
+        if visual is not None:
+            v = [_Arg(visual["pf_w"], np.float64), _Arg(visual["anchor_slot"], np.int32), _Arg(visual["obs"], np.float64),
+                 _Arg(visual["obs_mask"], np.uint8), _Arg(visual["chi2_dof"], np.int32), _Arg(visual.get("feat_ok"), np.uint8),
+                 _Arg(visual.get("n_accepted_out"), np.int32), _Arg(visual.get("gamma_out"), np.float64)]
+            keep += v
+            va = capi.igv_msckf_args()
+            va.mode, va.n_feats, va.obs_slots = int(visual["mode"]), int(v[0].keep.shape[1]), int(v[3].keep.shape[2])
+            va.noise, va.max_valid = float(visual["noise"]), int(visual.get("max_valid", 0))
+            (va.pf_w, va.anchor_slot, va.obs, va.obs_mask, va.chi2_dof, va.feat_ok, va.n_accepted_out,
+             va.gamma_out) = [x.ptr for x in v]
+            fa.visual = C.cast(C.pointer(va), C.c_void_p)
+        if gnss is not None:
+            gk = [_Arg(gnss[k], np.float64) for k in ("unit", "res_pos", "res_vel", "sigma_psr", "sigma_dopp")]
+            gk += [_Arg(gnss["sys"], np.int32), _Arg(gnss["R_enu2ecef"], np.float64)]
+            keep += gk
+            ga = capi.igv_gnss_args()
+            ga.n_sats = int(gk[1].keep.shape[1])
+            (ga.unit, ga.res_pos, ga.res_vel, ga.sigma_psr, ga.sigma_dopp, ga.sys, ga.R_enu2ecef) = [x.ptr for x in gk]
+            ga.is_adjust_yof, ga.chi2_test = int(gnss.get("is_adjust_yof", 0)), int(gnss.get("chi2_test", 0))
+            ga.strong_reject = int(gnss.get("strong_reject", 1))
+            fa.gnss = C.cast(C.pointer(ga), C.c_void_p)
+        self._set_mode([x for x in keep if x.ptr is not None])
+        ms = (C.c_int * max(1, len(marg_slots)))(*[int(s) for s in marg_slots])
+        fa.n_marg, fa.marg_slots = len(marg_slots), ms
+        self._ck(self.lib.igv_frame_step(self.h, C.byref(fa)))
+
+    @property
+    def graph_replays(self):
+        return int(self.lib.igv_graph_replays(self.h))
+
     # ---- one frame cycle (IngvioFilter.cpp:143-231 order) ----------------------------------------------
     def step(self, fr: FramePacket, noise=0.12, psr_amp=1.0, dopp_amp=1.0, is_adjust_yof=0, gnss_chi2_test=0,
              gnss_strong_reject=1, want=False):

@@ -15,7 +15,7 @@ CSRC = os.path.join(ROOT, "ingvio_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 GEN = os.path.join(BUILD, "gen")
 OUT = os.path.join(BUILD, "libingvio_emul.so")
-MODELLED = ["igv_api.cu", "k_state.cu", "k_misc.cu", "k_gnss.cu", "k_gnss_res.cu", "k_tri.cu", "k_tracks.cu",
+MODELLED = ["igv_api.cu", "igv_frame.cu", "k_state.cu", "k_misc.cu", "k_gnss.cu", "k_gnss_res.cu", "k_tri.cu", "k_tracks.cu",
             "k_propagate.cu", "k_ekf.cu", "k_gram.cu", "k_qr.cu", "k_msckf.cu", "k_landmark.cu"]
 
 sys.path.insert(0, HERE)

@@ -282,3 +282,57 @@ def test_triangulate_group_kernel_vs_thread_kernel(wname, monkeypatch):
     assert np.array_equal(ok0, ok1)
     assert ok0.sum() > 0.5 * ok0.size and not ok0[:, 1].any()
     assert np.abs(pf0 - pf1)[ok0].max() <= 1e-9
+
+
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_frame_step_graph_replay(graph, monkeypatch):
+    """igv_frame_step: a whole frame cycle behind one call. Device-resident argument buffers at fixed addresses are
+    refilled every frame; from the third frame of a steady window the kernel sequence is a CUDA-graph replay
+    (two graphs alternate with the covariance ping-pong). Every frame is compared with the oracle, and the graph run
+    must equal the call-by-call run bit for bit."""
+    import torch
+    from ingvio_b200 import capi
+    monkeypatch.setenv("IGV_GRAPH", graph)
+    wl = WORKLOADS["tiny"]
+    fp = filter_params(wl)
+    B = 2
+    st = SyntheticStream(wl, B)
+    orc = make_oracles(wl, st, fp)
+    g = make_gpu(wl, st, fp)
+    gref = make_gpu(wl, SyntheticStream(wl, B), fp)
+    dev = torch.device("cuda:0")
+    buf = None
+    replays_seen = 0
+    for i in range(wl.sw + 12):
+        fr = st.next_frame()
+        gstep(gref, fr, fp)
+        for b, f in enumerate(orc):
+            f.step(fr.seq(b))
+        G = fr.gnss
+        host = dict(gyro=fr.gyro, accel=fr.accel, dt=fr.dt, pf_w=fr.pf_w, anchor_slot=fr.anchor_slot.astype(np.int32),
+                    obs=fr.obs, obs_mask=fr.obs_mask.astype(np.uint8), chi2_dof=(fr.obs_total.astype(np.int32) - 1),
+                    unit=G.unit, res_pos=G.res_pos, res_vel=G.res_vel, sigma_psr=G.sigma_psr(fp.psr_noise_amp),
+                    sigma_dopp=G.sigma_dopp(fp.dopp_noise_amp), sys=G.sys.astype(np.int32), R_enu2ecef=G.R_enu2ecef.reshape(B, 9))
+        if buf is None or any(buf[k].shape != torch.Size(v.shape) for k, v in host.items()):
+            buf = {k: torch.as_tensor(np.ascontiguousarray(v)).to(dev) for k, v in host.items()}     # (re)allocated: new addresses
+        else:
+            for k, v in host.items():
+                buf[k].copy_(torch.as_tensor(np.ascontiguousarray(v)))                               # same addresses, new contents
+        vis = None
+        if fr.visual_mode is not None:
+            vis = dict(mode=capi.VIS_ALL_OBS, pf_w=buf["pf_w"], anchor_slot=buf["anchor_slot"], obs=buf["obs"], obs_mask=buf["obs_mask"],
+                       chi2_dof=buf["chi2_dof"], noise=fp.visual_noise, max_valid=fr.max_valid)
+        gn = dict(unit=buf["unit"], res_pos=buf["res_pos"], res_vel=buf["res_vel"], sigma_psr=buf["sigma_psr"], sigma_dopp=buf["sigma_dopp"],
+                  sys=buf["sys"], R_enu2ecef=buf["R_enu2ecef"], is_adjust_yof=fp.is_adjust_yof, chi2_test=fp.gnss_chi2_test,
+                  strong_reject=fp.gnss_strong_reject)
+        torch.cuda.synchronize()
+        g.frame_step(buf["gyro"], buf["accel"], buf["dt"], visual=vis, marg_slots=sorted(fr.marg_slots, reverse=True), gnss=gn)
+        g.synchronize()
+        assert_state_close(g, orc, wl.sw, what=f"frame_step frame {i} (graph={graph})")
+        assert np.array_equal(g.get_full_cov(), gref.get_full_cov()) and np.array_equal(g.get_state(), gref.get_state())
+        assert g.curr_cov_size() == gref.curr_cov_size() and g.num_clones() == gref.num_clones()
+        replays_seen = g.graph_replays
+    if graph == "1":
+        assert replays_seen >= 6, replays_seen        # steady state was served by graph launches
+    else:
+        assert replays_seen == 0
