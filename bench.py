@@ -90,15 +90,34 @@ def run_step(g, t, meta):
 
 
 class FixedFrame:
-    """Device-resident argument buffers at FIXED addresses, refilled every frame, and the frame handed to the library as
-    ONE call (igv_frame_step): from the third frame of a steady window the kernel sequence is a CUDA-graph replay."""
+    """Device-resident argument buffers at FIXED addresses -- views into ONE packed allocation, so that a frame's inputs
+    arrive with a single copy -- and the frame handed to the library as ONE call (igv_frame_step): from the third frame
+    of a steady window the kernel sequence is a CUDA-graph replay."""
 
     def __init__(self, torch, dev, example):
-        self.buf = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in example.items()}
+        self.torch = torch
+        self.layout, off = {}, 0
+        for k, v in example.items():
+            nbytes = v.numel() * v.element_size()
+            self.layout[k] = (off, nbytes, v.dtype, tuple(v.shape))
+            off += (nbytes + 255) & ~255
+        self.nbytes = off
+        self.store = torch.empty(off, dtype=torch.uint8, device=dev)
+        self.buf = {k: self.store[o:o + n].view(dt).view(sh) for k, (o, n, dt, sh) in self.layout.items()}
 
-    def load(self, src):
-        for k, v in src.items():
-            self.buf[k].copy_(v, non_blocking=True)
+    def pack(self, src, pinned):
+        """One frame's inputs in the packed layout (host-pinned or on the device of `src`)."""
+        torch = self.torch
+        first = next(iter(src.values()))
+        out = torch.empty(self.nbytes, dtype=torch.uint8, device="cpu" if pinned else first.device)
+        if pinned:
+            out = out.pin_memory()
+        for k, (o, n, dt, sh) in self.layout.items():
+            out[o:o + n].view(dt).view(sh).copy_(src[k])
+        return out
+
+    def load(self, packed):
+        self.store.copy_(packed, non_blocking=True)      # ONE copy per frame
 
     def step(self, g, meta):
         from ingvio_b200 import capi
@@ -396,9 +415,10 @@ def c4_sharded(args, wl_name, world, rank, local, dev, ts, dist, torch, total=64
         checks = {"sum": 0.0}
 
         ff = FixedFrame(torch, dev, pin[prefill][0])
+        packed = {i: ff.pack(pin[i][0], pinned=True) for i in range(prefill, len(pin))}
 
         def frame(a, m):
-            ff.load(a)                              # H2D of this frame's inputs from pinned memory, on the filter's stream
+            ff.load(a)                              # ONE H2D copy of this frame's packed inputs from pinned memory
             ff.step(g, m)                           # ONE C-ABI call; a CUDA-graph replay in the steady state
             g.get_state_async(xdev)                 # the read-out stays in HBM
             g.cov_trace_async(tdev)
@@ -409,8 +429,8 @@ def c4_sharded(args, wl_name, world, rank, local, dev, ts, dist, torch, total=64
                 ts.synchronize()
                 checks["sum"] += float(host[:, 12].sum())      # the host consumes the gathered read-out every frame
 
-        for a, m in pin[prefill:prefill + W]:
-            frame(a, m)
+        for i in range(prefill, prefill + W):
+            frame(packed[i], pin[i][1])
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -419,8 +439,8 @@ def c4_sharded(args, wl_name, world, rank, local, dev, ts, dist, torch, total=64
         l0 = g.launch_count
         t0 = time.perf_counter()
         e0.record(ts)
-        for a, m in pin[prefill + W:]:
-            frame(a, m)
+        for i in range(prefill + W, len(pin)):
+            frame(packed[i], pin[i][1])
         e1.record(ts)
         torch.cuda.synchronize(dev)
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -782,16 +802,17 @@ def main():
             for a, mta in t1[:prefill]:
                 run_step(g1, a, mta)
             ff1 = FixedFrame(torch, dev, t1[prefill][0])
-            for a, mta in t1[prefill:prefill + W]:
-                ff1.load(a)
-                ff1.step(g1, mta)
+            p1 = [ff1.pack(a, pinned=False) for a, _ in t1]
+            for i in range(prefill, prefill + W):
+                ff1.load(p1[i])
+                ff1.step(g1, t1[i][1])
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t_host = time.perf_counter()
             e0.record(ts)
-            for a, mta in t1[prefill + W:]:
-                ff1.load(a)          # device -> device refill of the fixed argument buffers
-                ff1.step(g1, mta)    # one igv_frame_step call: graph replay
+            for i in range(prefill + W, len(t1)):
+                ff1.load(p1[i])            # ONE device -> device refill of the fixed argument buffers
+                ff1.step(g1, t1[i][1])     # one igv_frame_step call: graph replay
             e1.record(ts)
             host_ms = (time.perf_counter() - t_host) * 1e3 / K
             torch.cuda.synchronize(dev)

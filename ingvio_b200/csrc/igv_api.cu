@@ -73,10 +73,12 @@ igv_status arena_reserve(igv_batch* h, size_t bytes, char** out) {
 void arena_reset(igv_batch* h) {
   igv_commit_copies(h);
   igv_batch::Slot& prev = h->slots[h->slot];
-  if (prev.used && prev.consumed) cudaEventRecord(prev.consumed, h->stream);
+  // (while igv_frame_step captures a graph no event of the staging ring may be touched: an event recorded inside a
+  // capture belongs to the graph; igv_arena_quiesce recorded it just before the capture began)
+  if (prev.used && prev.consumed && !h->capturing) cudaEventRecord(prev.consumed, h->stream);
   h->slot = (h->slot + 1) % igv_batch::kSlots;
   igv_batch::Slot& s = h->slots[h->slot];
-  if (s.used && s.consumed && h->copy_stream) cudaStreamWaitEvent(h->copy_stream, s.consumed, 0);
+  if (s.used && s.consumed && h->copy_stream && !h->capturing) cudaStreamWaitEvent(h->copy_stream, s.consumed, 0);
   s.off = 0;
   s.used = false;
   if (s.cap < h->slot_cap) {   // converge to the common capacity right away (the old block is retired, never freed here)
@@ -212,6 +214,13 @@ double reg_gamma_p(double a, double x) {
 }
 
 }  // namespace
+
+// Everything enqueued so far that reads the current staging slot is marked consumed NOW (eagerly, outside any capture).
+void igv_arena_quiesce(igv_batch* h) {
+  igv_commit_copies(h);
+  igv_batch::Slot& prev = h->slots[h->slot];
+  if (prev.used && prev.consumed) cudaEventRecord(prev.consumed, h->stream);
+}
 
 IgvLayout igv_batch::layout() const {
   IgvLayout L;
@@ -371,7 +380,6 @@ const char* igv_last_error(const igv_batch* h) { return h ? h->err.c_str() : "nu
 
 igv_status igv_set_pointer_mode(igv_batch* h, int mode) {
   IgvDeviceGuard dev_guard_(h);
-  if (h) h->cfg_version++;
   if (!h || (mode != IGV_PTR_HOST && mode != IGV_PTR_DEVICE)) return IGV_ERR_INVALID;
   h->ptr_mode = mode;
   return IGV_OK;

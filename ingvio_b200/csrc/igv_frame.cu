@@ -5,6 +5,8 @@
 // sizes) and replayed from then on: a steady-state sliding window alternates between two graphs (the covariance
 // ping-pong flips once per frame), the host submits one graph launch per frame instead of ~10 kernel launches and the
 // bookkeeping of the variable layout is replayed from the snapshot taken at capture time.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "igv_internal.h"
@@ -69,6 +71,10 @@ extern "C" igv_status igv_frame_step(igv_batch* h, const igv_frame_args* a) {
   if (a->n_imu > 0 && (!a->gyro || !a->accel || !a->dt)) return IGV_ERR_INVALID;
   const bool graphable = h->ptr_mode == IGV_PTR_DEVICE && h->knobs.graph != 0 && !h->prof_on;
   if (!graphable) return run_frame(h, a);
+  {   // errors left behind by earlier (unchecked) runtime calls must not be blamed on this frame
+    cudaError_t stale = cudaGetLastError();
+    if (stale != cudaSuccess && getenv("IGV_DEBUG")) std::fprintf(stderr, "igv_frame_step: stale error on entry: %s\n", cudaGetErrorString(stale));
+  }
   const std::vector<unsigned long long> key = frame_key(h, a);
   IgvFrameGraph* hit = nullptr;
   for (auto& g : h->frame_graphs)
@@ -82,6 +88,11 @@ extern "C" igv_status igv_frame_step(igv_batch* h, const igv_frame_args* a) {
     h->last_visual_path = hit->last_visual_path;
     h->graph_replays++;
     hit->uses++;
+    if (getenv("IGV_DEBUG")) {
+      cudaError_t e2 = cudaStreamSynchronize(h->stream);
+      std::fprintf(stderr, "igv_frame_step: replay N=%d cur=%d xcur=%d vars=%zu sync=%s last=%s\n", h->N, h->cur, h->xcur, h->vars.size(),
+                   cudaGetErrorString(e2), cudaGetErrorString(cudaGetLastError()));
+    }
     return IGV_OK;
   }
   if (!hit) {   // first sight of this frame shape: run it eagerly (workspaces grow, kernel attributes get set)
@@ -98,9 +109,12 @@ extern "C" igv_status igv_frame_step(igv_batch* h, const igv_frame_args* a) {
   }
   // second sight: capture, instantiate, launch
   const long long l0 = h->launches;
+  igv_arena_quiesce(h);
   cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { cudaGetLastError(); return run_frame(h, a); }
+  h->capturing = true;
   const igv_status s = run_frame(h, a);
+  h->capturing = false;
   cudaGraph_t graph = nullptr;
   e = cudaStreamEndCapture(h->stream, &graph);
   if (s != IGV_OK || e != cudaSuccess || !graph) {
@@ -116,6 +130,8 @@ extern "C" igv_status igv_frame_step(igv_batch* h, const igv_frame_args* a) {
   if (e != cudaSuccess) { h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return IGV_ERR_CUDA; }
   snapshot(h, *hit, l0);   // the host bookkeeping already advanced during capture
   hit->exec = exec;
+  if (getenv("IGV_DEBUG")) std::fprintf(stderr, "igv_frame_step: captured N=%d cur=%d xcur=%d launches=%lld last=%s\n", h->N, h->cur, h->xcur,
+                                        hit->launch_delta, cudaGetErrorString(cudaGetLastError()));
   e = cudaGraphLaunch(exec, h->stream);
   if (e != cudaSuccess) { h->err = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e); return IGV_ERR_CUDA; }
   h->graph_replays++;

@@ -113,6 +113,7 @@ struct igv_batch {
   unsigned long long cfg_version = 0;    // bumped by every setter whose values kernels receive by value
   std::vector<IgvFrameGraph> frame_graphs;
   long long graph_replays = 0;
+  bool capturing = false;                // igv_frame_step is capturing the stream: no staging-ring events
   int B = 0, ld = 0, xsize = 0, max_rows = 0, qmax = 0, ncols_max = 0, rho = 2;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -332,4 +333,5 @@ struct IgvGnssNewRowsLaunch {
 };
 void igv_launch_gnss_new_rows(igv_batch* h, const IgvGnssNewRowsLaunch& g);
 void igv_frame_graphs_destroy(igv_batch* h);
+void igv_arena_quiesce(igv_batch* h);
 void igv_launch_replace_var_linear(igv_batch* h, int tidx, int tsize, const IgvBlocks& blk, const double* H);
