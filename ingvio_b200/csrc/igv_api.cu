@@ -275,6 +275,7 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
     h->knobs.tri_cfg = knob("IGV_TRI_CFG", 0);
     h->knobs.graph = knob("IGV_GRAPH", -1);
     h->knobs.feat_const = knob("IGV_FEAT_CONST", 1);
+    h->knobs.prop_tma = knob("IGV_PROP_TMA", 1);
   }
   if (cfg->stream) {
     h->stream = static_cast<cudaStream_t>(cfg->stream);

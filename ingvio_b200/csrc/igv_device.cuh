@@ -111,6 +111,35 @@ __device__ inline void psi_func(const double* w, const double* a, double dt, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bulk asynchronous copy global -> shared through the TMA unit (cp.async.bulk, SASS UBLKCP), completion on an mbarrier.
+// One elected thread issues the copy; the data lands while the CTA does other work; every thread waits on the
+// barrier's phase before the first read.  Addresses and sizes are multiples of 16 bytes.
+// ---------------------------------------------------------------------------------------------
+#ifndef IGV_EMULATE
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // box-plus on the packed mean (PoseState.cpp:79-88,174-186, VecState.cpp:27-47)
 // ---------------------------------------------------------------------------------------------
 __device__ inline void retract_pose(double* R, double* p1, double* p2, const double* dth, const double* d1,

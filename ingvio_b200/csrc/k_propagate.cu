@@ -14,6 +14,7 @@ using namespace igv;
 namespace {
 
 constexpr int kMaxStrip = 20;  // 15 IMU + 4 clock biases + clock drift
+constexpr int kPreStride = 408; // doubles per (sequence, IMU sample) transition record: 225 + 180, padded to 16 bytes
 
 struct PropArgs {
   double* P; int ld; int N;
@@ -21,7 +22,8 @@ struct PropArgs {
   int n_steps;
   const double* gyro; const double* accel; const double* dt;  // IMU mode (Phi == nullptr)
   const double* Phi; const double* G;                         // covariance-only mode
-  const double* pre;                                          // IMU mode: per (b, step) 225 Phi + 180 G*sigma, row-major
+  const double* pre;                                          // IMU mode: per (b, step) 225 Phi + 180 G*sigma, row-major, stride kPreStride
+  int stage_pre;                                              // fetch the sequence's records with one bulk TMA copy
   IgvDevParams prm;
   int idx_cb[4]; int idx_fs; int enable_gnss;
 };
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kImuWarps * 32) k_imu_mean(double* X, int xsiz
     __syncwarp();
     if (live)
       imu_phi_g(s_st[wib][lane], s_st[wib][lane + 1] + 9, s_st[wib][lane + 1] + 12, Xl + 15, Xl + 18, gyro + o * 3, accel + o * 3,
-                d, prm, s_gam[wib][lane], pre + o * 405, pre + o * 405 + 225);
+                d, prm, s_gam[wib][lane], pre + o * kPreStride, pre + o * kPreStride + 225);
     __syncwarp();
   }
   for (int i = lane; i < 15; i += 32) Xb[i] = Xl[i];                  // R, p, v
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kImuWarps * 32) k_imu_mean(double* X, int xsiz
 }
 
 __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   constexpr int S = kMaxStrip;  // fixed stride of every small matrix: index math folds to shifts/multiplies
   const int b = blockIdx.x, N = a.N, ld = a.ld, tid = threadIdx.x;
   double* Pb = a.P + (size_t)b * ld * ld;
@@ -154,6 +156,15 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
   __shared__ __align__(16) double sPhi[225], sG[180], sT[S * S], sQ[S * S], sM[15 * 12];
   __shared__ __align__(16) double sBk[S * S], sX[S * S], sY[S * S], sTt[S * S], sTn[S * S];
   __shared__ double s_dt;
+  // IMU mode: the transition records of ALL samples of this sequence (n_steps x kPreStride doubles, one contiguous block
+  // written by k_imu_mean) are fetched by ONE bulk TMA copy issued here and landing behind the strip in shared memory
+  // while the strip itself is loaded; the per-sample loop then reads them in place (no per-sample global round trip).
+  __shared__ __align__(8) unsigned long long s_bar;
+  double* stage = sm + (size_t)S * N + (((size_t)S * N) & 1);   // 16-byte aligned
+  const bool staged = a.stage_pre != 0;
+#ifndef IGV_EMULATE
+  if (staged && tid == 0) mbar_init(&s_bar, 1);
+#endif
   if (tid == 0) {
     int n = 0;
     for (int i = 0; i < 15; ++i) cidx[n++] = i;
@@ -166,6 +177,18 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
     for (int i = n; i < S; ++i) cidx[i] = 0;
   }
   __syncthreads();
+  if (staged) {
+    const double* src = a.pre + (size_t)b * a.n_steps * kPreStride;
+    const unsigned bytes = (unsigned)(a.n_steps * kPreStride * sizeof(double));
+#ifndef IGV_EMULATE
+    if (tid == 0) {
+      mbar_expect_tx(&s_bar, bytes);
+      bulk_g2s(stage, src, bytes, &s_bar);
+    }
+#else
+    for (int t = tid; t < a.n_steps * kPreStride; t += blockDim.x) stage[t] = src[t];
+#endif
+  }
   const int nC = s_nC, nS = s_nS;
   const bool has_fs = s_has_fs != 0;
   double* W = sm;  // S x N row-major (rows >= nS are zero): W[r*N + j] = P[cidx[r], j]
@@ -182,8 +205,13 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
     sBk[t] = (r < nS && c < nS) ? W[r * N + cidx[c]] : 0.0;
     sTt[t] = (r == c) ? 1.0 : 0.0;
   }
+#ifndef IGV_EMULATE
+  if (staged) mbar_wait(&s_bar, 0);   // the bulk copy has landed (it overlapped the strip load above)
+#endif
   __syncthreads();
   for (int step = 0; step < a.n_steps; ++step) {
+    const double* cPhi = sPhi;     // this sample's Phi (15 x 15) and G diag(sigma) (15 x 12), row-major
+    const double* cG = sG;
     // load this step's Phi (15x15) and G*diag(sigma) (15x12), row-major, all threads
     if (a.Phi) {
       const double* Ph = a.Phi + (size_t)b * 225;
@@ -192,8 +220,12 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
       for (int t = tid; t < 225; t += blockDim.x) sPhi[t] = Ph[(t / 15) + 15 * (t % 15)];
       for (int t = tid; t < 180; t += blockDim.x) sG[t] = Gg[(t / 12) + 15 * (t % 12)] * sg[(t % 12) / 3];
       if (tid == 0) s_dt = a.dt[b];
+    } else if (staged) {
+      cPhi = stage + (size_t)step * kPreStride;
+      cG = cPhi + 225;
+      if (tid == 0) s_dt = a.dt[(size_t)b * a.n_steps + step];
     } else {
-      const double* pr = a.pre + ((size_t)b * a.n_steps + step) * 405;
+      const double* pr = a.pre + ((size_t)b * a.n_steps + step) * kPreStride;
       for (int t = tid; t < 225; t += blockDim.x) sPhi[t] = pr[t];
       for (int t = tid; t < 180; t += blockDim.x) sG[t] = pr[225 + t];
       if (tid == 0) s_dt = a.dt[(size_t)b * a.n_steps + step];
@@ -205,7 +237,7 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
     for (int t = tid; t < S * S; t += blockDim.x) {
       const int r = t / S, c = t % S;
       double val = (r == c && r < nS) ? 1.0 : 0.0;
-      if (r < 15 && c < 15) val = sPhi[r * 15 + c];
+      if (r < 15 && c < 15) val = cPhi[r * 15 + c];
       else if (r >= 15 && r < nC && c == nS - 1 && has_fs) val = dt;
       sT[t] = val;
     }
@@ -214,7 +246,7 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
     // two shared-memory loads per FMA and was bound by shared-memory bandwidth
     auto none = [](int, int) { return false; };
     // M = Phi * Gs (15 x 12)
-    cta_gemm_mma<1, 1>(15, 12, 15, [&](int i, int k) { return sPhi[i * 15 + k]; }, [&](int k, int j) { return sG[k * 12 + j]; },
+    cta_gemm_mma<1, 1>(15, 12, 15, [&](int i, int k) { return cPhi[i * 15 + k]; }, [&](int k, int j) { return cG[k * 12 + j]; },
                        [&](int i, int j, double v) { sM[i * 12 + j] = v; }, none);
     // X = Bk T^T and the accumulated transition Tn = T Tt
     cta_gemm_mma<1, 1>(S, S, S, [&](int i, int k) { return sBk[i * S + k]; }, [&](int k, int j) { return sT[j * S + k]; },
@@ -293,14 +325,14 @@ void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const d
   a.P = h->Pc(); a.ld = h->ld; a.N = h->N;
   a.X = h->Xc(); a.xsize = h->xsize;
   a.n_steps = n_steps;
-  a.gyro = gyro; a.accel = accel; a.dt = dt; a.Phi = Phi; a.G = G; a.pre = nullptr;
+  a.gyro = gyro; a.accel = accel; a.dt = dt; a.Phi = Phi; a.G = G; a.pre = nullptr; a.stage_pre = 0;
   a.prm = h->params;
   IgvLayout L = h->layout();
   for (int i = 0; i < 4; ++i) a.idx_cb[i] = L.idx_gnss[i];
   a.idx_fs = L.idx_gnss[IGV_GNSS_FS];
   a.enable_gnss = 1;
   if (!Phi) {
-    const size_t need = (size_t)h->B * n_steps * 405;
+    const size_t need = (size_t)h->B * n_steps * kPreStride;
     if (need > h->pre_cap) {
       if (h->pre_ws) { cudaStreamSynchronize(h->stream); cudaFree(h->pre_ws); }
       cudaMalloc(reinterpret_cast<void**>(&h->pre_ws), sizeof(double) * need);
@@ -313,8 +345,12 @@ void igv_launch_propagate(igv_batch* h, int n_steps, const double* gyro, const d
                                                       h->pre_ws);
     h->launches++;
   }
-  const size_t smem = sizeof(double) * kMaxStrip * h->N;
-  IGV_SMEM_OPTIN((k_propagate), 96 * 1024);   // 20 x 512 x 8 B at the largest max_dim igv_create accepts
+  size_t smem = sizeof(double) * kMaxStrip * h->N;
+  // IMU mode: stage the whole sequence's transition records behind the strip with one bulk TMA copy when they fit
+  const size_t stage_bytes = sizeof(double) * (size_t)n_steps * kPreStride;
+  a.stage_pre = (!Phi && h->knobs.prop_tma != 0 && smem + 16 + stage_bytes <= 160 * 1024) ? 1 : 0;
+  if (a.stage_pre) smem += 16 + stage_bytes;
+  IGV_SMEM_OPTIN((k_propagate), 168 * 1024);   // strip: 20 x 512 x 8 B at the largest max_dim igv_create accepts (+ staging)
   k_propagate<<<h->B, 128, smem, h->stream>>>(a);
   h->launches++;
 }

@@ -41,11 +41,56 @@ def tf32_round(x):
     return u.astype(np.uint32).view(np.float32)
 
 
+def tf32_split(x32):
+    """x = hi + lo with both parts representable as TF32 operands (the "3xTF32" trick: hi*hi + hi*lo + lo*hi)."""
+    hi = tf32_round(x32)
+    lo = tf32_round((x32 - hi).astype(np.float32))
+    return hi, lo
+
+
+def gram_reduced(W, mode, chunk=128):
+    """G = W^T W as a tcgen05 pipeline would form it: operands in the given format, FP32 accumulation inside a tile of
+    `chunk` stack rows (the TMEM accumulator), tiles summed in FP64 (a fix-up pass).
+      f32acc   FP32 operands, FP32 accumulation         (what a 3xTF32 split approximates)
+      tf32     TF32 operands (kind::tf32), FP32 accumulation
+      tf32x3   two-term TF32 split, three MMAs per tile (hi hi + hi lo + lo hi), FP32 accumulation"""
+    W32 = W.astype(np.float32)
+    n = W.shape[1]
+    G = np.zeros((n, n), np.float64)
+    for r0 in range(0, W.shape[0], chunk):
+        T = W32[r0:r0 + chunk]
+        if mode == "f32acc":
+            acc = (T.T @ T).astype(np.float32)
+        elif mode == "tf32":
+            h = tf32_round(T)
+            acc = (h.T @ h).astype(np.float32)
+        else:
+            h, l = tf32_split(T)
+            acc = ((h.T @ h).astype(np.float32) + (h.T @ l).astype(np.float32) + (l.T @ h).astype(np.float32)).astype(np.float32)
+        G += acc.astype(np.float64)
+    return G
+
+
+def compress_from_gram(G, n, tol=1e-13):
+    """[Hc | rc] with Hc^T Hc = G[:n,:n], Hc^T rc = G[:n,n] (what the device's Gram path hands to the EKF update)."""
+    lam, V = np.linalg.eigh(0.5 * (G[:n, :n] + G[:n, :n].T))
+    keep = lam > tol * lam.max()
+    Hc = np.sqrt(lam[keep])[:, None] * V[:, keep].T
+    rc = (V[:, keep].T @ G[:n, n]) / np.sqrt(lam[keep])
+    return Hc, rc
+
+
 VARIANTS = {
     "fp64": dict(stack=np.float64, tf32=False, ekf=np.float64, store32=False),
     "stack32": dict(stack=np.float32, tf32=False, ekf=np.float64, store32=False),
     "stack_tf32": dict(stack=np.float32, tf32=True, ekf=np.float64, store32=False),
     "all32": dict(stack=np.float32, tf32=False, ekf=np.float32, store32=True),
+    # the device's IGV_PREC_FP32_STACK mode (stack computed in f64, STORED as f32) with the Gram matrix of the stack formed
+    # by a tensor-core pipeline in reduced precision (see gram_reduced)
+    "store32_gram64": dict(stack=np.float64, tf32=False, ekf=np.float64, store32=False, gram="f64"),
+    "gram_f32acc": dict(stack=np.float64, tf32=False, ekf=np.float64, store32=False, gram="f32acc"),
+    "gram_tf32": dict(stack=np.float64, tf32=False, ekf=np.float64, store32=False, gram="tf32"),
+    "gram_tf32x3": dict(stack=np.float64, tf32=False, ekf=np.float64, store32=False, gram="tf32x3"),
 }
 
 
@@ -112,10 +157,15 @@ def visual_update(state, frame, noise, chi2_table, var, max_valid):
     W = np.vstack(blocks)
     if var["tf32"]:
         W = tf32_round(W)
-    if W.shape[0] > n:                                               # compression (:139-155), Q^T [H r]
-        W = np.linalg.qr(W, mode="r")[:min(n + 1, W.shape[0])]
     de = var["ekf"]
-    Hc, rc = W[:, :n].astype(de), W[:, n].astype(de)
+    if var.get("gram"):
+        W = W.astype(np.float32).astype(np.float64)                  # the stack is stored in single precision
+        G = W.T @ W if var["gram"] == "f64" else gram_reduced(W, var["gram"])
+        Hc, rc = compress_from_gram(G, n)
+    else:
+        if W.shape[0] > n:                                           # compression (:139-155), Q^T [H r]
+            W = np.linalg.qr(W, mode="r")[:min(n + 1, W.shape[0])]
+        Hc, rc = W[:, :n].astype(de), W[:, n].astype(de)
     P = state.cov.astype(de)
     PHt = P[:, idx_cols] @ Hc.T                                      # StateManager.cpp:381-397
     S = Hc @ PHt[idx_cols, :] + de(noise) ** 2 * np.eye(Hc.shape[0], dtype=de)
@@ -189,8 +239,9 @@ def sweep(workload, n_frames, variants=("stack32", "stack_tf32", "all32"), seq0=
 
 if __name__ == "__main__":
     args = sys.argv[1:] or ["c2", "12"]
-    table = [sweep(args[i], int(args[i + 1])) for i in range(0, len(args), 2)]
-    path = os.path.join(ROOT, "profiles", "r01_fp32_sweep.json")
+    vs = tuple(os.environ["IGV_SWEEP_VARIANTS"].split(",")) if os.environ.get("IGV_SWEEP_VARIANTS") else ("stack32", "stack_tf32", "all32")
+    table = [sweep(args[i], int(args[i + 1]), variants=vs) for i in range(0, len(args), 2)]
+    path = os.path.join(ROOT, "profiles", os.environ.get("IGV_SWEEP_OUT", "r01_fp32_sweep.json"))
     with open(path, "w") as fh:
         json.dump(table, fh, indent=1)
     print(json.dumps(table, indent=1))
