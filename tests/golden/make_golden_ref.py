@@ -33,6 +33,9 @@ def main():
             out[f"{k}_x{f}"] = recs[f]["x"]
             out[f"{k}_P{f}"] = recs[f]["P"]
             out[f"{k}_lms{f}"] = recs[f]["lms"]
+    recs = ref_pin.run_ref(False, False, **ref_pin.BIG)      # BASELINE-sized window and track count
+    for f in ref_pin.BIG_FRAMES:
+        out[f"big_x{f}"], out[f"big_P{f}"], out[f"big_ntr{f}"] = recs[f]["x"], recs[f]["P"], recs[f]["ntr"]
     np.savez_compressed(ref_pin.GOLDEN, **out)
     print("wrote", ref_pin.GOLDEN, os.path.getsize(ref_pin.GOLDEN), "bytes")
 

@@ -16,6 +16,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_frames.npz")
 CONFIGS = [(False, False), (True, False), (False, True), (True, True)]   # (keyframe, stereo) of test_cpp_updaters._stream
 GOLDEN_FRAMES = (0, 4, 8, 13)
 LM_CONFIGS = [(False, 6), (True, 6)]     # (keyframe, max_lm_feats): SLAM landmarks kept in the state (mono)
+# BASELINE-sized stream (configs[1]: mono, SW = 11, 150 tracked features per image): window 11, 150 persistent tracks
+BIG = dict(sw=11, n_tracks=150, m=160, n_frames=20)
+BIG_FRAMES = (10, 15, 19)
 
 
 def build_ref():
@@ -48,11 +51,12 @@ def _read_lm_output(path, max_clones):
     return recs
 
 
-def run_ref(keyframe, stereo, max_lm=0):
+def run_ref(keyframe, stereo, max_lm=0, **stream_kw):
     """The recorded stream of tests/test_cpp_updaters.py through the reference build; one record per frame.
     max_lm > 0 turns the SLAM-landmark branch of the frame callback on (LandmarkUpdate, mono)."""
     from test_cpp_updaters import SW, _read_output, _stream, _write_input
-    wl, fp, st, frames = _stream(keyframe, stereo)
+    wl, fp, st, frames = _stream(keyframe, stereo, **stream_kw)
+    SW = stream_kw.get("sw") or SW
     with tempfile.TemporaryDirectory() as d:
         fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
         _write_input(fin, wl, fp, st, frames, keyframe)
@@ -72,4 +76,5 @@ def load_golden():
     for keyframe, max_lm in LM_CONFIGS:
         k = config_key(keyframe, False, max_lm)
         out[k] = {int(f): dict(x=z[f"{k}_x{f}"], P=z[f"{k}_P{f}"], lms=z[f"{k}_lms{f}"]) for f in GOLDEN_FRAMES}
+    out["big"] = {int(f): dict(x=z[f"big_x{f}"], P=z[f"big_P{f}"], ntr=int(z[f"big_ntr{f}"])) for f in BIG_FRAMES}
     return out

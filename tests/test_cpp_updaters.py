@@ -27,13 +27,15 @@ EMUL = os.path.join(ROOT, "tests", "emul")
 SW, F, M, T, FRAMES = 5, 32, 32, 96, 14
 
 
-def _stream(keyframe, stereo):
-    wl = Workload("trk", 11 + int(stereo), SW + (0 if keyframe else 1), F, 0, stereo=stereo)
-    fp = filter_params(wl, max_sw_clones=SW, frame_select_interval=2)
+def _stream(keyframe, stereo, sw=None, n_tracks=18, m=None, n_frames=None):
+    """The recorded stream: window `sw` (default SW = 5), `n_tracks` persistent landmarks per message of at most `m`."""
+    sw, m, n_frames = sw or SW, m or M, n_frames or FRAMES
+    wl = Workload("trk", 11 + int(stereo), sw + (0 if keyframe else 1), max(F, m), 0, stereo=stereo)
+    fp = filter_params(wl, max_sw_clones=sw, frame_select_interval=2)
     st = SyntheticStream(wl, 1)
-    trk = TrackerStream(st, 18, M)
+    trk = TrackerStream(st, n_tracks, m)
     frames = []
-    for _ in range(FRAMES):
+    for _ in range(n_frames):
         st.n_clones = 0
         fr = st.next_frame(with_visual=False, with_gnss=False, marg_oldest=False)
         frames.append((fr,) + trk.message(fr.t))
@@ -45,7 +47,8 @@ def _write_input(path, wl, fp, st, frames, keyframe):
     sp = o.StateParams(fp)
     ini = st.initial_state()
     rho = wl.rho
-    out = [FRAMES, K_IMU, M, rho, int(keyframe), SW, F, fp.frame_select_interval, T,
+    m_ = frames[0][2].shape[1]           # message capacity of this stream
+    out = [len(frames), K_IMU, m_, rho, int(keyframe), fp.max_sw_clones, max(F, m_), fp.frame_select_interval, max(T, 4 * m_),
            sp.noise_g, sp.noise_a, sp.noise_bg, sp.noise_ba, sp.noise_clockbias, sp.noise_cb_rw, 0.0, 0.0, -fp.gravity_norm]
     out += list(np.asarray(fp.T_cl2i_R).reshape(9)) + list(fp.T_cl2i_p) + list(np.asarray(fp.T_cl2cr_R).reshape(9)) + list(fp.T_cl2cr_p)
     out += [sp.init_cov_rot, sp.init_cov_pos, sp.init_cov_vel, sp.init_cov_bg, sp.init_cov_ba, sp.init_cov_ext_rot, sp.init_cov_ext_pos]
@@ -173,6 +176,38 @@ def test_cuda_path_vs_reference_outputs(tmp_path, keyframe, stereo):
         for k, ref in enumerate(live):
             assert recs[k]["ntr"] == ref["ntr"] and recs[k]["N"] == ref["N"], (k, recs[k]["ntr"], ref["ntr"])
             close(recs[k], ref, f"frame {k} vs reference live")
+
+
+@pytest.mark.gpu
+def test_cuda_path_vs_reference_baseline_size(tmp_path):
+    """The same comparison on the BASELINE-sized stream (configs[1]: mono, window 11, 150 tracks per image): CUDA path
+    (C++ estimator mirror over the C-ABI) against the reference build's committed outputs and, where the binary
+    travelled, its live run frame by frame."""
+    import ref_pin
+    big = ref_pin.BIG
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "_build", "test_updaters_frames"), LIBDIR, LIBNAME)
+    wl, fp, st, frames = _stream(False, False, **big)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_input(fin, wl, fp, st, frames, False)
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and f"FRAMES DONE {big['n_frames']}" in r.stdout, r.stdout + r.stderr
+    recs = _read_output(fout, big["sw"] + 1)
+
+    def close(rec, ref, what):
+        assert rec["P"].shape == ref["P"].shape, (what, rec["P"].shape, ref["P"].shape)
+        err = np.linalg.norm(rec["P"] - ref["P"]) / max(1.0, np.linalg.norm(ref["P"]))
+        assert err <= 1e-8, f"{what}: |dP|_F/max(1,|P|_F) = {err:.3e}"
+        nu = 39 + 12 * rec["ncl"]
+        ex = np.max(np.abs(rec["x"][:nu] - ref["x"][:nu]) / np.maximum(1.0, np.abs(ref["x"][:nu])))
+        assert ex <= 1e-9, f"{what}: state mismatch {ex:.3e}"
+
+    for f, ref in ref_pin.load_golden()["big"].items():
+        assert recs[f]["ntr"] == ref["ntr"]
+        close(recs[f], ref, f"baseline-size frame {f} vs reference golden")
+    if os.path.exists(ref_pin.REF_DRIVER):
+        for k, ref in enumerate(ref_pin.run_ref(False, False, **big)):
+            assert recs[k]["ntr"] == ref["ntr"], (k, recs[k]["ntr"], ref["ntr"])
+            close(recs[k], ref, f"baseline-size frame {k} vs reference live")
 
 
 def test_imu_buffer_matches_oracle(tmp_path):

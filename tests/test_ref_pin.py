@@ -24,8 +24,9 @@ from track_frames import OracleFrontEnd
 TOL_P, TOL_X, TOL_BLOCK = 1e-10, 1e-10, 1e-9     # the reference's own unit bars are 1e-8 / 1e-10 (TestStateManager.cpp)
 
 
-def _oracle_records(keyframe, stereo, max_lm=0):
-    wl, fp, st, frames = _stream(keyframe, stereo)
+def _oracle_records(keyframe, stereo, max_lm=0, **stream_kw):
+    wl, fp, st, frames = _stream(keyframe, stereo, **stream_kw)
+    SW = stream_kw.get("sw") or globals()["SW"]
     fe = OracleFrontEnd(make_oracles(wl, st, fp, with_gnss=False)[0], keyframe, max_lm_feats=max_lm)
     recs = []
     for fr, n, ids, uv in frames:
@@ -109,3 +110,24 @@ def test_oracle_landmarks_match_reference_live(keyframe, max_lm):
     for k, (r, o_) in enumerate(zip(ref, orc)):
         assert r["ntr"] == o_["ntr"], (k, r["ntr"], o_["ntr"])
         _compare_lm(r, o_, f"{ref_pin.config_key(keyframe, False, max_lm)} frame {k} (live)")
+
+
+# ---- BASELINE-sized stream: window 11, 150 tracks per image (configs[1]) -- the RemoveLost stack reaches hundreds of rows,
+# SwMarg selects every second clone; same bars.
+def test_oracle_matches_reference_baseline_size_golden():
+    gold = ref_pin.load_golden()["big"]
+    orc = _oracle_records(False, False, **ref_pin.BIG)
+    for f, rec in gold.items():
+        assert rec["ntr"] == orc[f]["ntr"]
+        _compare(rec, orc[f], f"baseline-size frame {f} (golden)")
+    assert orc[-1]["P"].shape[0] == 21 + 6 * 11
+
+
+def test_oracle_matches_reference_baseline_size_live():
+    if not ref_pin.build_ref():
+        pytest.skip("oracle/_ref/ref_driver not built and /root/reference absent: the golden test above is the pin")
+    ref = ref_pin.run_ref(False, False, **ref_pin.BIG)
+    orc = _oracle_records(False, False, **ref_pin.BIG)
+    for k, (r, o_) in enumerate(zip(ref, orc)):
+        assert r["ntr"] == o_["ntr"], (k, r["ntr"], o_["ntr"])
+        _compare(r, o_, f"baseline-size frame {k} (live)")
