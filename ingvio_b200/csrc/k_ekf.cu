@@ -35,9 +35,11 @@ struct EkfArgs {
   int* flags;
 };
 
-constexpr int kEkfThreads = 384;   // 12 warps: two CTAs per SM at 80 registers, 24 warps to hide the operand latency
-
-__global__ void __launch_bounds__(kEkfThreads, 2) k_ekf_update(EkfArgs a) {
+// THREADS per CTA: 384 (12 warps, two CTAs per SM at 80 registers) for the wide visual update; few measurement rows
+// (GNSS, delayed initialisation, gates) are bound by the barriers of the serial Cholesky, so they run as smaller CTAs,
+// more of which are resident per SM (independent barrier domains overlap).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 384 ? 2 : (THREADS >= 256 ? 3 : 6)) k_ekf_update(EkfArgs a) {
   extern __shared__ double sm[];
   __shared__ int cols[6 * IGV_MAX_BLOCKS];
   __shared__ int s_ok;
@@ -193,7 +195,20 @@ void igv_launch_ekf(igv_batch* h, const IgvEkfLaunch& l) {
   if (a.z_in_smem) smem += zb;
   a.s_in_smem = (smem + sb <= cap) ? 1 : 0;
   if (a.s_in_smem) smem += sb;
-  IGV_SMEM_OPTIN((k_ekf_update), 220 * 1024);
-  k_ekf_update<<<h->B, kEkfThreads, smem, h->stream>>>(a);
+  // knobs: IGV_EKF_T_SMALL / IGV_EKF_T_BIG (threads per CTA for rows <= 32 / above)
+  // measured (c2, B200): 256-thread CTAs for the 24-row GNSS update gain 4 % of the EKF time once the batch fills the
+  // chip (B = 1184) and lose 2 % at B = 8, where one CTA per sequence is all there is
+  int want = (l.rows <= 32) ? h->knobs.ekf_t_small : h->knobs.ekf_t_big;
+  if (want == 0) want = (l.rows <= 32 && h->B >= 296) ? 256 : 384;
+  if (want <= 128) {
+    IGV_SMEM_OPTIN((k_ekf_update<128>), 220 * 1024);
+    k_ekf_update<128><<<h->B, 128, smem, h->stream>>>(a);
+  } else if (want <= 256) {
+    IGV_SMEM_OPTIN((k_ekf_update<256>), 220 * 1024);
+    k_ekf_update<256><<<h->B, 256, smem, h->stream>>>(a);
+  } else {
+    IGV_SMEM_OPTIN((k_ekf_update<384>), 220 * 1024);
+    k_ekf_update<384><<<h->B, 384, smem, h->stream>>>(a);
+  }
   h->launches++;
 }
