@@ -96,6 +96,12 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out);
 igv_status igv_destroy(igv_batch* h);
 const char* igv_last_error(const igv_batch* h);
 igv_status igv_set_pointer_mode(igv_batch* h, int mode);
+/* Lifetime of bulk arguments in HOST pointer mode: they are copied to the device ASYNCHRONOUSLY on the library's copy
+ * stream. Calls with an output argument return after the stream has been synchronised; calls without one
+ * (igv_propagate_imu, igv_tracks_collect, igv_box_plus, igv_msckf_update without outputs, ...) may return while the copy
+ * from a PAGE-LOCKED buffer is still in flight: such a buffer must not be modified until igv_synchronize (or an
+ * igv_fence_record / igv_fence_wait pair) has returned. Pageable buffers are staged by the driver before the copy call
+ * returns and may be reused at once. */
 igv_status igv_synchronize(igv_batch* h);
 igv_status igv_set_compression(igv_batch* h, int kind);   /* IGV_COMPRESS_* (default AUTO) */
 /* Arithmetic mode of the visual update (BASELINE configs[4], "FP32 vs FP64").

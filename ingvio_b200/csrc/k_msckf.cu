@@ -506,38 +506,80 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
       }
       __syncwarp();
       // ---- (5b) Cholesky of S = sS[3:M,3:M] (lower) with the rhs as row M: L y = r_proj rides along ----
-      // Left-looking, one column at a time: lane = row; entry (i, j) first subtracts the dot product of the finished
-      // parts of rows i and j (row j is a broadcast read), then the column is scaled by 1/sqrt(pivot). Every entry
-      // is written once and a column costs one barrier (the right-looking version rewrote the whole trailing
-      // block per column and took ~3x the instructions for the 41-row stereo / wide-window blocks).
-      for (int j = 3; j < M; ++j) {
-        const double* rowj = sS + j * ldm;
-        double dj = 0.0;
-        double accs[2] = {0.0, 0.0};
-        for (int pass = 0, i0 = j; i0 <= M; i0 += 32, ++pass) {
-          const int i = i0 + lane;
-          const int ii = (i <= M) ? i : j;
-          const double* rowi = sS + ii * ldm;
-          double s0 = rowi[j], s1 = 0.0;
-          int k = 3;
-          for (; k + 1 < j; k += 2) {
-            s0 = fma(-rowi[k], rowj[k], s0);
-            s1 = fma(-rowi[k + 1], rowj[k + 1], s1);
+      // Blocked right-looking factorisation inside ONE warp, 8 columns at a time (the 41-row stereo and the wide-window
+      // gates live here): (a) the 8 x 8 diagonal block is factored in registers, lane = row, columns exchanged by
+      // shuffles; (b) the panel rows below it (the right-hand side is the last one) are solved against it, one row per
+      // lane; (c) the trailing block is updated with DMMA.8x8x4 tiles. A column-at-a-time left-looking loop took half of
+      // this kernel's time for stereo (41 dependent steps of dot products through shared memory).
+      {
+        double* A = sS + 3 * ldm + 3;   // A(i, j) = S'(i, j), i = 0..q (row q: right-hand side), j = 0..q-1
+        const int fk = lane & 3, fc = lane >> 2;
+        for (int jb = 0; jb < q; jb += 8) {
+          const int nb = min(8, q - jb);
+          double arow[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) arow[c] = (lane < nb && c <= lane) ? A[(jb + lane) * ldm + jb + c] : 0.0;
+          double rd = 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k >= nb) break;
+            const double d = __shfl_sync(0xffffffffu, arow[k], k);
+            if (!(d > 0.0)) { pd = false; break; }
+            const double inv = rsqrt(d);
+            const double l = arow[k] * inv;          // L[lane][k] (lane == k: sqrt(d))
+            arow[k] = l;
+            if (lane == k) rd = inv;
+#pragma unroll
+            for (int c = k + 1; c < 8; ++c) {
+              const double lc = __shfl_sync(0xffffffffu, l, c);
+              if (c <= lane) arow[c] = fma(-l, lc, arow[c]);
+            }
           }
-          if (k < j) s0 = fma(-rowi[k], rowj[k], s0);
-          const double acc = s0 + s1;
-          if (pass == 0) dj = __shfl_sync(0xffffffffu, acc, 0);   // row j is lane 0 of the first pass
-          if (pass < 2) accs[pass] = acc;
-          else if (i <= M) sS[ii * ldm + j] = acc;                 // > 64 rows below the pivot: scaled after the barrier
+          if (!pd) break;
+          if (lane < nb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c <= lane && c < nb) A[(jb + lane) * ldm + jb + c] = arow[c];
+          }
+          double rdg[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rdg[k] = __shfl_sync(0xffffffffu, rd, k);
+          __syncwarp();
+          const int i0 = jb + nb;
+          for (int i = i0 + lane; i <= q; i += 32) {   // (b) panel: L21[i,:] = A21[i,:] L11^-T
+            double x[8];
+            double* row = A + i * ldm + jb;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < nb) {
+                double acc = row[k];
+#pragma unroll
+                for (int p2 = 0; p2 < 8; ++p2) if (p2 < k) acc = fma(-x[p2], A[(jb + k) * ldm + jb + p2], acc);
+                x[k] = acc * rdg[k];
+              }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k < nb) row[k] = x[k];
+          }
+          __syncwarp();
+          if (i0 >= q) break;   // no columns left: the right-hand side row is solved
+          const int nrt = (q + 1 - i0 + 7) / 8;   // (c) trailing update, 8 x 8 tiles of the lower triangle (+ the rhs row)
+          for (int it = 0; it < nrt; ++it)
+            for (int jt = 0; jt <= it; ++jt) {
+              const int ri = i0 + 8 * it + fc, cj = i0 + 8 * jt + fc, c0 = i0 + 8 * jt + 2 * fk;
+              double cx = 0.0, cy = 0.0;
+              for (int k0 = 0; k0 < nb; k0 += 4) {
+                const bool kv = k0 + fk < nb;
+                const double av = (kv && ri <= q) ? A[ri * ldm + jb + k0 + fk] : 0.0;
+                const double bv = (kv && cj < q) ? A[cj * ldm + jb + k0 + fk] : 0.0;
+                mma884(cx, cy, av, bv);
+              }
+              if (ri <= q) {
+                if (c0 < q && c0 <= ri) A[ri * ldm + c0] -= cx;
+                if (c0 + 1 < q && c0 + 1 <= ri) A[ri * ldm + c0 + 1] -= cy;
+              }
+            }
+          __syncwarp();
         }
-        if (!(dj > 0.0)) { pd = false; break; }
-        const double inv = rsqrt(dj);
-        __syncwarp();
-        if (lane == 0) sS[j * ldm + j] = dj * inv;
-        else if (j + lane <= M) sS[(j + lane) * ldm + j] = accs[0] * inv;
-        if (j + 32 + lane <= M) sS[(j + 32 + lane) * ldm + j] = accs[1] * inv;
-        for (int i = j + 64 + lane; i <= M; i += 32) sS[i * ldm + j] *= inv;
-        __syncwarp();
       }
       if (pd) {
         double g = 0.0;

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kImuWarps * 32) k_imu_mean(double* X, int xsiz
 }
 
 __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ double sm[];   // (dynamic shared memory starts 16-byte aligned: the bulk copy below relies on it)
   constexpr int S = kMaxStrip;  // fixed stride of every small matrix: index math folds to shifts/multiplies
   const int b = blockIdx.x, N = a.N, ld = a.ld, tid = threadIdx.x;
   double* Pb = a.P + (size_t)b * ld * ld;

@@ -33,6 +33,13 @@ cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size
   return cudaSuccess;
 }
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+// stream capture / graphs are not modelled: BeginCapture fails, igv_frame_step then runs the frame call by call
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return cudaErrorNotSupported; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { const cudaError_t e = g_last; g_last = cudaSuccess; return e; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "kernel not available in the CPU model (FP64 tensor-pipe kernels run on the GPU only)"; }
 }

@@ -336,3 +336,24 @@ def test_frame_step_graph_replay(graph, monkeypatch):
         assert replays_seen >= 6, replays_seen        # steady state was served by graph launches
     else:
         assert replays_seen == 0
+
+
+@pytest.mark.parametrize("stereo,sw", [(True, 9), (False, 18)])
+def test_large_gate_blocked_cholesky(stereo, sw):
+    """Gates with more than 32 rows (stereo windows from 9 clones, mono from 18: the 41-row stereo gate of c3, the 57-row
+    gate of c5) run the warp-level blocked Cholesky (register diagonal blocks, DMMA trailing updates): gate statistic of
+    every track and the state against the oracle, small enough to also run on the CPU model."""
+    from ingvio_b200.synth import Workload
+    wl = Workload("big_gate", 31 + int(stereo), sw, 6, 0, stereo=stereo)
+    fp = filter_params(wl)
+    st = SyntheticStream(wl, 1)
+    orc = make_oracles(wl, st, fp, with_gnss=False)
+    g = make_gpu(wl, st, fp, with_gnss=False)
+    for i in range(sw + 2):
+        fr = st.next_frame(with_gnss=False)
+        out = g.step(fr, noise=fp.visual_noise, want=True)
+        orc[0].step(fr.seq(0))
+        if "visual" in out:
+            for fid, gam, dof, ok in orc[0].last["gammas"]:
+                assert abs(out["visual"]["gamma"][0, fid] - gam) <= 1e-8 * max(1, abs(gam)), (i, fid, out["visual"]["gamma"][0, fid], gam)
+        assert_state_close(g, orc, wl.sw, what=f"frame {i}")
