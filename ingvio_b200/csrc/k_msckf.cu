@@ -46,9 +46,9 @@ struct FeatArgs {
   size_t hs_seq_stride; int F_alloc; // per-sequence strides of Hs and of f_rows / f_gamma
   int* f_rows; double* f_gamma;
   int Mmax;                          // rho * n_clones
-  int ldm;                           // row stride of the per-warp S matrix (odd)
+  int ldm;                           // (unused: the per-warp S matrix is packed, see SP below)
   int per_warp;                      // doubles of per-warp scratch
-  int ssz;                           // doubles of the per-warp S region (>= (Mmax+1)*ldm; FUSE: also holds Z rows + D blocks)
+  int ssz;                           // doubles of the per-warp S region (>= (Mmax+1)(Mmax+2)/2; FUSE: also holds Z rows + D blocks)
   // FUSE: the track's contribution to the Gram matrix of the stack is accumulated in the kernel (see (6'))
   int nt, ldz;                       // 8-column tiles of the stack's n+1 columns; row stride of the Z rows
   double* G; long g_seq_stride; int n1p;   // out: upper triangle of [H r]^T [H r], row stride n1p
@@ -57,7 +57,9 @@ struct FeatArgs {
   int hs_f32;                        // IGV_PREC_FP32_STACK: the projected block is stored as float (same element strides)
 };
 
-// per-warp scratch layout (doubles): A[M][3] B[M][3] V[M][3] Am[M][3] E[M][3] r[M] qr[M] S[(M+1)][ldm] maps
+// per-warp scratch layout (doubles): A[M][3] B[M][3] V[M][3] Am[M][3] E[M][3] r[M] qr[M] S (packed lower triangle of
+// (M+1) rows: half the shared memory of full storage, which is what bounds the resident warps of stereo / wide windows) maps
+__host__ __device__ inline int feat_ssz(int Mmax) { return (Mmax + 1) * (Mmax + 2) / 2; }
 __host__ __device__ inline int feat_per_warp(int Mmax, int ssz) {
   return Mmax * 15 + 2 * Mmax + ssz + 2 * Mmax + 8;
 }
@@ -67,13 +69,15 @@ __host__ __device__ inline int feat_per_warp(int Mmax, int ssz) {
 // NCL > 0: the window size is a compile-time constant (the shipped / benchmarked windows), so every shared-memory array
 // base and stride below folds into immediates instead of integer multiply-adds per access; NCL == 0: any window.
 template <int RHO, bool PS_SMEM, int QT, bool FUSE, int NCL>
-__global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ? 1 : 2) k_msckf_features(FeatArgs a) {
+__global__ void __launch_bounds__(FUSE ? 512 : (RHO == 4 ? 384 : kWarps * 32), (FUSE || RHO == 4) ? 1 : 2) k_msckf_features(FeatArgs a) {
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int ncl = NCL > 0 ? NCL : a.L.n_clones, n = 6 * ncl, Mmax = NCL > 0 ? RHO * NCL : a.Mmax, ldm = Mmax | 1;
+  const int ncl = NCL > 0 ? NCL : a.L.n_clones, n = 6 * ncl, Mmax = NCL > 0 ? RHO * NCL : a.Mmax;
+  // S is symmetric: only the lower triangle is stored, row r at r (r + 1) / 2; (r, c) with r >= c
+  auto SP = [](int r, int c) { return ((r * (r + 1)) >> 1) + c; };
   const int c_nt = NCL > 0 ? (6 * NCL + 1 + 7) / 8 : a.nt, c_ldz = 8 * c_nt + 4;
-  const int c_ssz = NCL > 0 ? (FUSE ? max((Mmax + 1) * ldm, 3 * c_ldz + NCL * 27) : (Mmax + 1) * ldm) : a.ssz;
+  const int c_ssz = NCL > 0 ? (FUSE ? max(feat_ssz(Mmax), 3 * c_ldz + NCL * 27) : feat_ssz(Mmax)) : a.ssz;
   const int c_per_warp = NCL > 0 ? feat_per_warp(Mmax, c_ssz) : a.per_warp;
   double* sPose = sm;                                   // 12 per clone
   double* sPs = sm + 12 * IGV_MAX_CLONES;               // [n][n] clone block of P (symmetric), if staged
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
   double* sE = sAm + Mmax * 3;     // [M][3] W T - V D
   double* sr = sE + Mmax * 3;      // [M] residual
   double* sqr = sr + Mmax;         // [M] Q^T r
-  double* sS = sqr + Mmax;         // [(M+1)][ldm] : H_x P_s H_x^T, then S and its Cholesky factor (+ rhs row)
+  double* sS = sqr + Mmax;         // packed lower triangle of (M+1) rows: H_x P_s H_x^T, then S and its Cholesky factor (+ rhs row M)
   int* k2slot = reinterpret_cast<int*>(sS + c_ssz);             // [ncl] obs k -> slot
   int* slot2k = k2slot + ncl;                                    // [ncl] slot -> obs k or -1
   const double* Xb = a.X + (size_t)b * a.xsize;
@@ -368,8 +372,8 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
               acc0 = fma(w[0][j], pa2[t2][j], acc0); acc0 = fma(ga[0][j], w2[t2][j], acc0);
               acc1 = fma(w[1][j], pa2[t2][j], acc1); acc1 = fma(ga[1][j], w2[t2][j], acc1);
             }
-            if (r2 <= r1) { sS[r1 * ldm + r2] = acc0; sS[r2 * ldm + r1] = acc0; }
-            if (r2 <= r1 + 1) { sS[(r1 + 1) * ldm + r2] = acc1; sS[r2 * ldm + r1 + 1] = acc1; }
+            if (r2 <= r1) sS[SP(r1, r2)] = acc0;
+            if (r2 <= r1 + 1) sS[SP(r1 + 1, r2)] = acc1;
           }
         }
       }
@@ -382,9 +386,8 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
       double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int i = lane; i < M; i += 32) {
         double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-        const double* mrow = sS + i * ldm;
         for (int k = 0; k < M; ++k) {
-          const double m = mrow[k];
+          const double m = sS[k <= i ? SP(i, k) : SP(k, i)];   // row i of the symmetric matrix (column part: consecutive lanes, consecutive words)
           w0 = fma(m, sV[k * 3 + 0], w0);
           w1 = fma(m, sV[k * 3 + 1], w1);
           w2 = fma(m, sV[k * 3 + 2], w2);
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
       for (int i = lane; i < M; i += 32) {
         const double qv = sr[i] - (sV[i * 3 + 0] * z0 + sV[i * 3 + 1] * z1 + sV[i * 3 + 2] * z2);
         sqr[i] = qv;
-        if (i >= 3) sS[M * ldm + i] = qv;       // extra row M of S: the right-hand side of L y = r_proj
+        if (i >= 3) sS[SP(M, i)] = qv;          // extra row M of S: the right-hand side of L y = r_proj
       }
       __syncwarp();
     }
@@ -460,16 +463,16 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
       const int ii = on ? 3 + row : 3;
       const double v0 = sV[ii * 3], v1 = sV[ii * 3 + 1], v2 = sV[ii * 3 + 2];
       const double e0 = sE[ii * 3], e1 = sE[ii * 3 + 1], e2 = sE[ii * 3 + 2];
-      const double* srow = sS + ii * ldm;
       double ar[QT];
 #pragma unroll
       for (int c = 0; c < QT; ++c) {
         const int j = min(c + 3, M - 1);
-        double val = srow[j] - (v0 * sAm[j * 3] + v1 * sAm[j * 3 + 1] + v2 * sAm[j * 3 + 2] +
-                                e0 * sV[j * 3] + e1 * sV[j * 3 + 1] + e2 * sV[j * 3 + 2]);
+        // lower triangle only (c <= row): the elimination below never reads a lane's entries right of its diagonal
+        double val = sS[SP(ii, min(j, ii))] - (v0 * sAm[j * 3] + v1 * sAm[j * 3 + 1] + v2 * sAm[j * 3 + 2] +
+                                               e0 * sV[j * 3] + e1 * sV[j * 3 + 1] + e2 * sV[j * 3 + 2]);
         if (c == row) val += a.noise2;
         if (row == q) val = sqr[j];
-        ar[c] = (c < q) ? val : 0.0;
+        ar[c] = (c < q && (c <= row || row == q)) ? val : 0.0;
       }
       double gacc = 0.0;
 #pragma unroll
@@ -496,12 +499,12 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
         const int ii = on ? i : 3;
         const double v0 = sV[ii * 3], v1 = sV[ii * 3 + 1], v2 = sV[ii * 3 + 2];
         const double e0 = sE[ii * 3], e1 = sE[ii * 3 + 1], e2 = sE[ii * 3 + 2];
-        double* srow = sS + ii * ldm;
         const int jmax = min(M, i0 + 32);
         for (int j = 3; j < jmax; ++j) {
-          const double val = srow[j] - (v0 * sAm[j * 3] + v1 * sAm[j * 3 + 1] + v2 * sAm[j * 3 + 2] +
-                                        e0 * sV[j * 3] + e1 * sV[j * 3 + 1] + e2 * sV[j * 3 + 2]);
-          if (on && j <= i) srow[j] = (j == i) ? val + a.noise2 : val;
+          const int at = SP(ii, min(j, ii));
+          const double val = sS[at] - (v0 * sAm[j * 3] + v1 * sAm[j * 3 + 1] + v2 * sAm[j * 3 + 2] +
+                                       e0 * sV[j * 3] + e1 * sV[j * 3 + 1] + e2 * sV[j * 3 + 2]);
+          if (on && j <= i) sS[at] = (j == i) ? val + a.noise2 : val;
         }
       }
       __syncwarp();
@@ -512,13 +515,13 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
       // lane; (c) the trailing block is updated with DMMA.8x8x4 tiles. A column-at-a-time left-looking loop took half of
       // this kernel's time for stereo (41 dependent steps of dot products through shared memory).
       {
-        double* A = sS + 3 * ldm + 3;   // A(i, j) = S'(i, j), i = 0..q (row q: right-hand side), j = 0..q-1
+        auto A = [&](int i, int j) -> double& { return sS[SP(3 + i, 3 + j)]; };   // S'(i, j), i >= j; row q: right-hand side
         const int fk = lane & 3, fc = lane >> 2;
         for (int jb = 0; jb < q; jb += 8) {
           const int nb = min(8, q - jb);
           double arow[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) arow[c] = (lane < nb && c <= lane) ? A[(jb + lane) * ldm + jb + c] : 0.0;
+          for (int c = 0; c < 8; ++c) arow[c] = (lane < nb && c <= lane) ? A(jb + lane, jb + c) : 0.0;
           double rd = 0.0;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
           if (lane < nb) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              if (c <= lane && c < nb) A[(jb + lane) * ldm + jb + c] = arow[c];
+              if (c <= lane && c < nb) A(jb + lane, jb + c) = arow[c];
           }
           double rdg[8];
 #pragma unroll
@@ -548,13 +551,13 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
           const int i0 = jb + nb;
           for (int i = i0 + lane; i <= q; i += 32) {   // (b) panel: L21[i,:] = A21[i,:] L11^-T
             double x[8];
-            double* row = A + i * ldm + jb;
+            double* row = &A(i, jb);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               if (k < nb) {
                 double acc = row[k];
 #pragma unroll
-                for (int p2 = 0; p2 < 8; ++p2) if (p2 < k) acc = fma(-x[p2], A[(jb + k) * ldm + jb + p2], acc);
+                for (int p2 = 0; p2 < 8; ++p2) if (p2 < k) acc = fma(-x[p2], A(jb + k, jb + p2), acc);
                 x[k] = acc * rdg[k];
               }
 #pragma unroll
@@ -569,13 +572,13 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
               double cx = 0.0, cy = 0.0;
               for (int k0 = 0; k0 < nb; k0 += 4) {
                 const bool kv = k0 + fk < nb;
-                const double av = (kv && ri <= q) ? A[ri * ldm + jb + k0 + fk] : 0.0;
-                const double bv = (kv && cj < q) ? A[cj * ldm + jb + k0 + fk] : 0.0;
+                const double av = (kv && ri <= q) ? A(ri, jb + k0 + fk) : 0.0;
+                const double bv = (kv && cj < q) ? A(cj, jb + k0 + fk) : 0.0;
                 mma884(cx, cy, av, bv);
               }
               if (ri <= q) {
-                if (c0 < q && c0 <= ri) A[ri * ldm + c0] -= cx;
-                if (c0 + 1 < q && c0 + 1 <= ri) A[ri * ldm + c0 + 1] -= cy;
+                if (c0 < q && c0 <= ri) A(ri, c0) -= cx;
+                if (c0 + 1 < q && c0 + 1 <= ri) A(ri, c0 + 1) -= cy;
               }
             }
           __syncwarp();
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : kWarps * 32, (FUSE || RHO == 4) ?
       }
       if (pd) {
         double g = 0.0;
-        for (int c = 3 + lane; c < M; c += 32) { const double y = sS[M * ldm + c]; g = fma(y, y, g); }
+        for (int c = 3 + lane; c < M; c += 32) { const double y = sS[SP(M, c)]; g = fma(y, y, g); }
         gamma = warp_sum(g);
       }
     }
@@ -912,8 +915,8 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   a.f_rows = h->f_rows; a.f_gamma = h->f_gamma;
   a.hs_seq_stride = (size_t)h->cfg.max_feats * h->qmax * (h->ncols_max + 1); a.F_alloc = h->cfg.max_feats;
   a.Mmax = h->rho * a.L.n_clones;
-  a.ldm = a.Mmax | 1;
-  a.ssz = (a.Mmax + 1) * a.ldm;
+  a.ldm = 0;
+  a.ssz = feat_ssz(a.Mmax);
   a.per_warp = feat_per_warp(a.Mmax, a.ssz);
   const int ncl = a.L.n_clones, n = 6 * ncl;
   a.nt = (n + 1 + 7) / 8; a.ldz = 8 * a.nt + 4;
@@ -951,8 +954,11 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
       }
     }
   }
-  int W = kWarps;
-  while (W > 1 && sizeof(double) * (fixed + (size_t)W * a.per_warp) > 200 * 1024) --W;
+  // unfused: mono runs two CTAs of 8 warps per SM; stereo (one CTA per SM: its per-warp scratch is twice as large) takes
+  // as many warps as fit, up to 12 (IGV_FEAT_WARPS caps it, for A/B runs)
+  int W = (h->rho == 4) ? 12 : kWarps;
+  if (h->knobs.feat_warps > 0) W = min(W, h->knobs.feat_warps);
+  while (W > 1 && sizeof(double) * (fixed + (size_t)W * a.per_warp) > ((h->rho == 4) ? 222 : 200) * 1024) --W;
   const size_t smem = sizeof(double) * (fixed + (size_t)W * a.per_warp);
   // each CTA stages P_s once and its warps loop over tracks: a few CTAs per sequence are enough
   // (staging costs ~10% of the kernel with 5 CTAs per sequence: one CTA per sequence once the batch alone
