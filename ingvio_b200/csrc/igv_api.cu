@@ -277,6 +277,7 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
     h->knobs.feat_const = knob("IGV_FEAT_CONST", 1);
     h->knobs.prop_tma = knob("IGV_PROP_TMA", 1);
     h->knobs.feat_warps = knob("IGV_FEAT_WARPS", 0);
+    h->knobs.feat_ps = knob("IGV_FEAT_PS", 1);
     h->knobs.ekf_t_small = knob("IGV_EKF_T_SMALL", 0);
     h->knobs.ekf_t_big = knob("IGV_EKF_T_BIG", 0);
   }

@@ -32,6 +32,9 @@ using namespace igv;
 namespace {
 
 constexpr int kWarps = 8;
+#ifndef IGV_STEREO_THREADS
+#define IGV_STEREO_THREADS 384   // unfused stereo: up to 12 warps per CTA (168 registers)
+#endif
 
 struct FeatArgs {
   const double* P; int ld;
@@ -69,7 +72,7 @@ __host__ __device__ inline int feat_per_warp(int Mmax, int ssz) {
 // NCL > 0: the window size is a compile-time constant (the shipped / benchmarked windows), so every shared-memory array
 // base and stride below folds into immediates instead of integer multiply-adds per access; NCL == 0: any window.
 template <int RHO, bool PS_SMEM, int QT, bool FUSE, int NCL>
-__global__ void __launch_bounds__(FUSE ? 512 : (RHO == 4 ? 384 : kWarps * 32), (FUSE || RHO == 4) ? 1 : 2) k_msckf_features(FeatArgs a) {
+__global__ void __launch_bounds__(FUSE ? 512 : (RHO == 4 ? IGV_STEREO_THREADS : kWarps * 32), (FUSE || RHO == 4) ? 1 : 2) k_msckf_features(FeatArgs a) {
   extern __shared__ double sm[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -924,7 +927,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   a.n_acc = h->n_acc; a.max_valid = l.max_valid;
   a.const_sizes = (h->knobs.feat_const != 0) ? 1 : 0;
   a.hs_f32 = h->stack_f32;
-  const bool ps = ((size_t)n * n * sizeof(double) <= 72 * 1024);
+  const bool ps = ((size_t)n * n * sizeof(double) <= 72 * 1024) && h->knobs.feat_ps != 0;
   const size_t fixed = 12 * IGV_MAX_CLONES + (ps ? (size_t)n * n : 0);
   // ---- fused Gram accumulation: one CTA of up to 16 warps per sequence -----------------------------------------
   h->feat_fused = false;
@@ -956,7 +959,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
   }
   // unfused: mono runs two CTAs of 8 warps per SM; stereo (one CTA per SM: its per-warp scratch is twice as large) takes
   // as many warps as fit, up to 12 (IGV_FEAT_WARPS caps it, for A/B runs)
-  int W = (h->rho == 4) ? 12 : kWarps;
+  int W = (h->rho == 4) ? IGV_STEREO_THREADS / 32 : kWarps;
   if (h->knobs.feat_warps > 0) W = min(W, h->knobs.feat_warps);
   while (W > 1 && sizeof(double) * (fixed + (size_t)W * a.per_warp) > ((h->rho == 4) ? 222 : 200) * 1024) --W;
   const size_t smem = sizeof(double) * (fixed + (size_t)W * a.per_warp);
