@@ -235,6 +235,37 @@ def cpu_single_thread(wl, n_frames, seq0=0):
     return n_frames / dt, dt
 
 
+def reference_build_rate():
+    """Frames/s of the REFERENCE's own code (oracle/_ref/ref_driver: its unmodified translation units on the stand-in
+    dense linear algebra of oracle/ref_shim) over the BASELINE-sized recorded stream of tests/ref_pin.py (window 11, 150
+    tracks per image, visual path only). Reported as context beside the port, NOT a timing baseline: the stand-in Eigen is
+    unoptimised, and the stream is the tracker-message one (no GNSS, real track lifetimes). None if the binary is absent."""
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(drv):
+        return None
+    try:
+        for p_ in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+            if p_ not in sys.path:
+                sys.path.insert(0, p_)
+        import ref_pin
+        from test_cpp_updaters import _stream, _write_input
+        big = dict(ref_pin.BIG, n_frames=60)
+        wl, fp, st, frames = _stream(False, False, **big)
+        with tempfile.TemporaryDirectory() as d:
+            fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+            _write_input(fin, wl, fp, st, frames, False)
+            t0 = time.perf_counter()
+            r = subprocess.run([drv, fin, fout], capture_output=True, text=True, timeout=300)
+            dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            return None
+        return {"frames_per_sec": big["n_frames"] / dt, "frames": big["n_frames"], "seconds": dt,
+                "what": "oracle/_ref/ref_driver: unmodified reference sources (propagate, augment, track table, triangulation, "
+                        "RemoveLost + SwMarg updates, marginalise) on the stand-in linear algebra, window 11, 150 tracks/image, 1 core"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
 def usable_cores():
     """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0))
@@ -827,6 +858,9 @@ def main():
                                 "sample": f"1 sequence, {args.cpu_sample_frames} steady-state frames of the same workload "
                                           f"({secs:.1f} s) on one host core; C++ port oracle/cpu_port "
                                           "(reference needs Eigen/SuiteSparse/Boost/ROS, absent here)"}
+        rb = reference_build_rate()
+        if rb is not None:
+            line["cpu_baseline"]["reference_build"] = rb
     g.close()
     if not args.no_c4 and wl.name == "c2":
         try:
