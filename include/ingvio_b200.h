@@ -67,7 +67,12 @@ enum { IGV_FLAG_NEG_DIAG = 1,      /* negative covariance diagonal after an upda
        IGV_FLAG_CHOL_FAIL = 2,     /* innovation covariance not positive definite; update skipped            */
        IGV_FLAG_GNSS_REJECTED = 4, /* joint chi^2 "strong reject" fired (GnssUpdate.cpp:286-287)             */
        IGV_FLAG_TRACKS_FULL = 8,   /* track table full: new tracks of a frame were dropped (igv_tracks_collect) */
-       IGV_FLAG_GATHER_CUT = 16    /* more selected tracks than max_feats: the highest ids were left out        */ };
+       IGV_FLAG_GATHER_CUT = 16,   /* more selected tracks than max_feats: the highest ids were left out        */
+       IGV_FLAG_WEAK_PIVOT = 32    /* informational: the Gram-form compression kept a column whose pivot is below 1e-11 of
+                                      the column's squared norm, within two decades of the 1e-13 threshold under which
+                                      it is treated as dependent, so that row of [R | Q^T r] carries about five digits.
+                                      The posterior's backward error is the same eps ||H||^2 as with a Householder R
+                                      (tests/test_gpu_illcond.py); IGV_COMPRESS_HOUSEHOLDER avoids the Gram form        */ };
 
 typedef struct {
   int batch;        /* B >= 1                                                                    */

@@ -16,7 +16,7 @@ GPS, GLO, GAL, BDS, FS, YOF = range(6)
 R_ISO, R_DIAG, R_FULL = 0, 1, 2
 VIS_ALL_OBS, VIS_SELECTED = 0, 1
 COMPRESS_AUTO, COMPRESS_HOUSEHOLDER, COMPRESS_GRAM = 0, 1, 2
-FLAG_NEG_DIAG, FLAG_CHOL_FAIL, FLAG_GNSS_REJECTED, FLAG_TRACKS_FULL, FLAG_GATHER_CUT = 1, 2, 4, 8, 16
+FLAG_NEG_DIAG, FLAG_CHOL_FAIL, FLAG_GNSS_REJECTED, FLAG_TRACKS_FULL, FLAG_GATHER_CUT, FLAG_WEAK_PIVOT = 1, 2, 4, 8, 16, 32
 TRK_LOST, TRK_SEEN_AT = 0, 1
 
 c_dp = C.POINTER(C.c_double)

@@ -364,7 +364,10 @@ __device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int r
 // panel / per right-hand side solves against it, (c) the trailing update of [S | Z] is a K = NB
 // register-tiled GEMM over all threads.  3 barriers per block; the right-hand sides ride along, so
 // there is no separate triangular solve.  Returns false (uniformly) on a non-positive pivot; with `dref` (the
-// original diagonal) the factorisation is the semi-definite one described at (a) and never fails.
+// original diagonal) the factorisation is the semi-definite one described at (a) and never fails; bit 1 of *s_ok then
+// reports a kept pivot below kWeakPivot of its column's original diagonal, i.e. within two decades of the threshold
+// under which the column would have been treated as dependent (that row of the factor carries about five digits).
+constexpr double kWeakPivot = 1e-11;
 template <int NB>
 __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z, int ldz, int c0, int nc, int* s_ok,
                                             const double* dref = nullptr, double tol = 0.0) {
@@ -382,7 +385,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z
       double arow[NB];
 #pragma unroll
       for (int c = 0; c < NB; ++c) arow[c] = (lane < nb && c <= lane) ? D[lane + (long)c * lds] : 0.0;
-      bool ok = true;
+      bool ok = true, weak = false;
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         if (k >= nb) break;
@@ -391,6 +394,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z
         // dependent column -- its column of L and its entry of the solved right-hand sides become zero
         const bool dead = dref && !(d > tol * dref[jb + k] && d > 1e-280);
         if (!dref && !(d > 0.0)) { ok = false; break; }
+        if (dref && !dead && d < kWeakPivot * dref[jb + k]) weak = true;
         const double inv = dead ? 0.0 : rsqrt(d);
         const double l = arow[k] * inv;          // L[lane][k] (lane == k: sqrt(d))
         arow[k] = l;
@@ -402,6 +406,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z
         }
       }
       if (!ok && lane == 0) *s_ok = 0;
+      if (ok && weak && lane == 0) *s_ok |= 2;
       if (lane < nb) {
 #pragma unroll
         for (int c = 0; c < NB; ++c)

@@ -320,6 +320,7 @@ struct FactorArgs {
   int n;
   double* out; long out_stride;    // n x (n+1) row-major [R | y]
   double tol;                      // relative pivot threshold
+  int* flags;                      // [B] IGV_FLAG_WEAK_PIVOT
 };
 
 __global__ void __launch_bounds__(256) k_gram_factor(FactorArgs a) {
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(256) k_gram_factor(FactorArgs a) {
     const int oj = off(j);
     const double d = U[oj + j];
     const bool live = d > a.tol * dref[j] && d > 1e-280;   // (the second test keeps the fast reciprocal in range)
+    if (live && tid == 0 && d < kWeakPivot * dref[j]) atomicOr(&a.flags[b], IGV_FLAG_WEAK_PIVOT);
     if (live) {
       const double inv = rcp_nobranch(d);   // d > 0 and normal here; every thread needs it, so no slow-path division
       for (int i = j + 1 + warp; i < n; i += nw) {
@@ -391,6 +393,7 @@ __global__ void __launch_bounds__(256) k_gram_factor_blocked(FactorArgs a) {
     }
   __syncthreads();
   cta_chol_solve_fused<8>(S, n, lds, Zr, lds, 0, 1, &s_ok, dref, a.tol);
+  if (tid == 0 && (s_ok & 2)) atomicOr(&a.flags[b], IGV_FLAG_WEAK_PIVOT);
   double* out = a.out + (size_t)b * a.out_stride;
   for (int i = warp; i < n; i += nw)
     for (int k = lane; k < n1; k += 32)
@@ -458,7 +461,7 @@ void igv_launch_gram_factor(igv_batch* h, int nparts) {
   f.G = h->Gws; f.g_seq_stride = (long)h->qr_split_cap * h->gram_n1p * h->gram_n1p;
   f.n1p = 24 * ((n + 1 + 23) / 24) + 8; f.nparts = nparts;
   f.n = n; f.out = h->Hc; f.out_stride = (long)h->ncols_max * (h->ncols_max + 1);
-  f.tol = 1e-13;
+  f.tol = 1e-13; f.flags = h->flags;
   IGV_SMEM_OPTIN((k_gram_factor), 220 * 1024);
   IGV_SMEM_OPTIN((k_gram_factor_blocked), 220 * 1024);
   const int factor_cfg = h->knobs.factor_cfg;     // test knob: 1 forces the column-by-column kernel
