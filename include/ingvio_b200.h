@@ -116,8 +116,15 @@ igv_status igv_set_compression(igv_batch* h, int kind);   /* IGV_COMPRESS_* (def
  *                       Jacobians, null-space projection and the chi^2 gate are still evaluated in double (no gate
  *                       decision can flip), the Gram matrix is accumulated in double and the whole EKF update is
  *                       double. Measured tolerance: tests/test_gpu_precision.py, profiles/r02_precision_sweep.md. */
-enum { IGV_PREC_FP64 = 0, IGV_PREC_FP32_STACK = 1 };
+/*   IGV_PREC_TF32_GRAM  as IGV_PREC_FP32_STACK, and the Gram matrix of the float stack is formed on the 5th-generation
+ *                       tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM): every float is split into two TF32
+ *                       terms and hi^T hi + hi^T lo + lo^T hi is accumulated in FP32 over 128 rows at a time, the
+ *                       128-row sums in FP64; factorisation and EKF update stay FP64. Stacks of up to 192 columns
+ *                       (windows <= 31 clones); wider ones fall back to IGV_PREC_FP32_STACK's kernel. The throughput
+ *                       mode for wide windows (c5); tolerance: a few 1e-7 relative in P (tests/test_gpu_precision.py). */
+enum { IGV_PREC_FP64 = 0, IGV_PREC_FP32_STACK = 1, IGV_PREC_TF32_GRAM = 2 };
 igv_status igv_set_precision(igv_batch* h, int mode);
+int igv_last_gram_tensor(const igv_batch* h);   /* 1 if the last visual update's Gram matrix came from the tcgen05 kernel */
 /* which kernels the last igv_msckf_update used: 0 Householder QR of the materialised stack, 1 Gram matrix of the
  * materialised stack, 2 Gram matrix accumulated inside the per-track kernel (no stack in HBM); -1 before any update */
 int igv_last_visual_path(const igv_batch* h);

@@ -400,10 +400,13 @@ igv_status igv_set_compression(igv_batch* h, int kind) {
 
 igv_status igv_set_precision(igv_batch* h, int mode) {
   if (h) h->cfg_version++;
-  if (!h || (mode != IGV_PREC_FP64 && mode != IGV_PREC_FP32_STACK)) return IGV_ERR_INVALID;
-  h->stack_f32 = (mode == IGV_PREC_FP32_STACK) ? 1 : 0;
+  if (!h || (mode != IGV_PREC_FP64 && mode != IGV_PREC_FP32_STACK && mode != IGV_PREC_TF32_GRAM)) return IGV_ERR_INVALID;
+  h->stack_f32 = (mode != IGV_PREC_FP64) ? 1 : 0;
+  h->gram_tc = (mode == IGV_PREC_TF32_GRAM) ? 1 : 0;
   return IGV_OK;
 }
+
+int igv_last_gram_tensor(const igv_batch* h) { return h ? h->last_gram_tc : -1; }
 
 int igv_last_visual_path(const igv_batch* h) { return h ? h->last_visual_path : -1; }
 

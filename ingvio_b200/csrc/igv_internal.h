@@ -147,7 +147,9 @@ struct igv_batch {
   double* Gws = nullptr;               // partial Gram matrices of the stack  B x qr_split_cap x gram_n1p^2 (k_gram.cu)
   int gram_n1p = 0;
   int compress = 0;                    // IGV_COMPRESS_*
-  int stack_f32 = 0;                   // IGV_PREC_FP32_STACK: Hs holds floats
+  int stack_f32 = 0;                   // IGV_PREC_FP32_STACK / IGV_PREC_TF32_GRAM: Hs holds floats
+  int gram_tc = 0;                     // IGV_PREC_TF32_GRAM: Gram matrix of the float stack on tcgen05 (k_gram_tc.cuh)
+  int last_gram_tc = 0;                // the last compression really ran k_gram_tc
   int last_visual_path = -1;           // igv_last_visual_path
   bool feat_fused = false;             // the last k_msckf_features launch accumulated the Gram matrix itself
   double* Zws = nullptr;               // B x max_rows x (ld+1)

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "igv_device.cuh"
+#include "k_gram_tc.cuh"
 
 using namespace igv;
 
@@ -435,6 +436,25 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
   const int nt = (n + 1 + 7) / 8;
   const int frange = (F + split - 1) / split;
   const int gram_cfg = h->knobs.gram_cfg;            // test knob: 1 forces the super-block kernel
+  h->last_gram_tc = 0;
+#ifndef IGV_EMULATE
+  if (h->gram_tc && h->stack_f32 && n + 1 <= 192) {
+    // IGV_PREC_TF32_GRAM: the float stack through tcgen05 (k_gram_tc.cuh); one CTA per (part, sequence), one CTA per SM
+    igv_tc::GramTcArgs t;
+    t.Hs = reinterpret_cast<const float*>(h->Hs); t.hs_seq_stride = 2 * a.hs_seq_stride;   // floats (the buffer is sized in doubles)
+    t.F = F; t.F_alloc = a.F_alloc; t.qmax = a.qmax; t.ldo = a.ldo; t.f_rows = a.f_rows; t.max_valid = max_valid;
+    t.n1 = n + 1; t.NC = (n + 1 + 31) / 32;
+    t.G = a.G; t.g_seq_stride = a.g_seq_stride; t.n1p = a.n1p; t.n_acc = a.n_acc; t.dbg = nullptr; t.dbg_flags = 0;
+    const size_t tsmem = igv_tc::gram_tc_smem_bytes(t.NC, frange);
+    IGV_SMEM_OPTIN((igv_tc::k_gram_tc), 226 * 1024);
+    dim3 tgrid(split, h->B);
+    igv_tc::k_gram_tc<<<tgrid, igv_tc::kThreads, tsmem, h->stream>>>(t);
+    h->last_gram_tc = 1;
+    igv_launch_gram_factor(h, split);
+    h->launches += 1;
+    return;
+  }
+#endif
   const bool wide = gram_cfg == 1 || nt > 9 || h->stack_f32;   // the stream kernel copies doubles asynchronously
   if (!wide) {
     if (nt <= 4) launch_stream_gram<4, 6>(a, split, h->B, frange, h->stream);
