@@ -201,19 +201,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
     // ===== producers: two rows of every stage per warp, lane = column within a 32-column atom ===========================
     const int pw = warp - kProducerWarp0;
     const float* src = a.Hs + (size_t)b * a.hs_seq_stride;
-    float x[2][2][6];     // [buffer][row][atom]
+    float x[3][2][6];     // [register buffer][row][atom]: loads run two stages ahead of the stores
+    int cur[2] = {0, 0};  // track of the row each slot fetched last (rows only move forward)
     auto fetch = [&](int st, float (&dst)[2][6]) {
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int v = st * kStageRows + 2 * pw + rr;
         const float* srow = nullptr;
         if (v < total) {
-          int lo = 0, hi = nfr;
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (rowstart[mid] <= v) lo = mid; else hi = mid;
-          }
-          srow = src + ((size_t)(f0 + lo) * a.qmax + (v - rowstart[lo])) * a.ldo;
+          int c = cur[rr];
+          while (rowstart[c + 1] <= v) ++c;          // v < total = rowstart[nfr]: stops at the track that holds row v
+          cur[rr] = c;
+          srow = src + ((size_t)(f0 + c) * a.qmax + (v - rowstart[c])) * a.ldo;
         }
 #pragma unroll
         for (int t = 0; t < 6; ++t) {
@@ -235,8 +234,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
         for (int t = 0; t < 6; ++t) {
           if (t < NC) {
             const float xv = val[rr][t];
-            const uint32_t h = tc_to_tf32(xv);
-            const uint32_t l = tc_to_tf32(xv - __uint_as_float(h));
+            // hi = x rounded to TF32's 10 mantissa bits (round half away on the bit pattern: two integer ops instead of
+            // the quarter-rate cvt.rna.tf32), lo = x - hi exactly (<= 13 significant bits; the unit reads its leading 11)
+            const uint32_t h = (__float_as_uint(xv) + 0x1000u) & 0xFFFFE000u;
+            const uint32_t l = __float_as_uint(xv - __uint_as_float(h));
             *reinterpret_cast<uint32_t*>(hi_base + inner + t * 512) = h;
             *reinterpret_cast<uint32_t*>(hi_base + half_bytes + inner + t * 512) = l;
           }
@@ -247,12 +248,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
       if (lane == 0) tc_bar_arrive(bar_full + 8 * stage);
     };
     if (nst > 0) fetch(0, x[0]);
-    for (int st = 0; st < nst; st += 2) {
-      if (st + 1 < nst) fetch(st + 1, x[1]);
+    if (nst > 1) fetch(1, x[1]);
+    for (int st = 0; st < nst; st += 3) {
+      if (st + 2 < nst) fetch(st + 2, x[2]);
       publish(st, x[0]);
       if (st + 1 < nst) {
-        if (st + 2 < nst) fetch(st + 2, x[0]);
+        if (st + 3 < nst) fetch(st + 3, x[0]);
         publish(st + 1, x[1]);
+      }
+      if (st + 2 < nst) {
+        if (st + 4 < nst) fetch(st + 4, x[1]);
+        publish(st + 2, x[2]);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -318,10 +324,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
           if (lane == 0) { a.dbg[128] = __uint_as_float(tmem); a.dbg[129] = (float)total; a.dbg[130] = (float)nst; a.dbg[131] = (float)ndrain; }
         }
         if (i < ncols) {
+          // all loads, then all adds, then all stores: the entries are distinct, which the compiler cannot see
+          const int jb = 32 * c;
+          double* col0 = acc + tc_off0(jb) + i;               // entry (i, jb); column j + 1 starts min(j, 127) + 1 further on
+          double s8[32];
+          int off = 0;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const int j = 32 * c + e;
-            if (j >= i) acc[tc_off0(j) + i] += (double)v[e];
+            s8[e] = (jb + e >= i) ? col0[off] : 0.0;
+            off += min(jb + e, 127) + 1;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) s8[e] += (double)v[e];
+          off = 0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (jb + e >= i) col0[off] = s8[e];
+            off += min(jb + e, 127) + 1;
           }
         }
       }
@@ -330,10 +349,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
         for (int c = 0; c < NC - 4; ++c) {
           tc_ld32(t0 + ncols + 32 * c, v);
           if (i1 >= 0) {
+            const int jb = 32 * c;
+            double* col0 = acc + base1 + (jb * (jb + 1)) / 2 + i1;
+            double s8[32];
+            int off = 0;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const int j1 = 32 * c + e;
-              if (j1 >= i1) acc[base1 + (j1 * (j1 + 1)) / 2 + i1] += (double)v[e];
+              s8[e] = (jb + e >= i1) ? col0[off] : 0.0;
+              off += jb + e + 1;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) s8[e] += (double)v[e];
+            off = 0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (jb + e >= i1) col0[off] = s8[e];
+              off += jb + e + 1;
             }
           }
         }
