@@ -49,8 +49,9 @@ def parse():
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic streams per GPU, tiled to --batch")
     ap.add_argument("--cpu-sample-frames", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32_stack"],
-                    help="fp32_stack: projected per-track blocks stored in single precision (IGV_PREC_FP32_STACK)")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32_stack", "tf32_gram"],
+                    help="fp32_stack: projected per-track blocks stored in single precision (IGV_PREC_FP32_STACK); tf32_gram: "
+                         "the same, and their Gram matrix on the tcgen05 tensor cores, 3 x TF32 split (IGV_PREC_TF32_GRAM)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the c4 leg (64 sequences sharded over the ranks, per-frame gather)")
     return ap.parse_args()
@@ -540,6 +541,8 @@ def main():
         g = make_filter(wl, B, st, ts, local)
         if args.precision == "fp32_stack":
             g.set_precision(capi.PREC_FP32_STACK)
+        elif args.precision == "tf32_gram":
+            g.set_precision(capi.PREC_TF32_GRAM)
         # fill the sliding window (untimed)
         for i in range(prefill):
             run_step(g, to_dev(frames[i][0]), frames[i][1])
@@ -787,7 +790,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if args.precision == "fp64" else "f64 (projected stack stored as f32)",
+        "dtype": {"fp64": "f64", "fp32_stack": "f64 (projected stack stored as f32)",
+                  "tf32_gram": "f64 (projected stack stored as f32, its Gram matrix as 3 x TF32 on tcgen05 with FP64 sums)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": f"{wl.name}: {'stereo' if wl.stereo else 'mono'} SW={wl.sw} F={wl.feats} S={wl.sats} "
                                f"(N={wl.dim}), B={B} independent sequences per GPU",

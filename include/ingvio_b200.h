@@ -119,9 +119,12 @@ igv_status igv_set_compression(igv_batch* h, int kind);   /* IGV_COMPRESS_* (def
 /*   IGV_PREC_TF32_GRAM  as IGV_PREC_FP32_STACK, and the Gram matrix of the float stack is formed on the 5th-generation
  *                       tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM): every float is split into two TF32
  *                       terms and hi^T hi + hi^T lo + lo^T hi is accumulated in FP32 over 128 rows at a time, the
- *                       128-row sums in FP64; factorisation and EKF update stay FP64. Stacks of up to 192 columns
- *                       (windows <= 31 clones); wider ones fall back to IGV_PREC_FP32_STACK's kernel. The throughput
- *                       mode for wide windows (c5); tolerance: a few 1e-7 relative in P (tests/test_gpu_precision.py). */
+ *                       128-row sums in FP64; factorisation and EKF update stay FP64. Used for stacks of 129..192
+ *                       columns (windows of 22..31 clones); narrower and wider ones take IGV_PREC_FP32_STACK's kernel.
+ *                       A throughput / accuracy trade-off for wide windows (c5: 1.6 x the FP64 path), NOT a parity mode:
+ *                       the unit's truncating FP32 accumulation leaves ~1.5e-6 relative in the Gram matrix, which at
+ *                       c5 moves the posterior by up to 2 cm / 5e-4 relative in P within 40 frames
+ *                       (tests/test_gpu_precision.py, profiles/r02_tcgen05_eval.md). */
 enum { IGV_PREC_FP64 = 0, IGV_PREC_FP32_STACK = 1, IGV_PREC_TF32_GRAM = 2 };
 igv_status igv_set_precision(igv_batch* h, int mode);
 int igv_last_gram_tensor(const igv_batch* h);   /* 1 if the last visual update's Gram matrix came from the tcgen05 kernel */

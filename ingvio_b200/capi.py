@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libingvio_b200.so")
 
 IGV_OK, IGV_ERR_INVALID, IGV_ERR_CUDA, IGV_ERR_STATE, IGV_ERR_CAPACITY = range(5)
-PREC_FP64, PREC_FP32_STACK = 0, 1
+PREC_FP64, PREC_FP32_STACK, PREC_TF32_GRAM = 0, 1, 2
 IGV_PTR_HOST, IGV_PTR_DEVICE = 0, 1
 GPS, GLO, GAL, BDS, FS, YOF = range(6)
 R_ISO, R_DIAG, R_FULL = 0, 1, 2
@@ -134,6 +134,7 @@ SIGNATURES = {
     "igv_launch_count": (C.c_longlong, [_H]),
     "igv_set_params": (C.c_int, [_H, C.POINTER(igv_params)]),
     "igv_set_precision": (C.c_int, [_H, C.c_int]),
+    "igv_last_gram_tensor": (C.c_int, [_H]),
     "igv_set_chi2_table": (C.c_int, [_H, c_dp, C.c_int]),
     "igv_chi2_quantile": (C.c_double, [C.c_double, C.c_int]),
     "igv_state_init": (C.c_int, [_H] + [_VP] * 7 + [c_dp]),

@@ -278,6 +278,8 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
     h->knobs.prop_tma = knob("IGV_PROP_TMA", 1);
     h->knobs.feat_warps = knob("IGV_FEAT_WARPS", 0);
     h->knobs.feat_ps = knob("IGV_FEAT_PS", 1);
+    h->knobs.tc_drain = knob("IGV_TC_DRAIN", 0);
+    if (const char* e = std::getenv("IGV_TC_PIVOT_TOL")) h->knobs.tc_pivot_tol = std::atof(e);
     h->knobs.ekf_t_small = knob("IGV_EKF_T_SMALL", 0);
     h->knobs.ekf_t_big = knob("IGV_EKF_T_BIG", 0);
   }

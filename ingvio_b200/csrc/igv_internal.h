@@ -80,6 +80,8 @@ struct IgvKnobs {
   int graph = -1;       // IGV_GRAPH: 0 disables CUDA-graph replay of igv_frame_step
   int feat_const = 1;   // IGV_FEAT_CONST: 0 forbids the compile-time-sized instances of the per-track kernel
   int ekf_t_small = 0, ekf_t_big = 0;       // (0 = automatic) IGV_EKF_T_SMALL / IGV_EKF_T_BIG: threads per CTA of k_ekf_update (rows <= 32 / above)
+  double tc_pivot_tol = 1e-13; // IGV_TC_PIVOT_TOL: relative pivot threshold of the factorisation behind k_gram_tc (A/B runs)
+  int tc_drain = 0;     // IGV_TC_DRAIN: 16-row stages per FP32 accumulation of k_gram_tc (0 = its default)
   int feat_ps = 1;      // IGV_FEAT_PS: 0 keeps the window's covariance block in global memory (A/B runs)
   int feat_warps = 0;   // IGV_FEAT_WARPS: cap on the warps per CTA of the unfused per-track kernel (0 = automatic)
   int prop_tma = 1;     // IGV_PROP_TMA: 0 forbids the bulk-TMA staging of the IMU transition records in k_propagate

@@ -438,13 +438,14 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
   const int gram_cfg = h->knobs.gram_cfg;            // test knob: 1 forces the super-block kernel
   h->last_gram_tc = 0;
 #ifndef IGV_EMULATE
-  if (h->gram_tc && h->stack_f32 && n + 1 <= 192) {
+  // (narrow stacks stay on the FP64 accumulation of the float stack: at n + 1 <= 128 the DMMA kernels are as fast)
+  if (h->gram_tc && h->stack_f32 && n + 1 <= 192 && (n + 1 > 128 || h->knobs.gram_cfg == 3)) {
     // IGV_PREC_TF32_GRAM: the float stack through tcgen05 (k_gram_tc.cuh); one CTA per (part, sequence), one CTA per SM
     igv_tc::GramTcArgs t;
     t.Hs = reinterpret_cast<const float*>(h->Hs); t.hs_seq_stride = 2 * a.hs_seq_stride;   // floats (the buffer is sized in doubles)
     t.F = F; t.F_alloc = a.F_alloc; t.qmax = a.qmax; t.ldo = a.ldo; t.f_rows = a.f_rows; t.max_valid = max_valid;
     t.n1 = n + 1; t.NC = (n + 1 + 31) / 32;
-    t.G = a.G; t.g_seq_stride = a.g_seq_stride; t.n1p = a.n1p; t.n_acc = a.n_acc; t.dbg = nullptr; t.dbg_flags = 0;
+    t.G = a.G; t.g_seq_stride = a.g_seq_stride; t.n1p = a.n1p; t.n_acc = a.n_acc; t.dbg = nullptr; t.dbg_flags = 0; t.drain_stages = h->knobs.tc_drain;
     const size_t tsmem = igv_tc::gram_tc_smem_bytes(t.NC, frange);
     IGV_SMEM_OPTIN((igv_tc::k_gram_tc), 226 * 1024);
     dim3 tgrid(split, h->B);
@@ -481,7 +482,9 @@ void igv_launch_gram_factor(igv_batch* h, int nparts) {
   f.G = h->Gws; f.g_seq_stride = (long)h->qr_split_cap * h->gram_n1p * h->gram_n1p;
   f.n1p = 24 * ((n + 1 + 23) / 24) + 8; f.nparts = nparts;
   f.n = n; f.out = h->Hc; f.out_stride = (long)h->ncols_max * (h->ncols_max + 1);
-  f.tol = 1e-13; f.flags = h->flags;
+  // (measured on c5: thresholds between 1e-13 and 1e-5 give identical results behind the tensor-core Gram matrix, 1e-4 and
+  // above start dropping observable directions; the knob stays for A/B runs)
+  f.tol = h->last_gram_tc ? h->knobs.tc_pivot_tol : 1e-13; f.flags = h->flags;
   IGV_SMEM_OPTIN((k_gram_factor), 220 * 1024);
   IGV_SMEM_OPTIN((k_gram_factor_blocked), 220 * 1024);
   const int factor_cfg = h->knobs.factor_cfg;     // test knob: 1 forces the column-by-column kernel

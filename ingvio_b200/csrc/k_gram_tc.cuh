@@ -47,6 +47,7 @@ struct GramTcArgs {
   int* n_acc;
   float* dbg;               // bring-up only: first accumulator rows / staged bytes of CTA (0, 0), or nullptr
   int dbg_flags;
+  int drain_stages;         // 16-row stages per FP32 accumulation in TMEM (8 = 128 rows); 0 = default
 };
 
 __host__ __device__ inline int tc_ncs(int NC) { return NC < 4 ? 4 : NC; }
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
   const uint32_t tmem = s_tmem;
   const int total = s_total;
   const int nst = (total + kStageRows - 1) / kStageRows;
-  const int ndrain = (nst + kDrainStages - 1) / kDrainStages;
+  const int dstages = a.drain_stages > 0 ? a.drain_stages : kDrainStages;
+  const int ndrain = (nst + dstages - 1) / dstages;
 
   if (warp >= kProducerWarp0) {
     // ===== producers: two rows of every stage per warp, lane = column within a 32-column atom ===========================
@@ -235,9 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
           if (t < NC) {
             const float xv = val[rr][t];
             // hi = x rounded to TF32's 10 mantissa bits (round half away on the bit pattern: two integer ops instead of
-            // the quarter-rate cvt.rna.tf32), lo = x - hi exactly (<= 13 significant bits; the unit reads its leading 11)
+            // the quarter-rate cvt.rna.tf32), lo = x - hi (exact, <= 13 significant bits) rounded the same way
             const uint32_t h = (__float_as_uint(xv) + 0x1000u) & 0xFFFFE000u;
-            const uint32_t l = __float_as_uint(xv - __uint_as_float(h));
+            const uint32_t l = (__float_as_uint(xv - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;   // rounded too: the unit would truncate
             *reinterpret_cast<uint32_t*>(hi_base + inner + t * 512) = h;
             *reinterpret_cast<uint32_t*>(hi_base + half_bytes + inner + t * 512) = l;
           }
@@ -269,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
       const uint32_t idesc1 = tc_idesc(128, NC > 4 ? 32 * (NC - 4) : 32, fl);
       const uint32_t stage0 = tc_smem_u32(stages);
       for (int st = 0; st < nst; ++st) {
-        const int stage = st % kStages, dchunk = st / kDrainStages, buf = dchunk & 1;
-        const bool first = (st % kDrainStages) == 0;
+        const int stage = st % kStages, dchunk = st / dstages, buf = dchunk & 1;
+        const bool first = (st % dstages) == 0;
         if (first) {
           tc_bar_wait(bar_tempty + 8 * buf, ((dchunk >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
           }
         }
         tc_commit(bar_empty + 8 * stage);                                   // the stage may be refilled once these MMAs are done
-        if ((st % kDrainStages) == kDrainStages - 1 || st == nst - 1) tc_commit(bar_tfull + 8 * buf);
+        if ((st % dstages) == dstages - 1 || st == nst - 1) tc_commit(bar_tfull + 8 * buf);
       }
     }
     __syncwarp();

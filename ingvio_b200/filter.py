@@ -115,8 +115,13 @@ class BatchFilter:
         self._ck(self.lib.igv_set_compression(self.h, int(kind)))
 
     def set_precision(self, mode):
-        """capi.PREC_FP64 (default) | capi.PREC_FP32_STACK: projected per-track blocks stored in single precision."""
+        """capi.PREC_FP64 (default) | capi.PREC_FP32_STACK: projected per-track blocks stored in single precision |
+        capi.PREC_TF32_GRAM: the same, and their Gram matrix formed on the tcgen05 tensor cores (3 x TF32 split)."""
         self._ck(self.lib.igv_set_precision(self.h, int(mode)))
+
+    def last_gram_tensor(self):
+        """1 if the last visual update's Gram matrix came from the tcgen05 kernel (k_gram_tc.cuh)."""
+        return int(self.lib.igv_last_gram_tensor(self.h))
 
     def last_visual_path(self):
         """0 Householder QR, 1 Gram of the materialised stack, 2 Gram fused into the per-track kernel."""

@@ -41,7 +41,7 @@ static int run_case(int B, int F, int qmax, int n1, int parts, int max_valid, bo
   igv_tc::GramTcArgs a;
   a.Hs = dH; a.hs_seq_stride = seq; a.F = F; a.F_alloc = F; a.qmax = qmax; a.ldo = ldo; a.f_rows = dfr; a.max_valid = max_valid;
   float* ddbg; CK(cudaMalloc(&ddbg, 4096)); CK(cudaMemset(ddbg, 0, 4096));
-  a.dbg = (B == 2 && n1 == 31) ? ddbg : nullptr; a.dbg_flags = flags; if (flags) printf("--- variant flags %d\n", flags);
+  a.dbg = (B == 2 && n1 == 31) ? ddbg : nullptr; a.dbg_flags = flags; a.drain_stages = getenv("TC_DRAIN") ? atoi(getenv("TC_DRAIN")) : 0; if (flags) printf("--- variant flags %d\n", flags);
   a.n1 = n1; a.NC = NC; a.G = dG; a.g_seq_stride = (long)parts * n1p * n1p; a.n1p = n1p; a.n_acc = dnacc;
   const size_t smem = igv_tc::gram_tc_smem_bytes(NC, (F + parts - 1) / parts);
   CK(cudaFuncSetAttribute(igv_tc::k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
