@@ -445,7 +445,7 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
     t.Hs = reinterpret_cast<const float*>(h->Hs); t.hs_seq_stride = 2 * a.hs_seq_stride;   // floats (the buffer is sized in doubles)
     t.F = F; t.F_alloc = a.F_alloc; t.qmax = a.qmax; t.ldo = a.ldo; t.f_rows = a.f_rows; t.max_valid = max_valid;
     t.n1 = n + 1; t.NC = (n + 1 + 31) / 32;
-    t.G = a.G; t.g_seq_stride = a.g_seq_stride; t.n1p = a.n1p; t.n_acc = a.n_acc; t.dbg = nullptr; t.dbg_flags = 0; t.drain_stages = h->knobs.tc_drain;
+    t.G = a.G; t.g_seq_stride = a.g_seq_stride; t.n1p = a.n1p; t.n_acc = a.n_acc; t.drain_stages = h->knobs.tc_drain;
     const size_t tsmem = igv_tc::gram_tc_smem_bytes(t.NC, frange);
     IGV_SMEM_OPTIN((igv_tc::k_gram_tc), 226 * 1024);
     dim3 tgrid(split, h->B);

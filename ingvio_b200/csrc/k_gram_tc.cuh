@@ -45,8 +45,6 @@ struct GramTcArgs {
   int NC;                   // ceil(n1 / 32)
   double* G; long g_seq_stride; int n1p;   // partial Gram matrices [b][part][n1p x n1p], row-major, upper triangle
   int* n_acc;
-  float* dbg;               // bring-up only: first accumulator rows / staged bytes of CTA (0, 0), or nullptr
-  int dbg_flags;
   int drain_stages;         // 16-row stages per FP32 accumulation in TMEM (8 = 128 rows); 0 = default
 };
 
@@ -92,23 +90,15 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 // shared-memory matrix descriptor, MN-major (cute::UMMA::SmemDescriptor: start address [0,14), leading byte offset
 // [16,30), stride byte offset [32,46), version 1 at [46,48), layout type SWIZZLE_128B_BASE32B = 1 at [61,64);
 // all offsets in units of 16 bytes)
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int flags = 0) {
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((flags & 2) ? 0ull : (1ull << 61));
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both MN-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__device__ __forceinline__ uint32_t tc_idesc(int M, int N, int flags = 0) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((flags & 1) ? 0u : ((1u << 15) | (1u << 16))) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t tc_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void tc_mma_tf32_masked(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}" ::"r"(
-          tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
-      : "memory");
-}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
@@ -266,9 +256,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
   } else if (warp == kMmaWarp) {
     // ===== MMA issuer (one thread) ======================================================================================
     if (lane == 0) {
-      const int fl = a.dbg_flags;
-      const uint32_t idesc0 = tc_idesc(128, 32 * NC, fl);
-      const uint32_t idesc1 = tc_idesc(128, NC > 4 ? 32 * (NC - 4) : 32, fl);
+      const uint32_t idesc0 = tc_idesc(128, 32 * NC);
+      const uint32_t idesc1 = tc_idesc(128, NC > 4 ? 32 * (NC - 4) : 32);
       const uint32_t stage0 = tc_smem_u32(stages);
       for (int st = 0; st < nst; ++st) {
         const int stage = st % kStages, dchunk = st / dstages, buf = dchunk & 1;
@@ -285,13 +274,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
           const uint32_t hi = stage0 + stage * stage_bytes + kg * kg_bytes, lo = hi + half_bytes;
           const uint32_t accf = (first && kg == 0) ? 0u : 1u;
           const uint32_t lbo = 512, sbo = kg_bytes >> 1;     // atom stride along MN, stride between 4-row K atoms
-          const uint64_t ah = tc_desc(hi, lbo, sbo, fl), al = tc_desc(lo, lbo, sbo, fl);
-          if (fl & 4) tc_mma_tf32_masked(d0, ah, ah, idesc0, accf); else if (!(fl & 8)) tc_mma_tf32(d0, ah, ah, idesc0, accf);
+          const uint64_t ah = tc_desc(hi, lbo, sbo), al = tc_desc(lo, lbo, sbo);
+          tc_mma_tf32(d0, ah, ah, idesc0, accf);
           tc_mma_tf32(d0, ah, al, idesc0, 1u);
           tc_mma_tf32(d0, al, ah, idesc0, 1u);
           if (NC > 4) {
-            const uint64_t a1h = tc_desc(hi + (NC - 4) * 512, lbo, sbo, fl), a1l = tc_desc(lo + (NC - 4) * 512, lbo, sbo, fl);
-            const uint64_t b1h = tc_desc(hi + 4 * 512, lbo, sbo, fl), b1l = tc_desc(lo + 4 * 512, lbo, sbo, fl);
+            const uint64_t a1h = tc_desc(hi + (NC - 4) * 512, lbo, sbo), a1l = tc_desc(lo + (NC - 4) * 512, lbo, sbo);
+            const uint64_t b1h = tc_desc(hi + 4 * 512, lbo, sbo), b1l = tc_desc(lo + 4 * 512, lbo, sbo);
             tc_mma_tf32(d1, a1h, b1h, idesc1, accf);
             tc_mma_tf32(d1, a1h, b1l, idesc1, 1u);
             tc_mma_tf32(d1, a1l, b1h, idesc1, 1u);
@@ -313,18 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
       const int buf = d & 1;
       tc_bar_wait(bar_tfull + 8 * buf, (d >> 1) & 1);
       tc_fence_after();
-      if (a.dbg_flags & 8) {
-        const uint32_t pat = __float_as_uint(1000.f + (float)i);
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n\ttcgen05.wait::st.sync.aligned;" ::"r"(tmem + ((uint32_t)(32 * warp) << 16) + buf * 256 + 3), "r"(pat) : "memory");
-      }
       const uint32_t t0 = tmem + ((uint32_t)(32 * warp) << 16) + buf * 256;
       for (int c = warp; c < NC; ++c) {             // columns 32 c .. 32 c + 31 hold entries j >= i only from chunk `warp` on
         tc_ld32(t0 + 32 * c, v);
-        if (a.dbg && d == 0 && c == 0 && warp == 0 && blockIdx.x == 0 && blockIdx.y == 0 && lane < 4) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) a.dbg[lane * 32 + e] = v[e];
-          if (lane == 0) { a.dbg[128] = __uint_as_float(tmem); a.dbg[129] = (float)total; a.dbg[130] = (float)nst; a.dbg[131] = (float)ndrain; }
-        }
         if (i < ncols) {
           // all loads, then all adds, then all stores: the entries are distinct, which the compiler cannot see
           const int jb = 32 * c;
@@ -379,10 +359,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_gram_tc(GramTcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid < 64) {
-    a.dbg[160 + tid] = __uint_as_float(reinterpret_cast<const uint32_t*>(stages)[tid]);             // hi, K-group 0, atom 0, rows 0..1
-    a.dbg[224 + tid] = __uint_as_float(reinterpret_cast<const uint32_t*>(stages + half_bytes)[tid]);  // lo
-  }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
