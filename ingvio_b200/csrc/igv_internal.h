@@ -77,6 +77,7 @@ struct IgvKnobs {
   int gram_cfg = 0;     // IGV_GRAM_CFG: 1 forces the super-block Gram kernel
   int factor_cfg = 0;   // IGV_FACTOR_CFG: 1 forces the column-by-column factorisation
   int tri_cfg = 0;      // IGV_TRI_CFG: 1 forces the thread-per-track triangulation kernel
+  int tri_minb = 4;     // IGV_TRI_MINB: resident blocks per SM the group kernel is compiled for (3: 168 regs .. 6: 80 regs)
   int graph = -1;       // IGV_GRAPH: 0 disables CUDA-graph replay of igv_frame_step
   int feat_const = 1;   // IGV_FEAT_CONST: 0 forbids the compile-time-sized instances of the per-track kernel
   int ekf_t_small = 0, ekf_t_big = 0;       // (0 = automatic) IGV_EKF_T_SMALL / IGV_EKF_T_BIG: threads per CTA of k_ekf_update (rows <= 32 / above)

@@ -521,7 +521,11 @@ void igv_launch_qr_compress(igv_batch* h, int F, int max_valid) {
   const int n = 6 * L.n_clones;
   // enough CTAs to cover the chip: split the rows of each sequence when the batch is small
   int split = 1;
-  const int target = 2 * 148;
+  // (wide stacks -- more than 72 columns: the super-block Gram kernel, 9 warps per CTA -- want 8 CTAs per SM, measured on
+  // c5 / B = 148: 9.2 / 7.6 / 7.1 / 6.9 ms with 2 / 4 / 6 / 8 parts; the narrow kernels are served by 2)
+  const bool gram_path = !(((h->knobs.qr_cfg > 0 && h->knobs.qr_cfg != 30) || h->compress == IGV_COMPRESS_HOUSEHOLDER) && !h->stack_f32) &&
+                         igv_gram_supported(n);
+  const int target = ((n + 1 > 72 && !h->feat_fused && gram_path) ? 8 : 2) * 148;
   if (h->B < target) split = min(h->qr_split_cap, max(1, min((target + h->B - 1) / h->B, (F + 7) / 8)));
   if (h->knobs.qr_split >= 1)   // test knob: force the row split
     split = min(h->qr_split_cap, min(h->knobs.qr_split, max(1, F)));

@@ -236,8 +236,8 @@ __device__ __forceinline__ double grp_sum(double v, unsigned gmask) {
 }
 
 // One group of GS lanes per track; lane gl owns views gl, gl + GS, ... (the first one cached in registers).
-template <int GS>
-__global__ void __launch_bounds__(128) k_triangulate_grp(TriArgs a) {
+template <int GS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_triangulate_grp(TriArgs a) {
   constexpr int GPB = 128 / GS;                      // groups per block
   const int gl = threadIdx.x % GS;
   const long gid = (long)blockIdx.x * GPB + threadIdx.x / GS;
@@ -440,8 +440,20 @@ void igv_launch_triangulate(igv_batch* h, int F, int obs_slots, const double* ob
   if (h->knobs.tri_cfg != 1) {
     // a group of lanes per track: 16 when every track fits (views <= 16: mono windows up to 16 clones), else 32
     const int max_views = (h->rho == 4 ? 2 : 1) * a.n_clones;
-    if (max_views <= 16) k_triangulate_grp<16><<<(unsigned)((n + 7) / 8), 128, 0, h->stream>>>(a);
-    else k_triangulate_grp<32><<<(unsigned)((n + 3) / 4), 128, 0, h->stream>>>(a);
+    // MINB resident blocks per SM: the natural register count (168) leaves 3; IGV_TRI_MINB caps the registers (A/B runs)
+    const unsigned g16 = (unsigned)((n + 7) / 8), g32 = (unsigned)((n + 3) / 4);
+    const int mb = h->knobs.tri_minb;
+    if (max_views <= 16) {
+      if (mb == 3) k_triangulate_grp<16, 3><<<g16, 128, 0, h->stream>>>(a);
+      else if (mb == 5) k_triangulate_grp<16, 5><<<g16, 128, 0, h->stream>>>(a);
+      else if (mb == 6) k_triangulate_grp<16, 6><<<g16, 128, 0, h->stream>>>(a);
+      else k_triangulate_grp<16, 4><<<g16, 128, 0, h->stream>>>(a);
+    } else {
+      if (mb == 3) k_triangulate_grp<32, 3><<<g32, 128, 0, h->stream>>>(a);
+      else if (mb == 5) k_triangulate_grp<32, 5><<<g32, 128, 0, h->stream>>>(a);
+      else if (mb == 6) k_triangulate_grp<32, 6><<<g32, 128, 0, h->stream>>>(a);
+      else k_triangulate_grp<32, 4><<<g32, 128, 0, h->stream>>>(a);
+    }
     h->launches++;
     return;
   }
