@@ -446,8 +446,10 @@ void igv_launch_gram_compress(igv_batch* h, int F, int max_valid, int split) {
     t.F = F; t.F_alloc = a.F_alloc; t.qmax = a.qmax; t.ldo = a.ldo; t.f_rows = a.f_rows; t.max_valid = max_valid;
     t.n1 = n + 1; t.NC = (n + 1 + 31) / 32;
     t.G = a.G; t.g_seq_stride = a.g_seq_stride; t.n1p = a.n1p; t.n_acc = a.n_acc; t.drain_stages = h->knobs.tc_drain;
-    // one CTA per SM (it owns the whole TMEM): as many parts as fill the chip in ONE wave
-    split = max(1, min(min(split, 148 / max(1, h->B)), F));
+    // one CTA per SM (it owns the whole TMEM): small batches get as many parts as fill the chip in ONE wave, batches that
+    // fill it anyway two (measured at c5: B = 148, 1 / 2 parts: 2.02 / 1.68 ms incl. the factorisation; B = 32, 4 / 10 parts:
+    // 0.93 / 0.95 ms)
+    split = max(1, min(min(split, h->B >= 148 ? 2 : 148 / max(1, h->B)), F));
     const size_t tsmem = igv_tc::gram_tc_smem_bytes(t.NC, (F + split - 1) / split);
     IGV_SMEM_OPTIN((igv_tc::k_gram_tc), 226 * 1024);
     dim3 tgrid(split, h->B);
