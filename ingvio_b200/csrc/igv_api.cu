@@ -273,6 +273,7 @@ igv_status igv_create(const igv_config* cfg, igv_batch** out) {
     h->knobs.gram_cfg = knob("IGV_GRAM_CFG", 0);
     h->knobs.factor_cfg = knob("IGV_FACTOR_CFG", 0);
     h->knobs.tri_cfg = knob("IGV_TRI_CFG", 0);
+    h->knobs.fuse_minw = knob("IGV_FUSE_MINW", 12);
     h->knobs.tri_minb = knob("IGV_TRI_MINB", 4);
     h->knobs.graph = knob("IGV_GRAPH", -1);
     h->knobs.feat_const = knob("IGV_FEAT_CONST", 1);

@@ -76,6 +76,7 @@ struct IgvKnobs {
   int qr_split = 0;     // IGV_QR_SPLIT: forces the row split
   int gram_cfg = 0;     // IGV_GRAM_CFG: 1 forces the super-block Gram kernel
   int factor_cfg = 0;   // IGV_FACTOR_CFG: 1 forces the column-by-column factorisation
+  int fuse_minw = 12;   // IGV_FUSE_MINW: fewest warps per CTA for which the fused per-track kernel is taken
   int tri_cfg = 0;      // IGV_TRI_CFG: 1 forces the thread-per-track triangulation kernel
   int tri_minb = 4;     // IGV_TRI_MINB: resident blocks per SM the group kernel is compiled for (3: 168 regs .. 6: 80 regs)
   int graph = -1;       // IGV_GRAPH: 0 disables CUDA-graph replay of igv_frame_step

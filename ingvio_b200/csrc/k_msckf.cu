@@ -944,7 +944,7 @@ void igv_launch_msckf_features(igv_batch* h, const IgvMsckfLaunch& l) {
       int W = 16;
       while (W > 1 && sizeof(double) * (fixed + (size_t)W * pw + extra) > 222 * 1024) --W;
       const bool room = (size_t)W * pw >= (size_t)(n + 1) * ((n + 1) | 1);   // G is assembled over the per-warp regions
-      if (W >= 12 && room) {
+      if (W >= h->knobs.fuse_minw && room) {
         W = (l.F + (l.F + W - 1) / W - 1) / ((l.F + W - 1) / W);   // fewest warps with the same number of rounds
         a.ssz = ssz; a.per_warp = pw;
         const size_t smem = sizeof(double) * (fixed + (size_t)W * pw + extra);
