@@ -704,6 +704,50 @@ def main():
             e1.record(ts)
             torch.cuda.synchronize(dev)
             gfe_ms = e0.elapsed_time(e1) / 5
+        # ---- (6) extra: SLAM landmarks in the state (mono): delayed initialisation and the per-frame update ----
+        lm_extra = None
+        if wl.feats >= 8 and not wl.stereo and not args.no_latency:
+            try:
+                from ingvio_b200.filter import BatchFilter
+                L = 8
+                glm = BatchFilter(B, wl.sw, max(wl.feats, 1), max(wl.sats, 1), stereo=False, device=local, stream=ts.cuda_stream,
+                                  noise=NOISE, T_cl2cr=(R_CL2CR, P_CL2CR), chi2_max_dof=160, max_landmarks=L)
+                ini = st.initial_state()
+                glm.init_state_and_cov(tile_to(ini["R"].reshape(-1, 9), B), tile_to(ini["p"], B), tile_to(ini["v"], B),
+                                       tile_to(ini["bg"], B), tile_to(ini["ba"], B), np.tile(R_C2I.reshape(1, 9), (B, 1)),
+                                       np.tile(P_C2I, (B, 1)), COV_DIAG21)
+                if wl.sats > 0:
+                    for gt, val, cov in GNSS_INIT:
+                        glm.add_gnss_variable(gt, val, cov)
+                for i in range(prefill):
+                    run_step(glm, to_dev(frames[i][0]), frames[i][1])
+                fr = to_dev(frames[prefill][0])      # the next frame: propagate + clone, then its tracks become landmarks
+                glm.propagate_imu(fr["gyro"], fr["accel"], fr["dt"])
+                glm.augment_sliding_window_pose()
+                ncl = glm.num_clones()
+                glm.synchronize()
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                for l in range(L):
+                    if l == 1:
+                        e0.record(ts)            # the first call grows the library's scratch arenas
+                    glm.landmark_init(fr["pf"][:, l].contiguous(), ncl - 1, fr["obs"][:, l, :ncl, :2].contiguous(),
+                                      fr["mask"][:, l, :ncl].contiguous(), VISUAL_NOISE)
+                e1.record(ts)
+                uv = fr["obs"][:, :L, ncl - 1, :2].contiguous()
+                seen = torch.ones((B, L), dtype=torch.uint8, device=dev)
+                for _ in range(5):
+                    glm.landmark_update(uv, seen, VISUAL_NOISE)
+                e2.record(ts)
+                torch.cuda.synchronize(dev)
+                lm_extra = {"landmarks_per_sequence": glm.num_landmarks(), "init_ms_per_landmark": e0.elapsed_time(e1) / (L - 1),
+                            "update_ms": e1.elapsed_time(e2) / 5,
+                            "landmark_updates_per_sec": B * glm.num_landmarks() / (e1.elapsed_time(e2) / 5 * 1e-3),
+                            "note": "igv_landmark_init (delayed initialisation, k = 3) of 8 tracks and igv_landmark_update of the "
+                                    "8 landmarks (2 x 24 rows each, chi^2 gate, one EKF update) on a second handle; outside the "
+                                    "metric (SURVEY 8f-3)"}
+                glm.close()
+            except Exception as e:   # the extra must never take the bench line down
+                lm_extra = {"error": repr(e)[:200]}
         flags = g.flags()
         tr = g.cov_trace()
         assert np.all(np.isfinite(tr)) and np.all(tr > 0), "filter diverged"
@@ -815,6 +859,8 @@ def main():
                                        "accepted_fraction": tri_ok,
                                        "note": "igv_triangulate on the same tracks; outside the metric (SURVEY 8f-1)"}
 
+    if lm_extra is not None:
+        line["landmark_extra"] = lm_extra
     if gfe_ms is not None:
         line["gnss_frontend_extra"] = {"ms_per_step": gfe_ms, "satellites_per_sec": B * wl.sats / (gfe_ms * 1e-3),
                                        "note": "igv_sat_states + igv_gnss_residuals on synthetic ephemerides; outside the "
