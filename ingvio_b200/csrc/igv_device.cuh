@@ -284,20 +284,29 @@ __device__ __forceinline__ void cta_gemm_mma_ex(int M, int N, int K, FA a, FB b,
         old[u][v][0] = cload(row, min(col, N - 1));
         old[u][v][1] = cload(row, min(col + 1, N - 1));
       }
-#pragma unroll 4
-    for (int k0 = kbegin(i0, j0); k0 < K; k0 += 4) {
-      const int k = k0 + fk;
-      const bool vk = k < K;
-      const int kk = vk ? k : K - 1;
-      double fa[TU], fb[TV];
+    // four k-steps per trip: all of their operand fetches are issued before the first DMMA, so operands that live in
+    // global memory (P, the compressed Jacobian) cost one round trip per 16 contraction indices instead of one per 4
+    for (int k0 = kbegin(i0, j0); k0 < K; k0 += 16) {
+      double fa[4][TU], fb[4][TV];
 #pragma unroll
-      for (int u = 0; u < TU; ++u) { const double x = a(ia[u], kk); fa[u] = vk ? x : 0.0; }
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int k = k0 + 4 * s4 + fk;
+        const bool vk = k < K;
+        const int kk = vk ? k : K - 1;
 #pragma unroll
-      for (int v = 0; v < TV; ++v) { const double x = b(kk, jb[v]); fb[v] = vk ? x : 0.0; }
+        for (int u = 0; u < TU; ++u) { const double x = a(ia[u], kk); fa[s4][u] = vk ? x : 0.0; }
 #pragma unroll
-      for (int u = 0; u < TU; ++u)
+        for (int v = 0; v < TV; ++v) { const double x = b(kk, jb[v]); fb[s4][v] = vk ? x : 0.0; }
+      }
 #pragma unroll
-        for (int v = 0; v < TV; ++v) mma884(acc[u][v][0], acc[u][v][1], fa[u], fb[v]);
+      for (int s4 = 0; s4 < 4; ++s4) {
+        if (k0 + 4 * s4 < K) {
+#pragma unroll
+          for (int u = 0; u < TU; ++u)
+#pragma unroll
+            for (int v = 0; v < TV; ++v) mma884(acc[u][v][0], acc[u][v][1], fa[s4][u], fb[s4][v]);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < TU; ++u)
