@@ -377,6 +377,7 @@ __device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int r
 // reports a kept pivot below kWeakPivot of its column's original diagonal, i.e. within two decades of the threshold
 // under which the column would have been treated as dependent (that row of the factor carries about five digits).
 constexpr double kWeakPivot = 1e-11;
+__device__ __forceinline__ double rsqrt_nobranch(double x);
 template <int NB>
 __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z, int ldz, int c0, int nc, int* s_ok,
                                             const double* dref = nullptr, double tol = 0.0) {
@@ -404,7 +405,7 @@ __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z
         const bool dead = dref && !(d > tol * dref[jb + k] && d > 1e-280);
         if (!dref && !(d > 0.0)) { ok = false; break; }
         if (dref && !dead && d < kWeakPivot * dref[jb + k]) weak = true;
-        const double inv = dead ? 0.0 : rsqrt(d);
+        const double inv = dead ? 0.0 : rsqrt_nobranch(d);   // d > 0 and normal here; no slow-path call on the serial chain
         const double l = arow[k] * inv;          // L[lane][k] (lane == k: sqrt(d))
         arow[k] = l;
         if (lane == k) s_rdiag[k] = inv;

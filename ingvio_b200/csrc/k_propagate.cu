@@ -192,9 +192,13 @@ __global__ void __launch_bounds__(128) k_propagate(PropArgs a) {
   const int nC = s_nC, nS = s_nS;
   const bool has_fs = s_has_fs != 0;
   double* W = sm;  // S x N row-major (rows >= nS are zero): W[r*N + j] = P[cidx[r], j]
-  for (int r = 0; r < S; ++r)
-    for (int j = tid; j < N; j += blockDim.x)
-      W[r * N + j] = (r < nS) ? Pb[j + (size_t)cidx[r] * ld] : 0.0;  // P symmetric: row == column (coalesced)
+  for (int j = tid; j < N; j += blockDim.x) {   // all S loads of a column in flight before the first store
+    double col[S];
+#pragma unroll
+    for (int r = 0; r < S; ++r) col[r] = (r < nS) ? Pb[j + (size_t)cidx[r] * ld] : 0.0;  // P symmetric: row == column (coalesced)
+#pragma unroll
+    for (int r = 0; r < S; ++r) W[r * N + j] = col[r];
+  }
   __syncthreads();
   // Per IMU sample the reference updates P11 <- sym(T P11 T^T + Q) and P21 <- P21 T^T (StateManager.cpp:51-118).
   // The strip x strip block Bk = P11 follows that recursion step by step (including the per-step symmetrisation);
