@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) k_gram_factor(FactorArgs a) {
         for (int k = i + lane; k < n1; k += 32) U[oi + k] = fma(-lij, U[oj + k], U[oi + k]);
       }
     }
-    if (tid == 0) dsc[j] = live ? rsqrt(d) : 0.0;
+    if (tid == 0) dsc[j] = live ? rsqrt_nobranch(d) : 0.0;
     __syncthreads();
   }
   double* out = a.out + (size_t)b * a.out_stride;

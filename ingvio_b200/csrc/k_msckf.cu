@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(FUSE ? 512 : (RHO == 4 ? IGV_STEREO_THREADS : 
             if (k >= nb) break;
             const double d = __shfl_sync(0xffffffffu, arow[k], k);
             if (!(d > 0.0)) { pd = false; break; }
-            const double inv = rsqrt(d);
+            const double inv = rsqrt_nobranch(d);   // d > 0 checked above
             const double l = arow[k] * inv;          // L[lane][k] (lane == k: sqrt(d))
             arow[k] = l;
             if (lane == k) rd = inv;
