@@ -377,6 +377,9 @@ __device__ inline void cta_trsm_lower(const double* L, int ldl, double* Z, int r
 // reports a kept pivot below kWeakPivot of its column's original diagonal, i.e. within two decades of the threshold
 // under which the column would have been treated as dependent (that row of the factor carries about five digits).
 constexpr double kWeakPivot = 1e-11;
+#ifndef IGV_EKF_NB
+#define IGV_EKF_NB 8    // panel width of the blocked Cholesky (measured at c2: 16 is slower, EKF 0.50 -> 0.63 ms, Gram factor 0.137 -> 0.211 ms)
+#endif
 __device__ __forceinline__ double rsqrt_nobranch(double x);
 template <int NB>
 __device__ inline bool cta_chol_solve_fused(double* S, int r, int lds, double* Z, int ldz, int c0, int nc, int* s_ok,

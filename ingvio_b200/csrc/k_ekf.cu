@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 384 ? 2 : (THREADS >= 256 
   __syncthreads();
   // (3) S = L L^T
   // (3)+(4)+(5) S = L L^T fused with Y = L^-1 Z (all N columns) and w = L^-1 res (column N)
-  const bool ok = a.gamma_only ? cta_chol_solve_fused<8>(S, r, lds, Z, ldz, N, 1, &s_ok)
-                               : cta_chol_solve_fused<8>(S, r, lds, Z, ldz, 0, N + 1, &s_ok);
+  const bool ok = a.gamma_only ? cta_chol_solve_fused<IGV_EKF_NB>(S, r, lds, Z, ldz, N, 1, &s_ok)
+                               : cta_chol_solve_fused<IGV_EKF_NB>(S, r, lds, Z, ldz, 0, N + 1, &s_ok);
   if (!ok) {
     if (tid == 0) {
       atomicOr(&a.flags[b], IGV_FLAG_CHOL_FAIL);

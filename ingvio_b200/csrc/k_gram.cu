@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256) k_gram_factor_blocked(FactorArgs a) {
       if (i == j) dref[j] = v;
     }
   __syncthreads();
-  cta_chol_solve_fused<8>(S, n, lds, Zr, lds, 0, 1, &s_ok, dref, a.tol);
+  cta_chol_solve_fused<IGV_EKF_NB>(S, n, lds, Zr, lds, 0, 1, &s_ok, dref, a.tol);
   if (tid == 0 && (s_ok & 2)) atomicOr(&a.flags[b], IGV_FLAG_WEAK_PIVOT);
   double* out = a.out + (size_t)b * a.out_stride;
   for (int i = warp; i < n; i += nw)
