@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(256) k_gram_factor(FactorArgs a) {
 // Blocked version for n <= 160: G (lower, column-major) and the right-hand side sit in shared memory and the
 // factorisation is cta_chol_solve_fused<4> in its semi-definite mode -- 4-column panels, the trailing update on DMMA,
 // the right-hand side riding along -- instead of one barrier and one rank-1 update per column.
+template <int NB>
 __global__ void __launch_bounds__(256) k_gram_factor_blocked(FactorArgs a) {
   extern __shared__ double sm[];
   __shared__ int s_ok;
@@ -393,7 +394,9 @@ __global__ void __launch_bounds__(256) k_gram_factor_blocked(FactorArgs a) {
       if (i == j) dref[j] = v;
     }
   __syncthreads();
-  cta_chol_solve_fused<4>(S, n, lds, Zr, lds, 0, 1, &s_ok, dref, a.tol);   // 4-column panels: one right-hand side only, the serial diagonal block dominates (measured 0.137 -> 0.117 ms at c2)
+  // panel width: with ONE right-hand side the serial diagonal block dominates; measured at c2: 4-column panels 0.137 -> 0.117 ms
+  // when the batch fills the chip, but 71 -> 81 us for a single sequence, where 8 stays
+  cta_chol_solve_fused<NB>(S, n, lds, Zr, lds, 0, 1, &s_ok, dref, a.tol);
   if (tid == 0 && (s_ok & 2)) atomicOr(&a.flags[b], IGV_FLAG_WEAK_PIVOT);
   double* out = a.out + (size_t)b * a.out_stride;
   for (int i = warp; i < n; i += nw)
@@ -490,12 +493,14 @@ void igv_launch_gram_factor(igv_batch* h, int nparts) {
   // above start dropping observable directions; the knob stays for A/B runs)
   f.tol = h->last_gram_tc ? h->knobs.tc_pivot_tol : 1e-13; f.flags = h->flags;
   IGV_SMEM_OPTIN((k_gram_factor), 220 * 1024);
-  IGV_SMEM_OPTIN((k_gram_factor_blocked), 220 * 1024);
+  IGV_SMEM_OPTIN((k_gram_factor_blocked<4>), 220 * 1024);
+  IGV_SMEM_OPTIN((k_gram_factor_blocked<8>), 220 * 1024);
   const int factor_cfg = h->knobs.factor_cfg;     // test knob: 1 forces the column-by-column kernel
   const int lds = n + ((4 - n % 8) + 8) % 8;
   const size_t bsmem = sizeof(double) * ((size_t)n * lds + lds + n);
   if (bsmem <= 200 * 1024 && factor_cfg != 1) {
-    k_gram_factor_blocked<<<h->B, 256, bsmem, h->stream>>>(f);
+    if (h->B >= 296) k_gram_factor_blocked<4><<<h->B, 256, bsmem, h->stream>>>(f);
+    else k_gram_factor_blocked<8><<<h->B, 256, bsmem, h->stream>>>(f);
   } else {
     const size_t fsmem = sizeof(double) * ((size_t)n * (n + 3) / 2 + 2 * n);
     k_gram_factor<<<h->B, 256, fsmem, h->stream>>>(f);
