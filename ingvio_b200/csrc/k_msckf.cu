@@ -746,16 +746,33 @@ __global__ void __launch_bounds__(FUSE ? 512 : (RHO == 4 ? IGV_STEREO_THREADS : 
           double* orow = out + (size_t)(i - 3) * a.ldo + j0 + lane;
 #pragma unroll
           for (int gq = 0; gq < 3; ++gq) {
+            // (the column's own entries, which live in RHO of the M rows, are added by the short pass below: a select chain
+            // over RHO candidates in this loop was 12 % of the stereo kernel's instructions)
             double v = -(s0 * z[gq][0] + s1 * z[gq][1] + s2 * z[gq][2]);
-            const int t = i - own_lo[gq];
-#pragma unroll
-            for (int tt = 0; tt < RHO; ++tt) if (tt == t) v += ownv[gq][tt];
             if (acomp[gq] >= 0 && not_anchor_row) v -= sB[i * 3 + acomp[gq]];
             if (isres[gq]) v = qri;
             if (live[gq]) {
               if (a.hs_f32)   // float elements with the SAME element strides, counted from the sequence's base
                 reinterpret_cast<float*>(a.Hs + (size_t)b * a.hs_seq_stride)[((size_t)f * a.qmax + (i - 3)) * a.ldo + j0 + lane + 32 * gq] = (float)v;
               else orow[32 * gq] = v;
+            }
+          }
+        }
+        // the RHO rows of the observation at the column's own clone: the same value plus the column's own entry (same order
+        // of operations as if it had been added in the loop above)
+#pragma unroll
+        for (int gq = 0; gq < 3; ++gq) {
+          if (!live[gq] || isres[gq]) continue;
+#pragma unroll
+          for (int tt = 0; tt < RHO; ++tt) {
+            const int i = own_lo[gq] + tt;
+            if (i >= 3 && i < M) {
+              double v = -(sV[i * 3] * z[gq][0] + sV[i * 3 + 1] * z[gq][1] + sV[i * 3 + 2] * z[gq][2]);
+              v += ownv[gq][tt];
+              if (acomp[gq] >= 0 && (i / RHO != kanc)) v -= sB[i * 3 + acomp[gq]];
+              const size_t at = ((size_t)f * a.qmax + (i - 3)) * a.ldo + j0 + lane + 32 * gq;
+              if (a.hs_f32) reinterpret_cast<float*>(a.Hs + (size_t)b * a.hs_seq_stride)[at] = (float)v;
+              else (a.Hs + (size_t)b * a.hs_seq_stride)[at] = v;
             }
           }
         }
