@@ -121,7 +121,7 @@ igv_status igv_set_compression(igv_batch* h, int kind);   /* IGV_COMPRESS_* (def
  *                       terms and hi^T hi + hi^T lo + lo^T hi is accumulated in FP32 over 128 rows at a time, the
  *                       128-row sums in FP64; factorisation and EKF update stay FP64. Used for stacks of 129..192
  *                       columns (windows of 22..31 clones); narrower and wider ones take IGV_PREC_FP32_STACK's kernel.
- *                       A throughput / accuracy trade-off for wide windows (c5: 1.71 x the FP64 path), NOT a parity mode:
+ *                       A throughput / accuracy trade-off for wide windows (c5: 1.74 x the FP64 path), NOT a parity mode:
  *                       the unit's truncating FP32 accumulation leaves ~1.5e-6 relative in the Gram matrix, which at
  *                       c5 moves the posterior by up to 2 cm / 5e-4 relative in P within 40 frames
  *                       (tests/test_gpu_precision.py, profiles/r02_tcgen05_eval.md). */
